@@ -1,0 +1,225 @@
+"""ctypes binding of libtiresias_gpu.so (include/tiresias_gpu.h) for tests/ and bench.py.
+
+No compute happens here: every call goes through the C ABI.  If the library is missing or there
+is no sm_100 GPU the calls fail loudly -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import uuid as _uuid
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtiresias_gpu.so")
+NULL_V = -(2**31)
+
+OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_NOTFOUND = 0, -1, -2, -3, -4, -5
+
+
+class TirError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tiresias_gpu error {code}: {msg}")
+        self.code = code
+
+
+class Cfg(C.Structure):
+    _fields_ = [("device", C.c_int), ("win", C.c_int), ("hop", C.c_int), ("n_filters", C.c_int),
+                ("samplerate", C.c_int), ("stream", C.c_void_p)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("uuid", C.c_uint8 * 16), ("match_count", C.c_int32), ("frame_count", C.c_int32)]
+
+
+HIT_DTYPE = np.dtype([("uuid", np.uint8, 16), ("match_count", np.int32), ("frame_count", np.int32)])
+assert HIT_DTYPE.itemsize == C.sizeof(Hit) == 24
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (raises if it has not been built: run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TirError(ERR_STATE, f"{LIB_PATH} is missing: build it with `python -m asterisk_tiresias_b200.build`")
+        L = C.CDLL(LIB_PATH)
+        vp, u64p = C.c_void_p, C.c_void_p
+        L.tir_abi_version.restype = C.c_int
+        L.tir_cfg_default.argtypes = [C.POINTER(Cfg)]
+        L.tir_open.argtypes = [C.POINTER(Cfg), C.POINTER(vp)]
+        L.tir_close.argtypes = [vp]
+        L.tir_last_error.restype = C.c_char_p
+        L.tir_last_error.argtypes = [vp]
+        L.tir_n_frames.restype = C.c_uint64
+        L.tir_n_frames.argtypes = [C.c_uint64, C.c_int]
+        L.tir_extract.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
+        L.tir_extract_dev.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
+        L.tir_get_tables.argtypes = [vp, vp, vp, vp]
+        L.tir_launch_count.restype = C.c_uint64
+        L.tir_launch_count.argtypes = [vp]
+        if hasattr(L, "tir_db_load"):
+            L.tir_db_load.argtypes = [vp, C.c_uint32, vp, u64p, vp, vp]
+            L.tir_db_add.argtypes = [vp, vp, vp, vp, C.c_uint32]
+            L.tir_db_remove.argtypes = [vp, vp]
+            L.tir_db_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+            L.tir_match.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_match_dev.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_merge_hits_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+            L.tir_shard_of.restype = C.c_uint32
+            L.tir_shard_of.argtypes = [vp, C.c_uint32]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def uuid_to_bytes(text: str) -> np.ndarray:
+    return np.frombuffer(_uuid.UUID(text).bytes, dtype=np.uint8).copy()
+
+
+def bytes_to_uuid(b) -> str:
+    return str(_uuid.UUID(bytes=bytes(bytearray(np.asarray(b, dtype=np.uint8).tolist()))))
+
+
+class Context:
+    """tir_ctx wrapper.  `stream` is a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, win=512, hop=256, n_filters=40, samplerate=8000, stream=None):
+        L = lib()
+        cfg = Cfg()
+        L.tir_cfg_default(C.byref(cfg))
+        cfg.device, cfg.win, cfg.hop, cfg.n_filters, cfg.samplerate = device, win, hop, n_filters, samplerate
+        cfg.stream = stream
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = L.tir_open(C.byref(cfg), C.byref(self._h))
+        if rc != OK:
+            msg = L.tir_last_error(self._h).decode() if self._h else "tir_open failed"
+            if self._h:
+                L.tir_close(self._h)
+            self._h = None
+            raise TirError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.tir_close(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise TirError(rc, lib().tir_last_error(self._h).decode())
+
+    @property
+    def hop(self):
+        return self.cfg.hop
+
+    @property
+    def launches(self):
+        return int(lib().tir_launch_count(self._h))
+
+    def tables(self):
+        win, nf = self.cfg.win, self.cfg.n_filters
+        w = np.empty(win, np.float32)
+        fb = np.empty((nf, win // 2 + 1), np.float32)
+        d = np.empty((2, nf), np.float32)
+        self._chk(lib().tir_get_tables(self._h, _p(w), _p(fb), _p(d)))
+        return w, fb, d
+
+    # ---- extraction -------------------------------------------------------------------------
+    def n_frames(self, clip_off):
+        lens = np.diff(np.asarray(clip_off, dtype=np.uint64).astype(np.int64))
+        return int(((lens + self.hop - 1) // self.hop).sum())
+
+    def extract(self, pcm, clip_off=None):
+        """Host buffers in, host buffers out: coef [F,2] f32, vq [F,2] i32."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if clip_off is None:
+            clip_off = np.array([0, pcm.size], np.uint64)
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        F = self.n_frames(clip_off)
+        coef = np.empty((F, 2), np.float32)
+        vq = np.empty((F, 2), np.int32)
+        nf = C.c_uint64()
+        self._chk(lib().tir_extract(self._h, _p(pcm), _p(clip_off), clip_off.size - 1, _p(coef), _p(vq), C.byref(nf)))
+        assert nf.value == F
+        return coef, vq
+
+    def extract_dev(self, d_pcm_ptr, clip_off, d_coef_ptr, d_vq_ptr):
+        """Device pointers (ints); asynchronous on the context's stream.  Returns frame count."""
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        nf = C.c_uint64()
+        self._chk(lib().tir_extract_dev(self._h, C.c_void_p(d_pcm_ptr), _p(clip_off), clip_off.size - 1,
+                                        C.c_void_p(d_coef_ptr), C.c_void_p(d_vq_ptr), C.byref(nf)))
+        return int(nf.value)
+
+    # ---- device DB --------------------------------------------------------------------------
+    def db_load(self, uuids, row_off, v1, v2):
+        """uuids: [n,16] uint8; row_off [n+1] uint64; v1/v2 int32 micro-units (NULL_V = NULL)."""
+        uuids = np.ascontiguousarray(uuids, dtype=np.uint8).reshape(-1, 16)
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+        v1 = np.ascontiguousarray(v1, dtype=np.int32)
+        v2 = np.ascontiguousarray(v2, dtype=np.int32)
+        assert row_off.size == uuids.shape[0] + 1 and v1.size == v2.size == int(row_off[-1])
+        self._chk(lib().tir_db_load(self._h, uuids.shape[0], _p(uuids), _p(row_off), _p(v1), _p(v2)))
+
+    def db_add(self, uuid16, v1, v2):
+        u = np.ascontiguousarray(uuid16, dtype=np.uint8)
+        v1 = np.ascontiguousarray(v1, dtype=np.int32)
+        v2 = np.ascontiguousarray(v2, dtype=np.int32)
+        self._chk(lib().tir_db_add(self._h, _p(u), _p(v1), _p(v2), v1.size))
+
+    def db_remove(self, uuid16):
+        u = np.ascontiguousarray(uuid16, dtype=np.uint8)
+        self._chk(lib().tir_db_remove(self._h, _p(u)))
+
+    def db_stats(self):
+        a, r = C.c_uint64(), C.c_uint64()
+        self._chk(lib().tir_db_stats(self._h, C.byref(a), C.byref(r)))
+        return int(a.value), int(r.value)
+
+    # ---- match ------------------------------------------------------------------------------
+    def match(self, y, frame_off=None, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1, 2)
+        if frame_off is None:
+            frame_off = np.array([0, y.shape[0]], np.uint64)
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        nq = frame_off.size - 1
+        hits = np.zeros(nq, HIT_DTYPE)
+        self._chk(lib().tir_match(self._h, _p(y), _p(frame_off), nq, coefs, float(tolerance), int(freq_ignore_low),
+                                  int(freq_ignore_high), _p(hits)))
+        return hits
+
+    def match_dev(self, d_coef_ptr, frame_off, d_hits_ptr, coefs=1, tolerance=0.001, freq_ignore_low=-1,
+                  freq_ignore_high=-1):
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        self._chk(lib().tir_match_dev(self._h, C.c_void_p(d_coef_ptr), _p(frame_off), frame_off.size - 1, coefs,
+                                      float(tolerance), int(freq_ignore_low), int(freq_ignore_high),
+                                      C.c_void_p(d_hits_ptr)))
+
+    def search(self, pcm, clip_off=None, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if clip_off is None:
+            clip_off = np.array([0, pcm.size], np.uint64)
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        nq = clip_off.size - 1
+        hits = np.zeros(nq, HIT_DTYPE)
+        self._chk(lib().tir_search(self._h, _p(pcm), _p(clip_off), nq, coefs, float(tolerance), int(freq_ignore_low),
+                                   int(freq_ignore_high), _p(hits)))
+        return hits
+
+    def merge_hits_dev(self, d_gathered_ptr, n_shards, n_queries, d_out_ptr):
+        self._chk(lib().tir_merge_hits_dev(self._h, C.c_void_p(d_gathered_ptr), n_shards, n_queries,
+                                           C.c_void_p(d_out_ptr)))
+
+
+def shard_of(uuid16, n_shards: int) -> int:
+    u = np.ascontiguousarray(uuid16, dtype=np.uint8)
+    return int(lib().tir_shard_of(_p(u), n_shards))

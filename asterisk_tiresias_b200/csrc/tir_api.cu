@@ -1,0 +1,182 @@
+// tir_api.cu -- C ABI entry points of libtiresias_gpu.so (context, extraction); the device DB and
+// the match entry points live in tir_match.cu.  See include/tiresias_gpu.h.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+
+#include "tir_internal.h"
+
+int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int tir_reserve(tir_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return TIR_OK;
+  if (b.p) {
+    TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TIR_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr, b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, cap);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return tir_fail(ctx, e == cudaErrorMemoryAllocation ? TIR_ERR_NOMEM : TIR_ERR_CUDA, "cudaMalloc(%zu): %s", cap,
+                    cudaGetErrorString(e));
+  }
+  b.cap = cap;
+  return TIR_OK;
+}
+
+int tir_reserve_host(tir_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return TIR_OK;
+  if (b.p) {
+    TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TIR_CUDA(ctx, cudaFreeHost(b.p));
+    b.p = nullptr, b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMallocHost(&b.p, cap);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return tir_fail(ctx, TIR_ERR_NOMEM, "cudaMallocHost(%zu): %s", cap, cudaGetErrorString(e));
+  }
+  b.cap = cap;
+  return TIR_OK;
+}
+
+static void free_dev(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr, b.cap = 0;
+}
+
+extern "C" {
+
+int tir_abi_version(void) { return TIR_ABI_VERSION; }
+
+void tir_cfg_default(tir_cfg *cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0;
+  cfg->win = 512, cfg->hop = 256, cfg->n_filters = 40, cfg->samplerate = 8000;
+  cfg->stream = nullptr;
+}
+
+uint64_t tir_n_frames(uint64_t n_samples, int hop) {
+  if (hop <= 0) return 0;
+  return (n_samples + (uint64_t)hop - 1) / (uint64_t)hop;
+}
+
+static int upload(tir_ctx *ctx, float2 **dst, const std::vector<float2> &src) {
+  TIR_CUDA(ctx, cudaMalloc((void **)dst, src.size() * sizeof(float2)));
+  TIR_CUDA(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  return TIR_OK;
+}
+
+int tir_open(const tir_cfg *cfg, tir_ctx **out) {
+  if (!cfg || !out) return TIR_ERR_ARG;
+  *out = nullptr;
+  tir_ctx *ctx = new (std::nothrow) tir_ctx();
+  if (!ctx) return TIR_ERR_NOMEM;
+  ctx->cfg = *cfg;
+  *out = ctx; // handed back even on failure so that tir_last_error() can be read; tir_close() frees it
+  if (!tir_build_tables(cfg->win, cfg->hop, cfg->n_filters, TIR_N_COEFS, cfg->samplerate, ctx->tab))
+    return tir_fail(ctx, TIR_ERR_ARG, "unsupported plan win=%d hop=%d filters=%d rate=%d", cfg->win, cfg->hop,
+                    cfg->n_filters, cfg->samplerate);
+  int ndev = 0;
+  TIR_CUDA(ctx, cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) return tir_fail(ctx, TIR_ERR_CUDA, "no CUDA device: libtiresias_gpu has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return tir_fail(ctx, TIR_ERR_ARG, "device %d of %d", cfg->device, ndev);
+  TIR_CUDA(ctx, cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  TIR_CUDA(ctx, cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return tir_fail(ctx, TIR_ERR_CUDA, "device %s is sm_%d%d; this library carries sm_100a code only", prop.name,
+                    prop.major, prop.minor);
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cfg->stream) {
+    ctx->stream = (cudaStream_t)cfg->stream;
+  } else {
+    TIR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  int rc;
+  if ((rc = upload(ctx, &ctx->d_win2, ctx->tab.win2))) return rc;
+  if ((rc = upload(ctx, &ctx->d_tw_pass, ctx->tab.tw_pass))) return rc;
+  if ((rc = upload(ctx, &ctx->d_tw_unt, ctx->tab.tw_unt))) return rc;
+  if ((rc = upload(ctx, &ctx->d_tw32, ctx->tab.tw32))) return rc;
+  return TIR_OK;
+}
+
+void tir_close(tir_ctx *ctx) {
+  if (!ctx) return;
+  if (ctx->num_sms) {
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  }
+  if (ctx->db) tir_db_destroy(ctx->db);
+  cudaFree(ctx->d_win2), cudaFree(ctx->d_tw_pass), cudaFree(ctx->d_tw_unt), cudaFree(ctx->d_tw32);
+  free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
+  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y);
+  if (ctx->h_meta.p) cudaFreeHost(ctx->h_meta.p);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *tir_last_error(tir_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+uint64_t tir_launch_count(tir_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tir_get_tables(tir_ctx *ctx, float *window, float *filters, float *dct) {
+  if (!ctx) return TIR_ERR_ARG;
+  if (window) std::memcpy(window, ctx->tab.window.data(), ctx->tab.window.size() * sizeof(float));
+  if (filters) std::memcpy(filters, ctx->tab.filters.data(), ctx->tab.filters.size() * sizeof(float));
+  if (dct) std::memcpy(dct, ctx->tab.dct.data(), ctx->tab.dct.size() * sizeof(float));
+  return TIR_OK;
+}
+
+int tir_extract_dev(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips, float *d_coef,
+                    int32_t *d_vq, uint64_t *n_frames) {
+  if (!ctx || !clip_off || (!d_pcm && n_clips && clip_off[n_clips] > clip_off[0])) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return tir_extract_launch(ctx, d_pcm, clip_off[n_clips], clip_off, n_clips, d_coef, d_vq, n_frames);
+}
+
+int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, float *coef, int32_t *vq,
+                uint64_t *n_frames) {
+  if (!ctx || !clip_off || (!pcm && n_clips && clip_off[n_clips] > clip_off[0])) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  const uint64_t base = clip_off[0], total = clip_off[n_clips] - base;
+  uint64_t F = 0;
+  for (uint32_t c = 0; c < n_clips; c++) F += tir_n_frames(clip_off[c + 1] - clip_off[c], ctx->cfg.hop);
+  if (n_frames) *n_frames = F;
+  if (F == 0) return TIR_OK;
+  int rc;
+  if ((rc = tir_reserve(ctx, ctx->d_pcm, total * sizeof(int16_t) + 16))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_coef, F * TIR_N_COEFS * sizeof(float)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_vq, F * TIR_N_COEFS * sizeof(int32_t)))) return rc;
+  TIR_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcm.p, pcm + base, total * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  // offsets relative to the staged copy
+  std::vector<uint64_t> rel((size_t)n_clips + 1);
+  for (uint32_t c = 0; c <= n_clips; c++) rel[c] = clip_off[c] - base;
+  if ((rc = tir_extract_launch(ctx, (const int16_t *)ctx->d_pcm.p, total, rel.data(), n_clips, (float *)ctx->d_coef.p,
+                               (int32_t *)ctx->d_vq.p, nullptr)))
+    return rc;
+  if (coef)
+    TIR_CUDA(ctx, cudaMemcpyAsync(coef, ctx->d_coef.p, F * TIR_N_COEFS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (vq)
+    TIR_CUDA(ctx, cudaMemcpyAsync(vq, ctx->d_vq.p, F * TIR_N_COEFS * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TIR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,57 @@
+// tir_internal.h -- context object shared by the translation units of libtiresias_gpu.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tiresias_gpu.h"
+#include "tir_tables.h"
+
+struct TirDb; // tir_match.cu
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct tir_ctx {
+  tir_cfg cfg{};
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::mutex mu;
+  std::string err;
+  uint64_t launches = 0;
+  TirHostTables tab;
+  // device copies of the kernel-layout tables
+  float2 *d_win2 = nullptr, *d_tw_pass = nullptr, *d_tw_unt = nullptr, *d_tw32 = nullptr;
+  // reusable device scratch
+  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y;
+  // pinned staging for small metadata
+  DevBuf h_meta;
+  TirDb *db = nullptr;
+};
+
+int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...);
+#define TIR_CUDA(ctx, expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return tir_fail((ctx), TIR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                      __FILE__, __LINE__);                                                      \
+  } while (0)
+
+int tir_reserve(tir_ctx *ctx, DevBuf &b, size_t bytes);      // device scratch, grows only
+int tir_reserve_host(tir_ctx *ctx, DevBuf &b, size_t bytes); // pinned host scratch
+
+// tir_extract.cu
+int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
+                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames);
+size_t tir_extract_smem_bytes(int win);
+
+// tir_match.cu
+void tir_db_destroy(TirDb *db);

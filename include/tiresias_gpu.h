@@ -1,0 +1,155 @@
+/*
+ * tiresias_gpu.h -- C ABI of libtiresias_gpu.so, the B200 (sm_100a) implementation of the
+ * fingerprint hot path of asterisk-tiresias.
+ *
+ * The reference has no FFI: its hot path is two in-process seams inside src/fp_handler.c,
+ *   (A) create_audio_fingerprints(filename, uuid)            src/fp_handler.c:577-671
+ *       libaubio source -> pvoc -> mfcc per hop, then 10*log10(fabs(c)), later "%f"
+ *       (src/db_ctx_handler.c:480) on the way into SQLite;
+ *   (B) the per-frame SQL probe + tally in fp_search_fingerprint_info()
+ *       src/fp_handler.c:285-374, over the rows written by
+ *       create_audio_fingerprint_info() src/fp_handler.c:538-575 and removed by
+ *       fp_delete_audio_list_info() src/fp_handler.c:147.
+ * Each entry point below names the seam it replaces.  Plain C types only; all buffers are owned
+ * by the caller; every function returns TIR_OK (0) or a negative tir_status and never aborts.
+ * A CUDA failure is reported as TIR_ERR_CUDA -- there is NO CPU fallback.  INTEGRATION.md shows
+ * the fp_handler.c patch that binds these.
+ *
+ * Thread safety: a tir_ctx may be used from any number of host threads (the dialplan runs
+ * fp_search_fingerprint_info on one PBX thread per channel); calls are serialised per context.
+ *
+ * Units: "micro-units" are the integer the reference's "%f" text denotes, v = y * 1e6 rounded the
+ * way printf rounds; TIR_NULL_V marks a NULL column (non-finite y never becomes a JSON real).
+ */
+#ifndef TIRESIAS_GPU_H_
+#define TIRESIAS_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIR_ABI_VERSION 1
+#define TIR_NULL_V INT32_MIN
+#define TIR_N_COEFS 2 /* DEF_AUBIO_COEFS, src/fp_handler.c:39 */
+
+typedef enum {
+  TIR_OK = 0,
+  TIR_ERR_ARG = -1,     /* bad argument (the reference returns NULL/false + LOG_WARNING) */
+  TIR_ERR_CUDA = -2,    /* CUDA runtime error, see tir_last_error() */
+  TIR_ERR_NOMEM = -3,
+  TIR_ERR_STATE = -4,   /* e.g. match before any tir_db_* call */
+  TIR_ERR_NOTFOUND = -5 /* tir_db_remove of an unknown uuid */
+} tir_status;
+
+typedef struct tir_ctx tir_ctx;
+
+/* The DSP constants are compile-time #defines in the reference (src/fp_handler.c:33-39):
+ * win 512 / hop 256 (or the commented 1024 / 512), 40 filters, 2 coefficients; the sample rate
+ * is the file's own (DEF_AUBIO_SAMPLERATE 0). */
+typedef struct {
+  int device;       /* CUDA device ordinal */
+  int win;          /* DEF_AUBIO_BUFSIZE : 512 (or 1024)        */
+  int hop;          /* DEF_AUBIO_HOPSIZE : win / 2              */
+  int n_filters;    /* DEF_AUBIO_FILTER  : 40                   */
+  int samplerate;   /* rate the mel filterbank is built for     */
+  void *stream;     /* cudaStream_t to run on, NULL = own stream */
+} tir_cfg;
+
+void tir_cfg_default(tir_cfg *cfg); /* 512 / 256 / 40 / 8000 Hz, device 0 */
+
+int tir_open(const tir_cfg *cfg, tir_ctx **out); /* fp_init() device side, src/fp_handler.c:68 */
+void tir_close(tir_ctx *ctx);                    /* fp_term(),             src/fp_handler.c:92 */
+const char *tir_last_error(tir_ctx *ctx);        /* text of the last failure on this context    */
+int tir_abi_version(void);
+
+/* ---- seam (A): extraction ------------------------------------------------------------------ */
+
+/* frames aubio_source_do delivers for n_samples (loop src/fp_handler.c:632-636): ceil(n/hop) */
+uint64_t tir_n_frames(uint64_t n_samples, int hop);
+
+/*
+ * create_audio_fingerprints() for a batch of mono PCM16 clips held in HOST memory.
+ *   pcm       all clips back to back; clip c = pcm[clip_off[c] .. clip_off[c+1])
+ *   coef      [n_frames_total][2] float   mfcc_out->data[i]                      (may be NULL)
+ *   vq        [n_frames_total][2] int32   10*log10(fabs(c)) as stored through "%f", micro-units
+ *   n_frames  out: frames written (sum over clips of ceil(len/hop)), frames in clip order
+ * Copies pcm host->device, runs the fused kernel, copies the results back (all on ctx's stream)
+ * and returns when they are in the caller's buffers.
+ */
+int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, float *coef,
+                int32_t *vq, uint64_t *n_frames);
+
+/* Same with DEVICE buffers (d_pcm, d_coef, d_vq); clip_off stays a host array.  Asynchronous on
+ * ctx's stream. */
+int tir_extract_dev(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,
+                    float *d_coef, int32_t *d_vq, uint64_t *n_frames);
+
+/* the plan's aubio-layout tables, for table-level parity tests (host copies) */
+int tir_get_tables(tir_ctx *ctx, float *window /*[win]*/, float *filters /*[n_filters][win/2+1]*/,
+                   float *dct /*[2][n_filters]*/);
+
+/* ---- seam (B): the device-resident mirror of table audio_fingerprint ------------------------- */
+
+/* Bulk load (fp_init's restore of the backup DB, src/fp_handler.c:82-88): audio a has uuid
+ * uuid[a] (16 raw bytes; canonical lower-case text order == byte order) and rows
+ * v1/v2[row_off[a] .. row_off[a+1]) in frame_idx order.  Replaces the current contents. */
+int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off,
+                const int32_t *v1, const int32_t *v2);
+/* create_audio_fingerprint_info(): the rows of one new audio, src/fp_handler.c:538-575 */
+int tir_db_add(tir_ctx *ctx, const uint8_t uuid[16], const int32_t *v1, const int32_t *v2, uint32_t n_rows);
+/* delete from audio_fingerprint where audio_uuid=..., src/fp_handler.c:147 */
+int tir_db_remove(tir_ctx *ctx, const uint8_t uuid[16]);
+int tir_db_stats(tir_ctx *ctx, uint64_t *n_audio, uint64_t *n_rows);
+
+/* ---- seam (B): match ------------------------------------------------------------------------- */
+
+typedef struct {
+  uint8_t uuid[16];     /* winning audio_uuid (greatest uuid among equal counts, as SQLite 3.45.1
+                           orders "group by audio_uuid order by count(*) DESC") */
+  int32_t match_count;  /* count(*) : query frames with >=1 row of that uuid in their window;
+                           0 => no row matched at all (reference returns NULL / NOTFOUND) */
+  int32_t frame_count;  /* all query frames, ignored ones included (src/fp_handler.c:286,403) */
+} tir_hit;
+
+/*
+ * The probe/tally block of fp_search_fingerprint_info() (src/fp_handler.c:285-374) for a batch of
+ * queries whose frames were already extracted.
+ *   y          [n_frames_total][2] double : max1,max2 of every query frame (query q owns frames
+ *              frame_off[q] .. frame_off[q+1]); NaN = JSON key missing (read back as 0.0)
+ *   coefs      1 or 2 (src/fp_handler.c:247); tolerance < 0 -> 0.001 (:252-256)
+ *   freq_ignore_low/high  <= 0 disables the filter (:293-306, :324-337)
+ * Errors: coefs outside [1,2] -> TIR_ERR_ARG.
+ */
+int tir_match(tir_ctx *ctx, const double *y, const uint64_t *frame_off, uint32_t n_queries, int coefs,
+              double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits);
+
+/* Same from device-resident mfcc coefficients as written by tir_extract_dev (y is recomputed as
+ * 10*log10(fabs((double)c)) on the device); d_hits is a device array of n_queries tir_hit. */
+int tir_match_dev(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
+                  double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_hits);
+
+/* fp_search_fingerprint_info() minus the audio_list lookup: extract + match for a batch of query
+ * clips in HOST memory (what each dialplan Tiresias() call does for its recording). */
+int tir_search(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
+               double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits);
+
+/* Multi-GPU (DB sharded by uuid, one context per GPU): fold the per-shard winners of the same
+ * queries into the global winner.  d_gathered is [n_shards][n_queries] tir_hit on this device
+ * (e.g. the output of an NCCL all-gather of each rank's d_hits); result in d_out[n_queries]. */
+int tir_merge_hits_dev(tir_ctx *ctx, const tir_hit *d_gathered, uint32_t n_shards, uint32_t n_queries,
+                       tir_hit *d_out);
+
+/* which shard (0..n_shards-1) owns a uuid */
+uint32_t tir_shard_of(const uint8_t uuid[16], uint32_t n_shards);
+
+/* bookkeeping for the benches: kernels launched by this context so far, and the device time of
+ * the last tir_extract*() / tir_match*() kernels measured with CUDA events on ctx's stream (ms) */
+uint64_t tir_launch_count(tir_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIRESIAS_GPU_H_ */
