@@ -12,12 +12,18 @@
 
 #include "tir_internal.h"
 
+// one tile = T consecutive frames of one clip
+struct __align__(16) TirTile {
+  uint64_t c0;    // first sample of the clip in the PCM buffer
+  int64_t nsamp;  // samples in the clip
+  uint64_t out0;  // output frame index of the tile's first frame
+  int32_t f0;     // first frame of the tile within the clip
+  int32_t nvalid; // frames of the tile that exist (1..T)
+};
+
 struct TirExtractArgs {
   const int16_t *pcm;
-  const uint64_t *clip_off;  // [n_clips+1] samples
-  const uint64_t *frame_off; // [n_clips+1] output frame index
-  const uint32_t *tile_off;  // [n_clips+1] first tile of each clip
-  const uint32_t *tile_clip; // [n_tiles]   owning clip of each tile
+  const TirTile *tiles; // [n_tiles]
   const float2 *win2, *tw_pass, *tw_unt;
   float *coef;
   int32_t *vq;
@@ -27,39 +33,81 @@ struct TirExtractArgs {
 
 __device__ const double2 k_logf_tab[16] = TIR_LOGF_TAB_INIT;
 
-__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
+// tile descriptors from the per-clip prefix arrays (one thread per tile, binary search for its clip)
+template <int T, int HOP>
+__global__ void tir_build_tiles_kernel(const uint64_t *__restrict__ clip_off, const uint64_t *__restrict__ frame_off,
+                                       const uint32_t *__restrict__ tile_off, uint32_t n_clips, uint32_t n_tiles,
+                                       TirTile *__restrict__ tiles) {
+  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n_tiles) return;
+  uint32_t lo = 0, hi = n_clips; // largest c with tile_off[c] <= tile
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+  }
+  TirTile td;
+  td.c0 = clip_off[lo];
+  td.nsamp = (int64_t)(clip_off[lo + 1] - clip_off[lo]);
+  td.f0 = (int32_t)((tile - tile_off[lo]) * T);
+  const int64_t nframes = (td.nsamp + HOP - 1) / HOP;
+  td.nvalid = (int32_t)min((int64_t)T, nframes - td.f0);
+  td.out0 = frame_off[lo] + (uint64_t)td.f0;
+  tiles[tile] = td;
 }
 
-// P0: (T+1) hops of the clip -> sm.pcm ; samples outside the clip are zeros (the first hop of a
-// clip sees the all-zero pvoc history, the last hop is zero padded: aubio_source_do / new_aubio_pvoc)
+__device__ __forceinline__ TirTile tir_load_tile_desc(const TirTile *p) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+  const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+  TirTile t;
+  t.c0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
+  t.nsamp = (int64_t)((uint64_t)a.z | ((uint64_t)a.w << 32));
+  t.out0 = (uint64_t)b.x | ((uint64_t)b.y << 32);
+  t.f0 = (int32_t)b.z, t.nvalid = (int32_t)b.w;
+  return t;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// P0: (T+1) hops of the clip -> buf (asynchronously where the 16-byte vector lies inside the clip);
+// samples outside the clip are zeros (the first hop of a clip sees the all-zero pvoc history, the
+// last hop is zero padded: new_aubio_pvoc / aubio_source_do)
 template <int WIN>
-__device__ __forceinline__ void tir_load_tile(TirSmem<WIN> &sm, const int16_t *__restrict__ clip, int64_t nsamp,
-                                              int64_t s_first, bool aligned, int tid) {
+__device__ __forceinline__ void tir_issue_tile_load(uint32_t *buf, const int16_t *__restrict__ pcm, const TirTile &td,
+                                                    bool base_aligned, int tid) {
   using C = TirCfg<WIN>;
   constexpr int VPC = C::HOP / 8; // 16-byte vectors per hop chunk
   constexpr int TOTAL = (C::T + 1) * VPC;
+  const int16_t *clip = pcm + td.c0;
+  const bool aligned = base_aligned && ((td.c0 & 7) == 0);
+  const int64_t nsamp = td.nsamp;
+  const int64_t s_first = ((int64_t)td.f0 - 1) * C::HOP;
+#pragma unroll 1
   for (int v = tid; v < TOTAL; v += C::NT) {
     const int chunk = v / VPC, iv = v % VPC;
     const int64_t s = s_first + (int64_t)chunk * C::HOP + iv * 8;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (s >= 0 && s + 8 <= nsamp && aligned) {
-      val = ldg_stream16(clip + s);
-    } else if (s + 8 > 0 && s < nsamp) {
-      uint32_t h[8];
+    uint32_t *dst = buf + chunk * C::PCM_STRIDE_W + iv * 4;
+    if (aligned && s >= 0 && s + 8 <= nsamp) {
+      cp_async16(dst, clip + s);
+    } else {
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (s + 8 > 0 && s < nsamp) {
+        uint32_t h[8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const int64_t i = s + e;
-        h[e] = (i >= 0 && i < nsamp) ? (uint32_t)(uint16_t)__ldg(clip + i) : 0u;
+        for (int e = 0; e < 8; e++) {
+          const int64_t i = s + e;
+          h[e] = (i >= 0 && i < nsamp) ? (uint32_t)(uint16_t)__ldg(clip + i) : 0u;
+        }
+        val = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
       }
-      val = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+      *reinterpret_cast<uint4 *>(dst) = val;
     }
-    *reinterpret_cast<uint4 *>(&sm.pcm[chunk * C::PCM_STRIDE_W + iv * 4]) = val;
   }
+  cp_async_commit();
 }
 
 template <int WIN>
@@ -68,44 +116,56 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, 2)
   using C = TirCfg<WIN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TirSmem<WIN> &sm = *reinterpret_cast<TirSmem<WIN> *>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler
+  const bool base_aligned = a.pcm_aligned16 != 0;
+
+  uint32_t tile = blockIdx.x; // grid <= n_tiles
+  TirTile cur = tir_load_tile_desc(a.tiles + tile);
+  tir_issue_tile_load<WIN>(sm.pcm[0], a.pcm, cur, base_aligned, tid);
+  TirTile nxt = cur;
+  bool have_nxt = tile + gridDim.x < a.n_tiles;
+  if (have_nxt) nxt = tir_load_tile_desc(a.tiles + tile + gridDim.x);
 
   for (int i = tid; i < C::M; i += C::NT) sm.win2[i] = a.win2[i];
   for (int i = tid; i < C::N1 * 16; i += C::NT) sm.tw_pass[i] = a.tw_pass[i];
   for (int i = tid; i < 16 * C::TPF; i += C::NT) sm.tw_unt[i] = a.tw_unt[i];
   if (tid < 16) sm.logtab[tid] = k_logf_tab[tid];
-  __syncthreads();
+  // pad words of the exchange buffer are never written by P1 but may be read (times a zero
+  // weight) by the padded mel loop: make sure they are finite
+  for (int i = tid; i < TirSmem<WIN>::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
 
-  for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const uint32_t clip = __ldg(a.tile_clip + tile);
-    const uint64_t c0 = __ldg(a.clip_off + clip), c1 = __ldg(a.clip_off + clip + 1);
-    const int64_t nsamp = (int64_t)(c1 - c0);
-    const int64_t f0 = (int64_t)(tile - __ldg(a.tile_off + clip)) * C::T;
-    const int64_t nframes = (nsamp + C::HOP - 1) / C::HOP;
-    const int nvalid = (int)min((int64_t)C::T, nframes - f0);
-    const uint64_t out0 = __ldg(a.frame_off + clip) + (uint64_t)f0;
-    const bool aligned = a.pcm_aligned16 && ((c0 & 7) == 0);
-
-    tir_load_tile<WIN>(sm, a.pcm + c0, nsamp, (f0 - 1) * C::HOP, aligned, tid);
-    __syncthreads();
-    tir_pass1<WIN>(sm, tid);
+  int b = 0;
+  for (;;) {
+    cp_async_wait_all();
+    __syncthreads(); // pcm[b] is complete; the previous tile's log-mel values (in pcm[b^1]) are consumed
+    TirTile nn = nxt;
+    bool have_nn = false;
+    if (have_nxt) {
+      tir_issue_tile_load<WIN>(sm.pcm[b ^ 1], a.pcm, nxt, base_aligned, tid); // streams in under P1..P4
+      have_nn = tile + 2 * gridDim.x < a.n_tiles;
+      if (have_nn) nn = tir_load_tile_desc(a.tiles + tile + 2 * gridDim.x);
+    }
+    tir_pass1<WIN>(sm, sm.pcm[b], tid);
     __syncthreads();
     TirPass2Regs rg;
     tir_pass2_load<WIN>(sm, tid, rg);
     __syncthreads(); // the magnitudes overwrite the exchange buffer
     tir_pass2_compute<WIN>(sm, tid, rg);
     __syncthreads();
-    tir_mel_phase(sm.xch, sm.lg, sm.logtab, mp, warp, lane);
+    float *lg = reinterpret_cast<float *>(sm.pcm[b]); // P1 is done with this buffer
+    tir_mel_phase(sm.xch, lg, sm.logtab, mp, warp, lane);
     __syncthreads();
-    if (warp < mp.n_coefs && lane < nvalid) {
+    if (warp < mp.n_coefs && lane < cur.nvalid) {
       float c;
       int32_t v;
-      tir_dct_phase(sm.lg, mp, warp, lane, c, v);
-      const uint64_t o = (out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
+      tir_dct_phase(lg, mp, warp, tir_col_of_frame<WIN>(lane), c, v);
+      const uint64_t o = (cur.out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
       if (a.coef) a.coef[o] = c;
       if (a.vq) a.vq[o] = v;
     }
-    // no barrier needed here: sm.lg is next written four barriers from now
+    if (!have_nxt) break;
+    cur = nxt, nxt = nn, have_nxt = have_nn, tile += gridDim.x, b ^= 1;
   }
 }
 
@@ -134,28 +194,28 @@ int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_sample
   if (n_tiles == 0) return TIR_OK;
 
   const size_t off_clip = 0, off_frame = off_clip + nc1 * 8, off_tileoff = off_frame + nc1 * 8;
-  const size_t off_tileclip = (off_tileoff + nc1 * 4 + 15) & ~(size_t)15;
-  const size_t meta_bytes = off_tileclip + (size_t)n_tiles * 4;
+  const size_t meta_bytes = (off_tileoff + nc1 * 4 + 15) & ~(size_t)15;
   int rc;
   if ((rc = tir_reserve_host(ctx, ctx->h_meta, meta_bytes))) return rc;
-  if ((rc = tir_reserve(ctx, ctx->d_tilemeta, meta_bytes))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_clipmeta, meta_bytes))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_tilemeta, (size_t)n_tiles * sizeof(TirTile)))) return rc;
   unsigned char *h = (unsigned char *)ctx->h_meta.p;
   TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the staging buffer may still be in flight
   std::memcpy(h + off_clip, clip_off, nc1 * 8);
   std::memcpy(h + off_frame, frame_off.data(), nc1 * 8);
   std::memcpy(h + off_tileoff, tile_off.data(), nc1 * 4);
-  uint32_t *tc = (uint32_t *)(h + off_tileclip);
-  for (uint32_t c = 0; c < n_clips; c++)
-    for (uint32_t t = tile_off[c]; t < tile_off[c + 1]; t++) tc[t] = c;
-  unsigned char *d = (unsigned char *)ctx->d_tilemeta.p;
+  unsigned char *d = (unsigned char *)ctx->d_clipmeta.p;
   TIR_CUDA(ctx, cudaMemcpyAsync(d, h, meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TirTile *d_tiles = (TirTile *)ctx->d_tilemeta.p;
+  tir_build_tiles_kernel<C::T, C::HOP><<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(
+      (const uint64_t *)(d + off_clip), (const uint64_t *)(d + off_frame), (const uint32_t *)(d + off_tileoff), n_clips,
+      n_tiles, d_tiles);
+  TIR_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
 
   TirExtractArgs a;
   a.pcm = d_pcm;
-  a.clip_off = (const uint64_t *)(d + off_clip);
-  a.frame_off = (const uint64_t *)(d + off_frame);
-  a.tile_off = (const uint32_t *)(d + off_tileoff);
-  a.tile_clip = (const uint32_t *)(d + off_tileclip);
+  a.tiles = d_tiles;
   a.win2 = ctx->d_win2, a.tw_pass = ctx->d_tw_pass, a.tw_unt = ctx->d_tw_unt;
   a.coef = d_coef, a.vq = d_vq;
   a.n_tiles = n_tiles;

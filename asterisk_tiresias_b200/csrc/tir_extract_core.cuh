@@ -34,15 +34,19 @@ struct TirCpx {
 // ---- kernel-parameter block (lives in the constant bank; warp-uniform reads are free operands)
 struct TirMelParams {
   int16_t start[TIR_MAX_FILTERS];   // first bin with non-zero weight
-  int16_t len[TIR_MAX_FILTERS];     // number of bins
-  int16_t woff[TIR_MAX_FILTERS];    // offset into w[]
+  int16_t len[TIR_MAX_FILTERS];     // number of bins (weights are zero padded to a multiple of 4)
+  int16_t woff[TIR_MAX_FILTERS];    // offset into w[], multiple of 4
   uint8_t warp_nf[TIR_MEL_WARPS];   // filters handled by mel warp w
   uint8_t warp_filters[TIR_MEL_WARPS][TIR_MAX_FILTERS];
-  float w[TIR_MAX_NNZ];             // 0.5 * aubio filter weight (the 0.5 of the scaled FFT)
+  float4 w4[TIR_MAX_NNZ / 4];       // 0.5 * aubio filter weight (the 0.5 of the scaled FFT)
   float dct[TIR_MAX_COEFS][TIR_MAX_FILTERS];
   float log_clamp;                  // (float)2e-42 : aubio VERY_SMALL_NUMBER
   int n_filters, n_coefs;
 };
+
+static_assert(sizeof(float4) == 16 && alignof(float4) == 16 && alignof(float2) == 8 && alignof(double2) == 16,
+              "vector types must have the CUDA layout in every translation unit");
+static_assert(sizeof(TirMelParams) % 16 == 0, "TirMelParams layout");
 
 template <int WIN>
 struct TirCfg;
@@ -55,22 +59,24 @@ struct TirCfg<512> {
   static constexpr int PCM_STRIDE_W = 136;     // 32-bit words per hop chunk (128 + 8 pad)
   static constexpr int XCH_ROW = 17;           // float2 per k1 row (16 + 1 pad)
   static constexpr int XCH_FRAME_W = 560;      // words per frame (N1*XCH_ROW*2 = 544, +16)
+  static constexpr int NORM_STRIDE = 33;       // words per bin row of the magnitude buffer (32 frames + 1 pad)
 };
 
 template <int WIN>
 struct TirSmem {
   using C = TirCfg<WIN>;
-  static constexpr int PCM_WORDS = (C::T + 1) * C::PCM_STRIDE_W;
+  static constexpr int PCM_WORDS = ((C::T + 1) * C::PCM_STRIDE_W + 3) & ~3; // keep what follows 16-byte aligned
   static constexpr int XCH_WORDS = C::T * C::XCH_FRAME_W;
-  static constexpr int NORM_WORDS = (C::M + 1) * 32;
+  static constexpr int NORM_WORDS = (C::M + 1) * C::NORM_STRIDE;
   static_assert(NORM_WORDS <= XCH_WORDS, "magnitudes alias the exchange buffer");
-  uint32_t pcm[PCM_WORDS];
+  static_assert(XCH_WORDS % 4 == 0 && C::XCH_FRAME_W % 2 == 0, "float2 / double2 alignment of the members below");
+  static_assert(TIR_MAX_FILTERS * 32 <= PCM_WORDS, "log-mel values alias the consumed PCM buffer");
+  uint32_t pcm[2][PCM_WORDS];   // double buffered: tile N+1 streams in (cp.async) while tile N computes
   float xch[XCH_WORDS];
   float2 win2[C::M];            // window pairs in z[] order, pre-scaled by 2^-15
   float2 tw_pass[C::N1 * 16];   // [k1][n2]  W_M^(n2*k1)
   float2 tw_unt[16 * C::TPF];   // [slot][t] W_{2M}^k
   double2 logtab[16];
-  float lg[TIR_MAX_FILTERS * 32];
 };
 
 // ---- complex helpers, TIR-FFT operation order -------------------------------------------------
@@ -116,24 +122,28 @@ TIR_DEV void tir_dft16(TirCpx (&x)[16]) {
 }
 
 // ---- thread <-> work mapping -------------------------------------------------------------------
-// warp w, lane l: frame slot fl = 4*w + (l>>3) for TPF=8 (consecutive frames in a warp so that the
-// PCM, exchange and magnitude accesses below are bank-conflict free), t = l & (TPF-1).
+// warp w, lane l: t = l % TPF, q = l / TPF, frame slot fl = (32/TPF)*w + q (consecutive frames in a
+// warp).  The magnitude / log-mel buffers are indexed by the permuted slot col = (NT/32)*q + w, which
+// together with the strides (PCM chunk 136 words, exchange frame 560 words, magnitude row 33 words)
+// makes every shared-memory access of P1..P4 bank-conflict free.
 template <int WIN>
 TIR_DEV int tir_frame_of(int tid) { return tid / TirCfg<WIN>::TPF; }
 template <int WIN>
 TIR_DEV int tir_t_of(int tid) { return tid % TirCfg<WIN>::TPF; }
-
-// magnitude store slot: bin-major, frame rotated so that writes (8 threads x 4 frames) and reads
-// (32 frames, one bin) both hit 32 distinct banks
-TIR_DEV int tir_norm_idx(int bin, int fl) {
-  int rot = ((fl & 3) << 3) | (fl >> 2);
-  return bin * 32 + ((rot + bin) & 31);
+template <int WIN>
+TIR_DEV int tir_col_of_frame(int fl) {
+  using C = TirCfg<WIN>;
+  constexpr int FPW = 32 / C::TPF; // frames per warp
+  return (C::NT / 32) * (fl % FPW) + fl / FPW;
 }
+
+// magnitude buffer: bin-major rows of 33 words, frame slot within the row
+#define TIR_NORM_IDX(bin, fl) ((bin) * 33 + (fl))
 
 // ---- P1 ---------------------------------------------------------------------------------------
 // `frames_valid`: frames of this tile that exist; threads of other frames still run (zeros).
 template <int WIN>
-TIR_DEV void tir_pass1(TirSmem<WIN> &sm, int tid) {
+TIR_DEV void tir_pass1(TirSmem<WIN> &sm, const uint32_t *pcm, int tid) {
   using C = TirCfg<WIN>;
   const int fl = tir_frame_of<WIN>(tid), t = tir_t_of<WIN>(tid);
   float2 *xch = reinterpret_cast<float2 *>(sm.xch) + (size_t)fl * (C::XCH_FRAME_W / 2);
@@ -146,7 +156,7 @@ TIR_DEV void tir_pass1(TirSmem<WIN> &sm, int tid) {
     for (int n1 = 0; n1 < 16; n1++) {
       // z[n], n = 16*n1 + n2, after fvec_shift: sample index (2n + WIN/2) mod WIN
       const int chunk = fl + 1 - (n1 >> 3);
-      const uint32_t word = sm.pcm[chunk * C::PCM_STRIDE_W + 16 * (n1 & 7) + n2];
+      const uint32_t word = pcm[chunk * C::PCM_STRIDE_W + 16 * (n1 & 7) + n2];
       const float2 w = sm.win2[16 * n1 + n2];
       x[n1].r = TIR_FMUL((float)(int16_t)(word & 0xffffu), w.x);
       x[n1].i = TIR_FMUL((float)(int16_t)(word >> 16), w.y);
@@ -199,59 +209,71 @@ TIR_DEV void tir_untangle_mag(TirCpx U, TirCpx V, float2 w, float &mk, float &mm
 template <int WIN>
 TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int tid, TirPass2Regs &rg) {
   using C = TirCfg<WIN>;
-  const int fl = tir_frame_of<WIN>(tid), t = tir_t_of<WIN>(tid);
+  static_assert(C::NORM_STRIDE == 33, "TIR_NORM_IDX");
+  const int fl = tir_col_of_frame<WIN>(tir_frame_of<WIN>(tid)), t = tir_t_of<WIN>(tid);
   const bool t0 = (t == 0);
   tir_dft16(rg.A); // A[k2] = Z[kA + N1*k2]
   tir_dft16(rg.B); // B[k2] = Z[kB + N1*k2]
-  float *norm = sm.xch;
-  // t >= 1 : rows kA=t, kB=N1-t.   slots s=0..7  : U=A[s]   (k = t + N1*s),        V=B[15-s]
-  //                                slots 8+i     : U=B[i]   (k = N1-t + N1*i),     V=A[15-i]
-  // t == 0 : rows kA=0, kB=N1/2.   slots s=0..7  : U=B[s]   (k = N1/2 + N1*s),     V=B[15-s]
-  //                                slots 8+i,i>0 : U=A[i]   (k = N1*i),            V=A[16-i]
-  //                                slot  8       : U=V=A[8] (k = M/2)
+  // rows: t >= 1: kA = t, kB = N1-t ; t == 0: kA = 0, kB = N1/2.  Sixteen (k, M-k) pairs per thread:
+  //   slots s=0..7   k = (t ? t : N1/2) + N1*s   U = t ? A[s] : B[s]      V = B[15-s]
+  //   slots 8+i      k = (N1 - t) + N1*i         U = t ? B[i] : A[i+1]    V = A[15-i]
+  // (for t == 0 the last slot is k = M/2 paired with itself: U = V = A[8])
+  float *nlo = sm.xch + TIR_NORM_IDX(t0 ? C::N1 / 2 : t, fl);
+  float *nhi = sm.xch + TIR_NORM_IDX(C::M - (t0 ? C::N1 / 2 : t), fl);
 #pragma unroll
   for (int s = 0; s < 8; s++) {
     TirCpx U, V = rg.B[15 - s];
     U.r = t0 ? rg.B[s].r : rg.A[s].r, U.i = t0 ? rg.B[s].i : rg.A[s].i;
-    const int k = (t0 ? C::N1 / 2 : t) + C::N1 * s;
     float mk, mmk;
     tir_untangle_mag(U, V, sm.tw_unt[s * C::TPF + t], mk, mmk);
-    norm[tir_norm_idx(k, fl)] = mk;
-    norm[tir_norm_idx(C::M - k, fl)] = mmk;
+    nlo[TIR_NORM_IDX(C::N1 * s, 0)] = mk;
+    nhi[-TIR_NORM_IDX(C::N1 * s, 0)] = mmk;
   }
+  nlo = sm.xch + TIR_NORM_IDX(C::N1 - t, fl);
+  nhi = sm.xch + TIR_NORM_IDX(C::M - (C::N1 - t), fl);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    TirCpx U, V;
-    const TirCpx a_alt = rg.A[i ? i : 8], v_alt = rg.A[i ? 16 - i : 8];
-    U.r = t0 ? a_alt.r : rg.B[i].r, U.i = t0 ? a_alt.i : rg.B[i].i;
-    V.r = t0 ? v_alt.r : rg.A[15 - i].r, V.i = t0 ? v_alt.i : rg.A[15 - i].i;
-    const int k = t0 ? (i ? C::N1 * i : C::M / 2) : (C::N1 - t) + C::N1 * i;
+    TirCpx U, V = rg.A[15 - i];
+    U.r = t0 ? rg.A[i + 1].r : rg.B[i].r, U.i = t0 ? rg.A[i + 1].i : rg.B[i].i;
     float mk, mmk;
     tir_untangle_mag(U, V, sm.tw_unt[(8 + i) * C::TPF + t], mk, mmk);
-    norm[tir_norm_idx(k, fl)] = mk;
-    norm[tir_norm_idx(C::M - k, fl)] = mmk;
+    nlo[TIR_NORM_IDX(C::N1 * i, 0)] = mk;
+    nhi[-TIR_NORM_IDX(C::N1 * i, 0)] = mmk;
   }
 }
 
 // ---- P3 ---------------------------------------------------------------------------------------
-// warp `w` (0..TIR_MEL_WARPS-1), lane = frame slot
+// warp `w` (0..TIR_MEL_WARPS-1, warp-uniform), lane = permuted frame slot (tir_col_of_frame)
 TIR_DEV void tir_mel_phase(const float *norm, float *lg, const double2 *logtab, const TirMelParams &mp, int w,
                            int lane) {
   const int nf = mp.warp_nf[w];
   for (int q = 0; q < nf; q++) {
     const int f = mp.warp_filters[w][q];
-    const int b0 = mp.start[f], n = mp.len[f], wo = mp.woff[f];
+    const int n4 = (mp.len[f] + 3) >> 2;
+    const float *p = norm + TIR_NORM_IDX(mp.start[f], lane);
+    const float4 *wp = mp.w4 + (mp.woff[f] >> 2);
     float acc = 0.f;
-    for (int b = 0; b < n; b++) acc = TIR_FADD(acc, TIR_FMUL(norm[tir_norm_idx(b0 + b, lane)], mp.w[wo + b]));
+    // zero padded weights: acc + x*0 == acc (x is finite: a magnitude, or stale exchange data above
+    // the last bin row, which lies inside sm.xch)
+#pragma unroll 2
+    for (int b = 0; b < n4; b++) {
+      const float4 w = wp[b];
+      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 0, 0)], w.x));
+      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 1, 0)], w.y));
+      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 2, 0)], w.z));
+      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 3, 0)], w.w));
+    }
     const float v = acc < mp.log_clamp ? mp.log_clamp : acc;
     lg[f * 32 + lane] = tir_log10f_glibc(v, logtab);
   }
 }
 
 // ---- P4 ---------------------------------------------------------------------------------------
-TIR_DEV void tir_dct_phase(const float *lg, const TirMelParams &mp, int j, int lane, float &c, int32_t &vq) {
+// `col` = permuted slot of the frame this thread finishes
+TIR_DEV void tir_dct_phase(const float *lg, const TirMelParams &mp, int j, int col, float &c, int32_t &vq) {
   float acc = 0.f;
-  for (int f = 0; f < mp.n_filters; f++) acc = TIR_FADD(acc, TIR_FMUL(lg[f * 32 + lane], mp.dct[j][f]));
+#pragma unroll 8
+  for (int f = 0; f < mp.n_filters; f++) acc = TIR_FADD(acc, TIR_FMUL(lg[f * 32 + col], mp.dct[j][f]));
   c = acc;
   vq = tir_quantize_micro(tir_coef_to_y(acc));
 }

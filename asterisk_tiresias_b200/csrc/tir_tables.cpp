@@ -90,10 +90,9 @@ void build_dct(int n_filters, int n_coefs, std::vector<float> &dct) {
 } // namespace
 
 int tir_untangle_bin(int N1, int M, int slot, int t) {
+  (void)M;
   if (slot < 8) return (t ? t : N1 / 2) + N1 * slot;
-  const int i = slot - 8;
-  if (t) return (N1 - t) + N1 * i;
-  return i ? N1 * i : M / 2;
+  return (N1 - t) + N1 * (slot - 8);
 }
 
 bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplerate, TirHostTables &o) {
@@ -156,10 +155,12 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
         last = b;
       }
     const int len = first < 0 ? 0 : last - first + 1;
-    if (nnz + len > TIR_MAX_NNZ) return false;
+    const int len4 = (len + 3) & ~3; // zero padded to whole float4s
+    if (nnz + len4 > TIR_MAX_NNZ) return false;
     mp.start[f] = (int16_t)(first < 0 ? 0 : first), mp.len[f] = (int16_t)len, mp.woff[f] = (int16_t)nnz;
-    for (int b = 0; b < len; b++) mp.w[nnz + b] = 0.5f * filt[first + b]; // interior zeros keep their (exact) 0 weight
-    nnz += len;
+    float *wdst = reinterpret_cast<float *>(mp.w4) + nnz;
+    for (int b = 0; b < len; b++) wdst[b] = 0.5f * filt[first + b];
+    nnz += len4;
   }
   for (int j = 0; j < n_coefs; j++)
     for (int f = 0; f < n_filters; f++) mp.dct[j][f] = o.dct[(size_t)j * n_filters + f];

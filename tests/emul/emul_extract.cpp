@@ -33,18 +33,19 @@ extern "C" int emul_extract(const int16_t *pcm, uint64_t n_samples, int samplera
         int64_t s = (f0 - 1 + chunk) * C::HOP + i;
         uint32_t lo = (s >= 0 && s < nsamp) ? (uint16_t)pcm[s] : 0;
         uint32_t hi = (s + 1 >= 0 && s + 1 < nsamp) ? (uint16_t)pcm[s + 1] : 0;
-        sm->pcm[chunk * C::PCM_STRIDE_W + i / 2] = lo | (hi << 16);
+        sm->pcm[0][chunk * C::PCM_STRIDE_W + i / 2] = lo | (hi << 16);
       }
-    for (int tid = 0; tid < C::NT; tid++) tir_pass1<512>(*sm, tid);
+    for (int tid = 0; tid < C::NT; tid++) tir_pass1<512>(*sm, sm->pcm[0], tid);
     for (int tid = 0; tid < C::NT; tid++) tir_pass2_load<512>(*sm, tid, regs[tid]);
     for (int tid = 0; tid < C::NT; tid++) tir_pass2_compute<512>(*sm, tid, regs[tid]);
+    float *lg = reinterpret_cast<float *>(sm->pcm[0]); // as in the kernel: aliases the consumed PCM buffer
     for (int w = 0; w < TIR_MEL_WARPS; w++)
-      for (int lane = 0; lane < 32; lane++) tir_mel_phase(sm->xch, sm->lg, sm->logtab, tab.mel, w, lane);
+      for (int lane = 0; lane < 32; lane++) tir_mel_phase(sm->xch, lg, sm->logtab, tab.mel, w, lane);
     for (int j = 0; j < 2; j++)
       for (int lane = 0; lane < nvalid; lane++) {
         float c;
         int32_t v;
-        tir_dct_phase(sm->lg, tab.mel, j, lane, c, v);
+        tir_dct_phase(lg, tab.mel, j, tir_col_of_frame<512>(lane), c, v);
         coef[(f0 + lane) * 2 + j] = c;
         vq[(f0 + lane) * 2 + j] = v;
       }
