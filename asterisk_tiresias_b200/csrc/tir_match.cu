@@ -1,4 +1,728 @@
-// placeholder, replaced by the match engine
+// tir_match.cu -- device-resident mirror of table audio_fingerprint and the match kernels.
+//
+// Replaces the SQL block of fp_search_fingerprint_info(), src/fp_handler.c:285-374:
+//   per query frame   insert into T select * from audio_fingerprint
+//                       where max1 >= %f and max1 <= %f [and max2 >= %f and max2 <= %f]
+//                       group by audio_uuid                                         (:308-358)
+//   then              select *, count(*) from T group by audio_uuid
+//                       order by count(*) DESC           -> first row only          (:367-373)
+// i.e. match_count(uuid) = number of query frames whose window holds at least one row of that
+// uuid; winner = greatest match_count, ties -> greatest audio_uuid (what SQLite 3.45.1 emits).
+//
+// All comparisons are done on int32 micro-units, the integers the "%f" texts denote
+// (src/db_ctx_handler.c:480 on the DB side, src/fp_handler.c:309-313 on the query side).
+//
+// Layout in HBM (one shard):
+//   master   uuid[n][16], row_off[n+1], v1[rows], v2[rows], alive[n]     (frame_idx order, as loaded)
+//   index    audios ranked by uuid (rank order == SQLite's text order); ranks cut into BLOCKS of
+//            TIR_BLOCK_UUIDS; the rows of each block sorted by v1:
+//            key1[rows] i32 | uid[rows] u16 (rank within the block) | key2[rows] i32
+//            block_start[n_blocks+1]
+// A window on v1 is therefore one contiguous, coalesced range of every block -- the role
+// idx_audio_fingerprint_max1 plays for SQLite (src/fp_handler.c:745-753).
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
 #include "tir_internal.h"
-struct TirDb { int dummy; };
-void tir_db_destroy(TirDb *db) { delete db; }
+
+#define TIR_BLOCK_UUIDS 16384 // uuids per index block: u16 local ids, 32 KB of u16 vote counters
+#define TIR_MATCH_THREADS 256
+
+struct TirWindow {
+  int32_t lo1, hi1, lo2, hi2;
+  uint32_t weight; // query frames that share this window
+  uint32_t pad;
+};
+
+struct UuidKey {
+  uint64_t hi, lo;
+  bool operator==(const UuidKey &o) const { return hi == o.hi && lo == o.lo; }
+};
+struct UuidKeyHash {
+  size_t operator()(const UuidKey &k) const { return (size_t)(k.hi * 0x9E3779B97F4A7C15ull ^ k.lo); }
+};
+static UuidKey uuid_key(const uint8_t *u) {
+  UuidKey k{0, 0};
+  for (int i = 0; i < 8; i++) k.hi = (k.hi << 8) | u[i], k.lo = (k.lo << 8) | u[8 + i];
+  return k;
+}
+
+struct TirDb {
+  // master copy (device) + small host mirrors
+  uint64_t n_audio = 0, n_rows = 0;
+  DevBuf uuids, row_off, v1, v2, alive;
+  std::vector<uint64_t> h_row_off; // [n_audio+1]
+  std::vector<uint8_t> h_alive;
+  std::vector<uint8_t> h_uuids;    // lazily mirrored for add/remove lookups
+  std::unordered_map<UuidKey, uint32_t, UuidKeyHash> by_uuid;
+  bool lookup_ready = false;
+  uint64_t n_alive = 0;
+  // index
+  bool dirty = true;
+  uint32_t n_blocks = 0;
+  uint64_t n_indexed = 0;
+  DevBuf order, key1, uid, key2, block_start;
+};
+
+void tir_db_destroy(TirDb *db) {
+  if (!db) return;
+  for (DevBuf *b : {&db->uuids, &db->row_off, &db->v1, &db->v2, &db->alive, &db->order, &db->key1, &db->uid, &db->key2,
+                    &db->block_start})
+    if (b->p) cudaFree(b->p);
+  delete db;
+}
+
+// grow a device buffer preserving its first `keep` bytes
+static int grow_keep(tir_ctx *ctx, DevBuf &b, size_t bytes, size_t keep) {
+  if (bytes <= b.cap) return TIR_OK;
+  size_t cap = bytes + bytes / 2 + 256;
+  void *np = nullptr;
+  cudaError_t e = cudaMalloc(&np, cap);
+  if (e != cudaSuccess) return tir_fail(ctx, TIR_ERR_NOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(e));
+  if (b.p && keep) TIR_CUDA(ctx, cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream));
+  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (b.p) cudaFree(b.p);
+  b.p = np, b.cap = cap;
+  return TIR_OK;
+}
+
+// ================================================================================ index build
+
+__global__ void tir_uuid_keys_kernel(const uint8_t *__restrict__ uuids, uint32_t n, uint64_t *__restrict__ hi,
+                                     uint64_t *__restrict__ lo, uint32_t *__restrict__ idx) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const uint8_t *u = uuids + (size_t)a * 16;
+  uint64_t h = 0, l = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) h = (h << 8) | u[i], l = (l << 8) | u[8 + i];
+  hi[a] = h, lo[a] = l, idx[a] = a;
+}
+
+__global__ void tir_gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n,
+                                      uint64_t *__restrict__ dst) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+__global__ void tir_invert_kernel(const uint32_t *__restrict__ order, uint32_t n, uint32_t *__restrict__ rank_of) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) rank_of[order[r]] = r;
+}
+
+// one warp per audio: emit (block | biased v1) sort keys and (v2 | local uid) payloads for its rows.
+// NULL max1 rows and rows of deleted audios can never be selected by "max1 >= lo and max1 <= hi":
+// they get the all-ones key, sort to the end and are cut off.
+__global__ void tir_row_keys_kernel(const uint64_t *__restrict__ row_off, const int32_t *__restrict__ v1,
+                                    const int32_t *__restrict__ v2, const uint8_t *__restrict__ alive,
+                                    const uint32_t *__restrict__ rank_of, uint32_t n_audio, uint64_t *__restrict__ keys,
+                                    uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_valid) {
+  const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (a >= n_audio) return;
+  const uint64_t r0 = row_off[a], r1 = row_off[a + 1];
+  const uint32_t rank = rank_of[a];
+  const uint64_t blk = rank / TIR_BLOCK_UUIDS, local = rank % TIR_BLOCK_UUIDS;
+  const bool live = alive[a] != 0;
+  unsigned long long cnt = 0;
+  for (uint64_t r = r0 + lane; r < r1; r += 32) {
+    const int32_t a1 = v1[r], a2 = v2[r];
+    const bool ok = live && a1 != TIR_NULL_V;
+    keys[r] = ok ? ((blk << 32) | (uint64_t)((uint32_t)a1 ^ 0x80000000u)) : ~0ull;
+    vals[r] = ((uint64_t)(uint32_t)a2 << 32) | local;
+    cnt += ok;
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0 && cnt) atomicAdd(n_valid, cnt);
+}
+
+__global__ void tir_split_rows_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t n,
+                                      int32_t *__restrict__ key1, uint16_t *__restrict__ uid, int32_t *__restrict__ key2) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i], v = vals[i];
+  key1[i] = (int32_t)((uint32_t)k ^ 0x80000000u);
+  uid[i] = (uint16_t)(v & 0xffffu);
+  key2[i] = (int32_t)(uint32_t)(v >> 32);
+}
+
+// block_start[b] = first sorted row whose block id is >= b
+__global__ void tir_block_start_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t n_blocks,
+                                       uint64_t *__restrict__ block_start) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_blocks) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if ((keys[mid] >> 32) < (uint64_t)b) lo = mid + 1; else hi = mid;
+  }
+  block_start[b] = lo;
+}
+
+static int db_build_index(tir_ctx *ctx, TirDb *db) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = (uint32_t)db->n_audio;
+  const uint64_t rows = db->n_rows;
+  db->n_blocks = (n + TIR_BLOCK_UUIDS - 1) / TIR_BLOCK_UUIDS;
+  db->n_indexed = 0;
+  int rc;
+  if ((rc = tir_reserve(ctx, db->order, (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
+  if ((rc = tir_reserve(ctx, db->block_start, ((size_t)db->n_blocks + 1) * 8))) return rc;
+  if (n == 0 || rows == 0) {
+    TIR_CUDA(ctx, cudaMemsetAsync(db->block_start.p, 0, ((size_t)db->n_blocks + 1) * 8, st));
+    db->dirty = false;
+    return TIR_OK;
+  }
+  // ---- rank audios by uuid bytes: two stable 64-bit radix passes (low half, then high half)
+  uint64_t *hi, *lo, *k_in, *k_out;
+  uint32_t *idx_a, *idx_b, *rank_of;
+  TIR_CUDA(ctx, cudaMalloc(&hi, (size_t)n * 8));
+  TIR_CUDA(ctx, cudaMalloc(&lo, (size_t)n * 8));
+  TIR_CUDA(ctx, cudaMalloc(&k_in, (size_t)n * 8));
+  TIR_CUDA(ctx, cudaMalloc(&k_out, (size_t)n * 8));
+  TIR_CUDA(ctx, cudaMalloc(&idx_a, (size_t)n * 4));
+  TIR_CUDA(ctx, cudaMalloc(&idx_b, (size_t)n * 4));
+  TIR_CUDA(ctx, cudaMalloc(&rank_of, (size_t)n * 4));
+  const uint32_t gb = (n + 255) / 256;
+  tir_uuid_keys_kernel<<<gb, 256, 0, st>>>((const uint8_t *)db->uuids.p, n, hi, lo, idx_a);
+  size_t tmp_bytes = 0, tmp2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lo, k_out, idx_a, idx_b, (int)n, 0, 64, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                  (uint64_t *)nullptr, (long long)rows, 0, 64, st);
+  tmp_bytes = std::max(tmp_bytes, tmp2);
+  void *tmp = nullptr;
+  TIR_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes));
+  TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lo, k_out, idx_a, idx_b, (int)n, 0, 64, st));
+  tir_gather_u64_kernel<<<gb, 256, 0, st>>>(hi, idx_b, n, k_in);
+  TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, idx_b, (uint32_t *)db->order.p, (int)n, 0, 64, st));
+  tir_invert_kernel<<<gb, 256, 0, st>>>((const uint32_t *)db->order.p, n, rank_of);
+  ctx->launches += 5;
+  TIR_CUDA(ctx, cudaFree(hi));
+  TIR_CUDA(ctx, cudaFree(lo));
+  TIR_CUDA(ctx, cudaFree(k_in));
+  TIR_CUDA(ctx, cudaFree(k_out));
+  TIR_CUDA(ctx, cudaFree(idx_a));
+  TIR_CUDA(ctx, cudaFree(idx_b));
+  // ---- rows: (block, v1) keys -> radix sort -> SoA
+  uint64_t *rk, *rv, *rk2, *rv2;
+  unsigned long long *d_nvalid;
+  TIR_CUDA(ctx, cudaMalloc(&rk, rows * 8));
+  TIR_CUDA(ctx, cudaMalloc(&rv, rows * 8));
+  TIR_CUDA(ctx, cudaMalloc(&rk2, rows * 8));
+  TIR_CUDA(ctx, cudaMalloc(&rv2, rows * 8));
+  TIR_CUDA(ctx, cudaMalloc(&d_nvalid, 8));
+  TIR_CUDA(ctx, cudaMemsetAsync(d_nvalid, 0, 8, st));
+  tir_row_keys_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, st>>>(
+      (const uint64_t *)db->row_off.p, (const int32_t *)db->v1.p, (const int32_t *)db->v2.p, (const uint8_t *)db->alive.p,
+      rank_of, n, rk, rv, d_nvalid);
+  // block ids need ceil(log2(n_blocks)) bits above the 32 key bits; the all-ones tail sorts last anyway
+  TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rk, rk2, rv, rv2, (long long)rows, 0, 64, st));
+  unsigned long long nvalid = 0;
+  TIR_CUDA(ctx, cudaMemcpyAsync(&nvalid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  db->n_indexed = nvalid;
+  if ((rc = tir_reserve(ctx, db->key1, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, db->uid, std::max<size_t>(nvalid, 1) * 2 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, db->key2, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
+  if (nvalid)
+    tir_split_rows_kernel<<<(uint32_t)((nvalid + 255) / 256), 256, 0, st>>>(rk2, rv2, nvalid, (int32_t *)db->key1.p,
+                                                                            (uint16_t *)db->uid.p, (int32_t *)db->key2.p);
+  tir_block_start_kernel<<<(db->n_blocks + 1 + 255) / 256, 256, 0, st>>>(rk2, nvalid, db->n_blocks,
+                                                                         (uint64_t *)db->block_start.p);
+  ctx->launches += 4;
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  TIR_CUDA(ctx, cudaGetLastError());
+  cudaFree(rk), cudaFree(rv), cudaFree(rk2), cudaFree(rv2), cudaFree(d_nvalid), cudaFree(tmp), cudaFree(rank_of);
+  db->dirty = false;
+  return TIR_OK;
+}
+
+// ================================================================================ query side
+
+struct TirMatchParams {
+  int coefs;
+  double tol;
+  int use_lo, use_hi;
+  double thr_lo, thr_hi; // 10*log10(freq_ignore_*), computed on the host exactly like the reference
+};
+
+// per-frame window of fp_search_fingerprint_info(), src/fp_handler.c:287-351.
+// returns false when the frame is skipped by the freq_ignore test on max1 (:293-306).
+__device__ __forceinline__ bool tir_frame_window(double y1, double y2, const TirMatchParams &mp, TirWindow &w) {
+  // a non-finite value never became a JSON real: ast_json_real_get(NULL) reads 0.0
+  const double v1 = (y1 == y1 && fabs(y1) != INFINITY) ? y1 : 0.0;
+  const double freq = (double)(int)v1; // :290 C truncation
+  if (mp.use_lo && freq < mp.thr_lo) return false;
+  if (mp.use_hi && freq > mp.thr_hi) return false;
+  w.lo1 = tir_quantize_micro(freq - mp.tol); // "%f" of the bound, :309-313
+  w.hi1 = tir_quantize_micro(freq + mp.tol);
+  w.lo2 = INT32_MIN, w.hi2 = INT32_MAX; // no predicate on max2
+  if (mp.coefs >= 2) {
+    const double v2 = (y2 == y2 && fabs(y2) != INFINITY) ? y2 : 0.0; // :321, untruncated
+    const bool dropped = (mp.use_lo && v2 < mp.thr_lo) || (mp.use_hi && v2 > mp.thr_hi); // :324-337 `continue`
+    if (!dropped) {
+      w.lo2 = max(tir_quantize_micro(v2 - mp.tol), INT32_MIN + 1); // NULL max2 (INT32_MIN) never satisfies it
+      w.hi2 = tir_quantize_micro(v2 + mp.tol);
+    }
+  }
+  w.weight = 1, w.pad = 0;
+  return true;
+}
+
+// One CTA per query: windows of all frames, identical windows folded into one with a weight
+// (a uuid gets one vote per frame, so frames with the same window vote identically).
+// FROM_COEF: y is recomputed from the float mfcc coefficients as the reference does (:651).
+template <bool FROM_COEF>
+__global__ void tir_qprep_kernel(const double *__restrict__ y, const float *__restrict__ coef,
+                                 const uint64_t *__restrict__ frame_off, const TirMatchParams mp,
+                                 TirWindow *__restrict__ windows, uint32_t *__restrict__ n_windows) {
+  const uint32_t q = blockIdx.x;
+  const uint64_t f0 = frame_off[q], f1 = frame_off[q + 1];
+  TirWindow *wq = windows + f0;
+  __shared__ uint32_t s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  // pass 1: every frame writes its own window (weight 0 = skipped) in place
+  for (uint64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+    double y1, y2;
+    if (FROM_COEF) {
+      y1 = tir_coef_to_y(coef[f * 2]), y2 = tir_coef_to_y(coef[f * 2 + 1]);
+    } else {
+      y1 = y[f * 2], y2 = y[f * 2 + 1];
+    }
+    TirWindow w;
+    if (!tir_frame_window(y1, y2, mp, w)) w.lo1 = 0, w.hi1 = -1, w.lo2 = 0, w.hi2 = -1, w.weight = 0, w.pad = 0;
+    wq[f - f0] = w;
+  }
+  __syncthreads();
+  // pass 2: a frame is a leader if no earlier frame has the same window; weight = multiplicity
+  const uint32_t nf = (uint32_t)(f1 - f0);
+  for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
+    const TirWindow w = wq[i];
+    uint32_t mult = 0;
+    bool leader = w.weight != 0;
+    if (leader) {
+      for (uint32_t j = 0; j < nf; j++) {
+        const TirWindow o = wq[j];
+        const bool same = o.weight != 0 && o.lo1 == w.lo1 && o.hi1 == w.hi1 && o.lo2 == w.lo2 && o.hi2 == w.hi2;
+        if (same && j < i) { leader = false; break; }
+        mult += same;
+      }
+    }
+    wq[i].pad = leader ? mult : 0; // stash, compacted below
+  }
+  __syncthreads();
+  // pass 3: compact leaders to the front (serial per query; the list is tiny for coefs == 1)
+  if (threadIdx.x == 0) {
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < nf; i++) {
+      TirWindow w = wq[i];
+      if (w.pad) {
+        w.weight = w.pad, w.pad = 0;
+        wq[k++] = w; // k <= i: never overwrites an unread entry
+      }
+    }
+    n_windows[q] = k;
+  }
+}
+
+// ================================================================================ match kernel
+
+// 32-ary search by one warp: first index in [lo,hi) with key[idx] >= target (UPPER: > target)
+template <bool UPPER>
+__device__ __forceinline__ uint64_t tir_warp_bound(const int32_t *__restrict__ key, uint64_t lo, uint64_t hi, int32_t target,
+                                                   int lane) {
+  while (hi - lo > 32) {
+    const uint64_t step = (hi - lo + 32) / 33; // 32 probes split the range in 33 parts
+    const uint64_t p = lo + (uint64_t)(lane + 1) * step - 1;
+    bool below = false;
+    if (p < hi) {
+      const int32_t k = __ldg(key + p);
+      below = UPPER ? (k <= target) : (k < target);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, below);
+    const int nb = __popc(m); // probes are monotone: the first nb are below
+    const uint64_t nlo = nb ? lo + (uint64_t)nb * step : lo;
+    const uint64_t nhi = (nb < 32) ? min(hi, lo + (uint64_t)(nb + 1) * step - 1 + 1) : hi;
+    lo = nlo, hi = nhi;
+  }
+  bool below = false;
+  if (lo + lane < hi) {
+    const int32_t k = __ldg(key + lo + lane);
+    below = UPPER ? (k <= target) : (k < target);
+  }
+  return lo + __popc(__ballot_sync(0xffffffffu, below));
+}
+
+// grid (n_blocks, n_queries).  Votes of one query into the uuids of one index block.
+template <int COEFS>
+__global__ void __launch_bounds__(TIR_MATCH_THREADS)
+    tir_match_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
+                     const uint64_t *__restrict__ block_start, const TirWindow *__restrict__ windows,
+                     const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
+                     unsigned long long *__restrict__ best, uint32_t q_base) {
+  __shared__ uint32_t s_cnt[TIR_BLOCK_UUIDS / 2];  // u16 vote counters, two per word
+  __shared__ uint32_t s_seen[TIR_BLOCK_UUIDS / 32]; // per-window "uuid already voted" bits
+  __shared__ uint64_t s_range[2];
+  __shared__ unsigned long long s_best[TIR_MATCH_THREADS / 32];
+  const uint32_t blk = blockIdx.x, q = q_base + blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
+  const uint32_t nw = n_windows[q];
+  if (bs == be || nw == 0) return;
+  const TirWindow *wq = windows + frame_off[q];
+  uint16_t *cnt16 = reinterpret_cast<uint16_t *>(s_cnt);
+  for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) s_cnt[i] = 0;
+  bool any = false;
+  for (uint32_t wi = 0; wi < nw; wi++) {
+    const TirWindow w = wq[wi];
+    for (int i = tid; i < TIR_BLOCK_UUIDS / 32; i += TIR_MATCH_THREADS) s_seen[i] = 0;
+    if (warp == 0) {
+      const uint64_t r = tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
+      if (lane == 0) s_range[0] = r;
+    } else if (warp == 1) {
+      const uint64_t r = tir_warp_bound<true>(key1, bs, be, w.hi1, lane);
+      if (lane == 0) s_range[1] = r;
+    }
+    __syncthreads();
+    const uint64_t r0 = s_range[0], r1 = s_range[1];
+    for (uint64_t r = r0 + tid; r < r1; r += TIR_MATCH_THREADS) {
+      if (COEFS >= 2) {
+        const int32_t k2 = __ldg(key2 + r);
+        if (k2 < w.lo2 || k2 > w.hi2) continue;
+      }
+      const uint32_t u = __ldg(uid + r);
+      const uint32_t bit = 1u << (u & 31);
+      const uint32_t old = atomicOr(&s_seen[u >> 5], bit); // group by audio_uuid: one vote per frame
+      if (!(old & bit)) cnt16[u] = (uint16_t)(cnt16[u] + w.weight);
+    }
+    any |= (r1 > r0);
+    __syncthreads();
+  }
+  // winner of this block: greatest count, ties -> greatest rank (== greatest uuid)
+  unsigned long long bestv = 0;
+  for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) {
+    const uint32_t pair = s_cnt[i];
+    const uint32_t c0 = pair & 0xffffu, c1 = pair >> 16;
+    const uint64_t rank0 = (uint64_t)blk * TIR_BLOCK_UUIDS + 2 * i;
+    if (c0) bestv = max(bestv, ((unsigned long long)c0 << 32) | rank0);
+    if (c1) bestv = max(bestv, ((unsigned long long)c1 << 32) | (rank0 + 1));
+  }
+  for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
+  if (lane == 0) s_best[warp] = bestv;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < TIR_MATCH_THREADS / 32; i++) bestv = max(bestv, s_best[i]);
+    if (bestv) atomicMax(best + q, bestv);
+  }
+  (void)any;
+}
+
+__global__ void tir_finalize_kernel(const unsigned long long *__restrict__ best, const uint32_t *__restrict__ order,
+                                    const uint8_t *__restrict__ uuids, const uint64_t *__restrict__ frame_off,
+                                    uint32_t n_queries, tir_hit *__restrict__ hits) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  const unsigned long long b = best[q];
+  tir_hit h;
+  h.match_count = (int32_t)(b >> 32);
+  h.frame_count = (int32_t)(frame_off[q + 1] - frame_off[q]); // all frames, :286,403
+  if (b) {
+    const uint8_t *u = uuids + (size_t)order[(uint32_t)b] * 16;
+#pragma unroll
+    for (int i = 0; i < 16; i++) h.uuid[i] = u[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) h.uuid[i] = 0;
+  }
+  hits[q] = h;
+}
+
+__global__ void tir_merge_hits_kernel(const tir_hit *__restrict__ gathered, uint32_t n_shards, uint32_t n_queries,
+                                      tir_hit *__restrict__ out) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  tir_hit bestv = gathered[q];
+  for (uint32_t s = 1; s < n_shards; s++) {
+    const tir_hit h = gathered[(size_t)s * n_queries + q];
+    bool better = h.match_count > bestv.match_count;
+    if (h.match_count == bestv.match_count && h.match_count > 0) {
+      int c = 0;
+      for (int i = 0; i < 16 && c == 0; i++) c = (int)h.uuid[i] - (int)bestv.uuid[i];
+      better = c > 0;
+    }
+    if (better) bestv = h;
+  }
+  out[q] = bestv;
+}
+
+// ================================================================================ host entry points
+
+static int ensure_db(tir_ctx *ctx) {
+  if (!ctx->db) ctx->db = new (std::nothrow) TirDb();
+  return ctx->db ? TIR_OK : tir_fail(ctx, TIR_ERR_NOMEM, "out of memory");
+}
+
+static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef, const uint64_t *frame_off,
+                           uint32_t n_queries, int coefs, double tolerance, int ign_lo, int ign_hi, tir_hit *d_hits) {
+  if (coefs < 1 || coefs > TIR_N_COEFS) return tir_fail(ctx, TIR_ERR_ARG, "Wrong coefs count. max[%d], coefs[%d]", TIR_N_COEFS, coefs);
+  if (!ctx->db) return tir_fail(ctx, TIR_ERR_STATE, "no fingerprint DB loaded");
+  if (n_queries == 0) return TIR_OK;
+  TirDb *db = ctx->db;
+  int rc;
+  if (db->dirty && (rc = db_build_index(ctx, db))) return rc;
+  cudaStream_t st = ctx->stream;
+  const uint64_t F = frame_off[n_queries] - frame_off[0];
+  if (frame_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "frame_off[0] must be 0");
+  for (uint32_t q = 0; q < n_queries; q++)
+    if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 65535)
+      return tir_fail(ctx, TIR_ERR_ARG, "a query may have at most 65535 frames (u16 vote counters)");
+  // scratch: frame_off (device) | n_windows | best | windows
+  const size_t o_foff = 0, o_nw = o_foff + ((size_t)n_queries + 1) * 8, o_best = (o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
+  const size_t o_win = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  const size_t bytes = o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
+  if ((rc = tir_reserve(ctx, ctx->d_qmeta, bytes))) return rc;
+  if ((rc = tir_reserve_host(ctx, ctx->h_meta, ((size_t)n_queries + 1) * 8))) return rc;
+  unsigned char *d = (unsigned char *)ctx->d_qmeta.p;
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  std::memcpy(ctx->h_meta.p, frame_off, ((size_t)n_queries + 1) * 8);
+  TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, ctx->h_meta.p, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+  TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, (size_t)n_queries * 8, st));
+  TirMatchParams mp;
+  mp.coefs = coefs;
+  mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
+  mp.use_lo = ign_lo > 0, mp.use_hi = ign_hi > 0;
+  mp.thr_lo = mp.use_lo ? 10 * log10((double)ign_lo) : 0.0; // :294, :300
+  mp.thr_hi = mp.use_hi ? 10 * log10((double)ign_hi) : 0.0;
+  const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
+  uint32_t *d_nw = (uint32_t *)(d + o_nw);
+  unsigned long long *d_best = (unsigned long long *)(d + o_best);
+  TirWindow *d_win = (TirWindow *)(d + o_win);
+  if (d_coef)
+    tir_qprep_kernel<true><<<n_queries, 128, 0, st>>>(nullptr, d_coef, d_foff, mp, d_win, d_nw);
+  else
+    tir_qprep_kernel<false><<<n_queries, 128, 0, st>>>(d_y, nullptr, d_foff, mp, d_win, d_nw);
+  ctx->launches++;
+  if (db->n_blocks && db->n_indexed) {
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += 32768) { // grid.y limit
+      dim3 grid(db->n_blocks, std::min<uint32_t>(32768, n_queries - q0));
+      if (coefs >= 2)
+        tir_match_kernel<2><<<grid, TIR_MATCH_THREADS, 0, st>>>((const int32_t *)db->key1.p, (const uint16_t *)db->uid.p,
+                                                                (const int32_t *)db->key2.p, (const uint64_t *)db->block_start.p,
+                                                                d_win, d_nw, d_foff, d_best, q0);
+      else
+        tir_match_kernel<1><<<grid, TIR_MATCH_THREADS, 0, st>>>((const int32_t *)db->key1.p, (const uint16_t *)db->uid.p,
+                                                                (const int32_t *)db->key2.p, (const uint64_t *)db->block_start.p,
+                                                                d_win, d_nw, d_foff, d_best, q0);
+      ctx->launches++;
+    }
+  }
+  tir_finalize_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(d_best, (const uint32_t *)db->order.p,
+                                                               (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits);
+  ctx->launches++;
+  TIR_CUDA(ctx, cudaGetLastError());
+  return TIR_OK;
+}
+
+extern "C" {
+
+int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off, const int32_t *v1,
+                const int32_t *v2) {
+  if (!ctx || (n_audio && (!uuid || !row_off))) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if ((rc = ensure_db(ctx))) return rc;
+  TirDb *db = ctx->db;
+  const uint64_t rows = n_audio ? row_off[n_audio] : 0;
+  if (n_audio && row_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "row_off[0] must be 0");
+  if (rows && (!v1 || !v2)) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  if ((rc = grow_keep(ctx, db->uuids, (size_t)n_audio * 16 + 16, 0))) return rc;
+  if ((rc = grow_keep(ctx, db->row_off, ((size_t)n_audio + 1) * 8, 0))) return rc;
+  if ((rc = grow_keep(ctx, db->alive, (size_t)n_audio + 1, 0))) return rc;
+  if ((rc = grow_keep(ctx, db->v1, rows * 4 + 4, 0))) return rc;
+  if ((rc = grow_keep(ctx, db->v2, rows * 4 + 4, 0))) return rc;
+  cudaStream_t st = ctx->stream;
+  if (n_audio) {
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->uuids.p, uuid, (size_t)n_audio * 16, cudaMemcpyHostToDevice, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->row_off.p, row_off, ((size_t)n_audio + 1) * 8, cudaMemcpyHostToDevice, st));
+    TIR_CUDA(ctx, cudaMemsetAsync(db->alive.p, 1, n_audio, st));
+  }
+  if (rows) {
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->v1.p, v1, rows * 4, cudaMemcpyHostToDevice, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->v2.p, v2, rows * 4, cudaMemcpyHostToDevice, st));
+  }
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  db->n_audio = n_audio, db->n_rows = rows, db->n_alive = n_audio;
+  db->h_row_off.assign(row_off ? row_off : nullptr, row_off ? row_off + n_audio + 1 : nullptr);
+  if (!n_audio) db->h_row_off.assign(1, 0);
+  db->h_alive.assign(n_audio, 1);
+  db->h_uuids.assign((const uint8_t *)uuid, (const uint8_t *)uuid + (size_t)n_audio * 16);
+  db->by_uuid.clear(), db->lookup_ready = false;
+  db->dirty = true;
+  return db_build_index(ctx, db);
+}
+
+static void ensure_lookup(TirDb *db) {
+  if (db->lookup_ready) return;
+  db->by_uuid.clear();
+  db->by_uuid.reserve(db->n_audio * 2 + 16);
+  for (uint64_t a = 0; a < db->n_audio; a++)
+    if (db->h_alive[a]) db->by_uuid[uuid_key(db->h_uuids.data() + a * 16)] = (uint32_t)a;
+  db->lookup_ready = true;
+}
+
+int tir_db_add(tir_ctx *ctx, const uint8_t uuid[16], const int32_t *v1, const int32_t *v2, uint32_t n_rows) {
+  if (!ctx || !uuid || (n_rows && (!v1 || !v2))) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if ((rc = ensure_db(ctx))) return rc;
+  TirDb *db = ctx->db;
+  if (db->h_row_off.empty()) db->h_row_off.assign(1, 0);
+  const uint64_t n = db->n_audio, rows = db->n_rows;
+  if ((rc = grow_keep(ctx, db->uuids, (n + 1) * 16 + 16, n * 16))) return rc;
+  if ((rc = grow_keep(ctx, db->row_off, (n + 2) * 8, (n + 1) * 8))) return rc;
+  if ((rc = grow_keep(ctx, db->alive, n + 2, n))) return rc;
+  if ((rc = grow_keep(ctx, db->v1, (rows + n_rows) * 4 + 4, rows * 4))) return rc;
+  if ((rc = grow_keep(ctx, db->v2, (rows + n_rows) * 4 + 4, rows * 4))) return rc;
+  cudaStream_t st = ctx->stream;
+  const uint64_t new_off[2] = {rows, rows + n_rows};
+  const uint8_t one = 1;
+  TIR_CUDA(ctx, cudaMemcpyAsync((uint8_t *)db->uuids.p + n * 16, uuid, 16, cudaMemcpyHostToDevice, st));
+  TIR_CUDA(ctx, cudaMemcpyAsync((uint64_t *)db->row_off.p + n, new_off, 16, cudaMemcpyHostToDevice, st));
+  TIR_CUDA(ctx, cudaMemcpyAsync((uint8_t *)db->alive.p + n, &one, 1, cudaMemcpyHostToDevice, st));
+  if (n_rows) {
+    TIR_CUDA(ctx, cudaMemcpyAsync((int32_t *)db->v1.p + rows, v1, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync((int32_t *)db->v2.p + rows, v2, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+  }
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  db->h_uuids.insert(db->h_uuids.end(), uuid, uuid + 16);
+  db->h_row_off.push_back(rows + n_rows);
+  db->h_alive.push_back(1);
+  if (db->lookup_ready) db->by_uuid[uuid_key(uuid)] = (uint32_t)n;
+  db->n_audio = n + 1, db->n_rows = rows + n_rows, db->n_alive++;
+  db->dirty = true; // the index is rebuilt by the next match
+  return TIR_OK;
+}
+
+int tir_db_remove(tir_ctx *ctx, const uint8_t uuid[16]) {
+  if (!ctx || !uuid) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  if (!ctx->db) return tir_fail(ctx, TIR_ERR_NOTFOUND, "unknown uuid");
+  TirDb *db = ctx->db;
+  ensure_lookup(db);
+  auto it = db->by_uuid.find(uuid_key(uuid));
+  if (it == db->by_uuid.end()) return tir_fail(ctx, TIR_ERR_NOTFOUND, "unknown uuid");
+  const uint32_t a = it->second;
+  db->by_uuid.erase(it);
+  db->h_alive[a] = 0;
+  const uint8_t zero = 0;
+  TIR_CUDA(ctx, cudaMemcpyAsync((uint8_t *)db->alive.p + a, &zero, 1, cudaMemcpyHostToDevice, ctx->stream));
+  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  db->n_alive--;
+  db->dirty = true;
+  return TIR_OK;
+}
+
+int tir_db_stats(tir_ctx *ctx, uint64_t *n_audio, uint64_t *n_rows) {
+  if (!ctx) return TIR_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  uint64_t a = 0, r = 0;
+  if (ctx->db) {
+    TirDb *db = ctx->db;
+    a = db->n_alive;
+    for (uint64_t i = 0; i < db->n_audio; i++)
+      if (db->h_alive[i]) r += db->h_row_off[i + 1] - db->h_row_off[i];
+  }
+  if (n_audio) *n_audio = a;
+  if (n_rows) *n_rows = r;
+  return TIR_OK;
+}
+
+int tir_match(tir_ctx *ctx, const double *y, const uint64_t *frame_off, uint32_t n_queries, int coefs, double tolerance,
+              int freq_ignore_low, int freq_ignore_high, tir_hit *hits) {
+  if (!ctx || !frame_off || !hits) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  if (n_queries == 0) return TIR_OK;
+  const uint64_t F = frame_off[n_queries];
+  if (F && !y) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = tir_reserve(ctx, ctx->d_y, std::max<uint64_t>(F, 1) * 2 * sizeof(double)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_hits, (size_t)n_queries * sizeof(tir_hit)))) return rc;
+  if (F) TIR_CUDA(ctx, cudaMemcpyAsync(ctx->d_y.p, y, F * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = match_on_device(ctx, (const double *)ctx->d_y.p, nullptr, frame_off, n_queries, coefs, tolerance,
+                            freq_ignore_low, freq_ignore_high, (tir_hit *)ctx->d_hits.p)))
+    return rc;
+  TIR_CUDA(ctx, cudaMemcpyAsync(hits, ctx->d_hits.p, (size_t)n_queries * sizeof(tir_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TIR_OK;
+}
+
+int tir_match_dev(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
+                  double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_hits) {
+  if (!ctx || !frame_off || !d_hits || !d_coef) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return match_on_device(ctx, nullptr, d_coef, frame_off, n_queries, coefs, tolerance, freq_ignore_low, freq_ignore_high,
+                         d_hits);
+}
+
+int tir_search(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs, double tolerance,
+               int freq_ignore_low, int freq_ignore_high, tir_hit *hits) {
+  if (!ctx || !clip_off || !hits || (!pcm && n_clips && clip_off[n_clips] > clip_off[0]))
+    return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  // argument checks come first in the reference too (src/fp_handler.c:247)
+  if (coefs < 1 || coefs > TIR_N_COEFS) return tir_fail(ctx, TIR_ERR_ARG, "Wrong coefs count. max[%d], coefs[%d]", TIR_N_COEFS, coefs);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  if (n_clips == 0) return TIR_OK;
+  const uint64_t base = clip_off[0], total = clip_off[n_clips] - base;
+  std::vector<uint64_t> rel((size_t)n_clips + 1), foff((size_t)n_clips + 1);
+  foff[0] = 0;
+  for (uint32_t c = 0; c <= n_clips; c++) rel[c] = clip_off[c] - base;
+  for (uint32_t c = 0; c < n_clips; c++) foff[c + 1] = foff[c] + tir_n_frames(rel[c + 1] - rel[c], ctx->cfg.hop);
+  const uint64_t F = foff[n_clips];
+  int rc;
+  if ((rc = tir_reserve(ctx, ctx->d_pcm, total * sizeof(int16_t) + 16))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_coef, std::max<uint64_t>(F, 1) * TIR_N_COEFS * sizeof(float)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_hits, (size_t)n_clips * sizeof(tir_hit)))) return rc;
+  if (total)
+    TIR_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcm.p, pcm + base, total * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = tir_extract_launch(ctx, (const int16_t *)ctx->d_pcm.p, total, rel.data(), n_clips, (float *)ctx->d_coef.p,
+                               nullptr, nullptr)))
+    return rc;
+  if ((rc = match_on_device(ctx, nullptr, (const float *)ctx->d_coef.p, foff.data(), n_clips, coefs, tolerance,
+                            freq_ignore_low, freq_ignore_high, (tir_hit *)ctx->d_hits.p)))
+    return rc;
+  TIR_CUDA(ctx, cudaMemcpyAsync(hits, ctx->d_hits.p, (size_t)n_clips * sizeof(tir_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TIR_OK;
+}
+
+int tir_merge_hits_dev(tir_ctx *ctx, const tir_hit *d_gathered, uint32_t n_shards, uint32_t n_queries, tir_hit *d_out) {
+  if (!ctx || !d_gathered || !d_out || n_shards == 0) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  if (n_queries == 0) return TIR_OK;
+  tir_merge_hits_kernel<<<(n_queries + 127) / 128, 128, 0, ctx->stream>>>(d_gathered, n_shards, n_queries, d_out);
+  ctx->launches++;
+  TIR_CUDA(ctx, cudaGetLastError());
+  return TIR_OK;
+}
+
+uint32_t tir_shard_of(const uint8_t uuid[16], uint32_t n_shards) {
+  if (!uuid || n_shards <= 1) return 0;
+  uint64_t h = 0xcbf29ce484222325ull; // FNV-1a over the 16 uuid bytes
+  for (int i = 0; i < 16; i++) h = (h ^ uuid[i]) * 0x100000001b3ull;
+  return (uint32_t)((h ^ (h >> 32)) % n_shards);
+}
+
+} // extern "C"

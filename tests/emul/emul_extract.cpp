@@ -68,3 +68,15 @@ extern "C" float emul_log10f(float x) {
   return tir_log10f_glibc(x, lt);
 }
 extern "C" int32_t emul_quantize(double y) { return tir_quantize_micro(y); }
+
+// count floats in [first, last] (bit patterns, stride `step`) where the model differs from libm
+extern "C" uint64_t emul_log10f_sweep(uint32_t first, uint32_t last, uint32_t step) {
+  const double2 lt[16] = TIR_LOGF_TAB_INIT;
+  uint64_t bad = 0;
+  for (uint64_t u = first; u <= last; u += step) {
+    float x = TIR_U2F((uint32_t)u);
+    float a = tir_log10f_glibc(x, lt), b = log10f(x);
+    bad += TIR_F2U(a) != TIR_F2U(b);
+  }
+  return bad;
+}

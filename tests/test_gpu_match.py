@@ -1,0 +1,181 @@
+"""GPU parity tests of the match path through the C ABI against the real SQLite running the
+reference's SQL text: identical winner uuid, match_count and frame_count on every query
+(bit-exact bar for integer work), ties and NULLs included."""
+import os
+
+import numpy as np
+import pytest
+
+from asterisk_tiresias_b200 import capi, synth, synth_db
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu_result(hit):
+    if hit["match_count"] == 0:
+        return None
+    return (capi.bytes_to_uuid(hit["uuid"]), int(hit["match_count"]), int(hit["frame_count"]))
+
+
+def sql_result(hit):
+    return None if hit is None else (hit["uuid"], hit["match_count"], hit["frame_count"])
+
+
+def test_golden_fixture(gpu_ctx):
+    g = np.load(os.path.join(GOLD, "match_golden.npz"))
+    off = g["db_off"]
+    v = synth_db.quantize_y(g["db_y"])
+    uu = np.stack([capi.uuid_to_bytes(str(u)) for u in g["db_uuid"]])
+    gpu_ctx.db_load(uu, off, v[:, 0], v[:, 1])
+    qo = g["q_off"].astype(np.int64)
+    for pi, (coefs, tol, lo, hi) in enumerate(g["params"]):
+        idx = np.nonzero(g["exp_param"] == pi)[0]
+        ys = [g["q_y"][qo[i]:qo[i + 1]] for i in idx]
+        foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+        hits = gpu_ctx.match(np.concatenate(ys), foff, int(coefs), float(tol), int(lo), int(hi))   # one batched call
+        for h, i in zip(hits, idx):
+            exp = None if g["exp_count"][i] == 0 else (str(g["exp_uuid"][i]), int(g["exp_count"][i]), int(g["exp_frames"][i]))
+            assert gpu_result(h) == exp, (pi, i)
+
+
+PARAMS = [(1, 0.001, -1, -1), (1, 0.01, -1, -1), (2, 0.5, -1, -1), (1, -1.0, 40, 70), (2, 2.0, 30, 60), (1, 0.0, -1, -1),
+          (2, 0.002, 50, -1), (1, 1e-6, -1, -1), (1, 1.5e-6, -1, -1)]
+
+
+@pytest.mark.parametrize("n_audio,null_frac,seed", [(40, 0.0, 1), (2500, 0.03, 2), (20000, 0.0, 3)])
+def test_differential_vs_sqlite(gpu_ctx, oracle, n_audio, null_frac, seed):
+    rng = np.random.default_rng(seed)
+    db = synth_db.make_db(n_audio, 5, 30 if n_audio > 10000 else 50, seed=seed, null_frac=null_frac)
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    assert gpu_ctx.db_stats() == (n_audio, sq.count_rows())
+    for coefs, tol, lo, hi in PARAMS:
+        if n_audio > 10000 and tol > 0.1:
+            continue          # keeps the SQLite side of the test in seconds
+        ys = []
+        for qi in range(8):
+            if qi % 3 == 0:
+                y = db[int(rng.integers(0, n_audio))][1].copy()
+                if qi % 6 == 0:
+                    y = y + rng.normal(0, 2e-4, y.shape)     # noisy copy
+            else:
+                y = synth_db.random_y(rng, int(rng.integers(1, 120)), null_frac=0.1 if qi % 4 == 1 else 0.0)
+            ys.append(y)
+        foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+        hits = gpu_ctx.match(np.concatenate(ys), foff, coefs, tol, lo, hi)
+        for y, h in zip(ys, hits):
+            exp = sq.search(y, coefs, tol, lo, hi, has_y=np.isfinite(y))
+            assert gpu_result(h) == sql_result(exp), (coefs, tol, lo, hi)
+
+
+def test_ties_resolve_to_greatest_uuid(gpu_ctx, oracle):
+    # many audios with identical rows, spread over several index blocks (> 16384 uuids)
+    n = 40000
+    rows = np.array([[17.0, 1.0], [18.0, 2.0], [16.0004, 3.0]])
+    uu = [synth.uuid_for(50_000_000 + i) for i in range(n)]
+    ub = np.stack([capi.uuid_to_bytes(u) for u in uu])
+    v = np.tile(synth_db.quantize_y(rows), (n, 1))
+    gpu_ctx.db_load(ub, np.arange(n + 1, dtype=np.uint64) * 3, v[:, 0], v[:, 1])
+    h = gpu_ctx.match(np.array([[17.3, 0], [18.2, 0], [16.9, 0], [5.0, 0]]))[0]
+    assert gpu_result(h) == (max(uu), 3, 4)
+    sq = oracle.SqliteDB()
+    for u in uu[:300]:
+        sq.add_audio(u, rows)
+    gpu_ctx.db_load(ub[:300], np.arange(301, dtype=np.uint64) * 3, v[:900, 0], v[:900, 1])
+    y = np.array([[17.3, 0], [18.2, 0], [16.9, 0], [5.0, 0]])
+    assert gpu_result(gpu_ctx.match(y)[0]) == sql_result(sq.search(y))
+
+
+def test_add_remove_follow_sqlite(gpu_ctx, oracle):
+    rng = np.random.default_rng(11)
+    db = synth_db.make_db(60, 10, 30, seed=9)
+    sq = oracle.SqliteDB()
+    gpu_ctx.db_load(*synth_db.db_arrays([]))
+    assert gpu_ctx.db_stats() == (0, 0)
+    assert gpu_ctx.match(db[0][1])[0]["match_count"] == 0
+    for u, y in db:
+        sq.add_audio(u, y)
+        v = synth_db.quantize_y(y)
+        gpu_ctx.db_add(capi.uuid_to_bytes(u), v[:, 0], v[:, 1])
+    queries = [db[i][1] for i in (0, 7, 33)] + [synth_db.random_y(rng, 40) for _ in range(4)]
+    for y in queries:
+        assert gpu_result(gpu_ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01))
+    for i in (7, 0, 59):
+        sq.delete_audio(db[i][0])
+        gpu_ctx.db_remove(capi.uuid_to_bytes(db[i][0]))
+    assert gpu_ctx.db_stats() == (57, sq.count_rows())
+    for y in queries:
+        assert gpu_result(gpu_ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01))
+    with pytest.raises(capi.TirError) as e:
+        gpu_ctx.db_remove(capi.uuid_to_bytes(db[7][0]))
+    assert e.value.code == capi.ERR_NOTFOUND
+
+
+def test_argument_rules(gpu_ctx):
+    db = synth_db.make_db(5, 5, 5, seed=4)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    for bad in (0, 3):
+        with pytest.raises(capi.TirError) as e:      # src/fp_handler.c:247 -> NULL
+            gpu_ctx.match(db[0][1], coefs=bad)
+        assert e.value.code == capi.ERR_ARG
+    h = gpu_ctx.match(np.zeros((0, 2)), np.array([0, 0], np.uint64))[0]
+    assert h["match_count"] == 0 and h["frame_count"] == 0
+
+
+def test_search_end_to_end_equals_oracle_chain(gpu_ctx, oracle):
+    """fp_search_fingerprint_info: PCM in, winner out.  Oracle chain = oracle extraction of the DB
+    clips -> SQLite ingest -> oracle extraction of the query -> SQLite search."""
+    plan = oracle.Plan()
+    pcm, off = synth.make_corpus(30, 3.0, first_index=3000)
+    sq = oracle.SqliteDB()
+    coef, vq = gpu_ctx.extract(pcm, off)
+    fo = np.concatenate([[0], np.cumsum((np.diff(off.astype(np.int64)) + 255) // 256)]).astype(np.uint64)
+    uu = [synth.uuid_for(777000 + i) for i in range(30)]
+    for i, u in enumerate(uu):
+        _, y, _ = plan.extract(pcm[int(off[i]):int(off[i + 1])])
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(np.stack([capi.uuid_to_bytes(u) for u in uu]), fo, vq[:, 0], vq[:, 1])
+    q_idx = [0, 5, 29, 13]
+    q_clips = [pcm[int(off[i]):int(off[i + 1])] for i in q_idx] + [synth.make_clip(99999, 3.0)]
+    qoff = np.zeros(len(q_clips) + 1, np.uint64); qoff[1:] = np.cumsum([c.size for c in q_clips])
+    for tol in (0.001, 0.05):
+        hits = gpu_ctx.search(np.concatenate(q_clips), qoff, tolerance=tol)
+        for c, h in zip(q_clips, hits):
+            _, y, _ = plan.extract(c)
+            assert gpu_result(h) == sql_result(sq.search(y, tolerance=tol, has_y=np.isfinite(y)))
+
+
+def test_shard_merge_equals_unsharded(gpu_ctx, oracle):
+    """DB split by uuid over S shards (S contexts on this one GPU), per-shard winners merged by
+    tir_merge_hits_dev == unsharded winner, for S in 1, 2, 4, 8."""
+    import torch
+    rng = np.random.default_rng(21)
+    db = synth_db.make_db(3000, 5, 20, seed=21)
+    for i in range(30):
+        db.append((synth.uuid_for(4_000_000 + i), db[i][1].copy()))      # ties across shards
+    ys = [db[int(rng.integers(0, len(db)))][1] for _ in range(6)] + [synth_db.random_y(rng, 50) for _ in range(6)]
+    foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    yall = np.concatenate(ys)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    want = gpu_ctx.match(yall, foff, tolerance=0.01)
+    for S in (2, 4, 8):
+        parts = [[] for _ in range(S)]
+        for u, y in db:
+            parts[capi.shard_of(capi.uuid_to_bytes(u), S)].append((u, y))
+        gathered = []
+        for part in parts:
+            c = capi.Context(device=0)
+            c.db_load(*synth_db.db_arrays(part))
+            gathered.append(c.match(yall, foff, tolerance=0.01))
+            c.close()
+        g = torch.from_numpy(np.concatenate(gathered).view(np.uint8)).cuda()
+        out = torch.zeros(len(ys) * 24, dtype=torch.uint8, device="cuda")
+        gpu_ctx.merge_hits_dev(g.data_ptr(), S, len(ys), out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(capi.HIT_DTYPE)
+        assert np.array_equal(got["match_count"], want["match_count"])
+        assert np.array_equal(got["uuid"], want["uuid"])
+        assert np.array_equal(got["frame_count"], want["frame_count"])
