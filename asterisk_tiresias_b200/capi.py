@@ -62,6 +62,10 @@ def lib():
         L.tir_launch_count.argtypes = [vp]
         if hasattr(L, "tir_db_load"):
             L.tir_db_load.argtypes = [vp, C.c_uint32, vp, u64p, vp, vp]
+            L.tir_db_load_dev.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_uint64]
+            L.tir_set_profiling.argtypes = [vp, C.c_int]
+            L.tir_last_kernel_ms.restype = C.c_float
+            L.tir_last_kernel_ms.argtypes = [vp, C.c_int]
             L.tir_db_add.argtypes = [vp, vp, vp, vp, C.c_uint32]
             L.tir_db_remove.argtypes = [vp, vp]
             L.tir_db_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -169,6 +173,16 @@ class Context:
         v2 = np.ascontiguousarray(v2, dtype=np.int32)
         assert row_off.size == uuids.shape[0] + 1 and v1.size == v2.size == int(row_off[-1])
         self._chk(lib().tir_db_load(self._h, uuids.shape[0], _p(uuids), _p(row_off), _p(v1), _p(v2)))
+
+    def db_load_dev(self, n_audio, d_uuid_ptr, d_row_off_ptr, d_v1_ptr, d_v2_ptr, n_rows):
+        self._chk(lib().tir_db_load_dev(self._h, n_audio, C.c_void_p(d_uuid_ptr), C.c_void_p(d_row_off_ptr),
+                                        C.c_void_p(d_v1_ptr), C.c_void_p(d_v2_ptr), n_rows))
+
+    def set_profiling(self, on=True):
+        lib().tir_set_profiling(self._h, 1 if on else 0)
+
+    def last_kernel_ms(self, which=0):
+        return float(lib().tir_last_kernel_ms(self._h, which))
 
     def db_add(self, uuid16, v1, v2):
         u = np.ascontiguousarray(uuid16, dtype=np.uint8)

@@ -112,6 +112,8 @@ int tir_open(const tir_cfg *cfg, tir_ctx **out) {
   if ((rc = upload(ctx, &ctx->d_tw_pass, ctx->tab.tw_pass))) return rc;
   if ((rc = upload(ctx, &ctx->d_tw_unt, ctx->tab.tw_unt))) return rc;
   if ((rc = upload(ctx, &ctx->d_tw32, ctx->tab.tw32))) return rc;
+  for (int w = 0; w < 2; w++)
+    for (int e = 0; e < 2; e++) TIR_CUDA(ctx, cudaEventCreate(&ctx->ev[w][e]));
   return TIR_OK;
 }
 
@@ -126,6 +128,9 @@ void tir_close(tir_ctx *ctx) {
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
   free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y);
   if (ctx->h_meta.p) cudaFreeHost(ctx->h_meta.p);
+  for (int w = 0; w < 2; w++)
+    for (int e = 0; e < 2; e++)
+      if (ctx->ev[w][e]) cudaEventDestroy(ctx->ev[w][e]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -133,6 +138,20 @@ void tir_close(tir_ctx *ctx) {
 const char *tir_last_error(tir_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 uint64_t tir_launch_count(tir_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void tir_set_profiling(tir_ctx *ctx, int on) {
+  if (ctx) ctx->profiling = on != 0;
+}
+
+float tir_last_kernel_ms(tir_ctx *ctx, int which) {
+  if (!ctx || which < 0 || which > 1 || !ctx->ev_valid[which]) return -1.f;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);
+  float ms = -1.f;
+  if (cudaEventSynchronize(ctx->ev[which][1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev[which][0], ctx->ev[which][1]) != cudaSuccess) return -1.f;
+  return ms;
+}
 
 int tir_get_tables(tir_ctx *ctx, float *window, float *filters, float *dct) {
   if (!ctx) return TIR_ERR_ARG;

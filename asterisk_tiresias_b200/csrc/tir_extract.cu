@@ -229,8 +229,13 @@ int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_sample
   }
   const uint32_t resident = (uint32_t)ctx->num_sms * 2u;
   const uint32_t grid = n_tiles < resident ? n_tiles : resident;
+  if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], ctx->stream));
   tir_extract_kernel<512><<<grid, C::NT, smem, ctx->stream>>>(a, ctx->tab.mel);
   TIR_CUDA(ctx, cudaGetLastError());
+  if (ctx->profiling) {
+    TIR_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], ctx->stream));
+    ctx->ev_valid[0] = true;
+  }
   ctx->launches++;
   return TIR_OK;
 }

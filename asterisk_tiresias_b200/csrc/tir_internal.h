@@ -26,6 +26,9 @@ struct tir_ctx {
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; // [which][begin/end]
+  bool ev_valid[2] = {false, false};
   TirHostTables tab;
   // device copies of the kernel-layout tables
   float2 *d_win2 = nullptr, *d_tw_pass = nullptr, *d_tw_unt = nullptr, *d_tw32 = nullptr;

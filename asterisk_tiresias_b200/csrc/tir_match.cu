@@ -509,6 +509,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     tir_qprep_kernel<false><<<n_queries, 128, 0, st>>>(d_y, nullptr, d_foff, mp, d_win, d_nw);
   ctx->launches++;
   if (db->n_blocks && db->n_indexed) {
+    if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     for (uint32_t q0 = 0; q0 < n_queries; q0 += 32768) { // grid.y limit
       dim3 grid(db->n_blocks, std::min<uint32_t>(32768, n_queries - q0));
       if (coefs >= 2)
@@ -521,6 +522,10 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
                                                                 d_win, d_nw, d_foff, d_best, q0);
       ctx->launches++;
     }
+    if (ctx->profiling) {
+      TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
+      ctx->ev_valid[1] = true;
+    }
   }
   tir_finalize_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(d_best, (const uint32_t *)db->order.p,
                                                                (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits);
@@ -531,41 +536,62 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
 
 extern "C" {
 
-int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off, const int32_t *v1,
-                const int32_t *v2) {
-  if (!ctx || (n_audio && (!uuid || !row_off))) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+static int db_load_common(tir_ctx *ctx, uint32_t n_audio, const void *uuid, const uint64_t *row_off, const int32_t *v1,
+                          const int32_t *v2, uint64_t rows, bool from_device) {
   int rc;
   if ((rc = ensure_db(ctx))) return rc;
   TirDb *db = ctx->db;
-  const uint64_t rows = n_audio ? row_off[n_audio] : 0;
-  if (n_audio && row_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "row_off[0] must be 0");
-  if (rows && (!v1 || !v2)) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
   if ((rc = grow_keep(ctx, db->uuids, (size_t)n_audio * 16 + 16, 0))) return rc;
   if ((rc = grow_keep(ctx, db->row_off, ((size_t)n_audio + 1) * 8, 0))) return rc;
   if ((rc = grow_keep(ctx, db->alive, (size_t)n_audio + 1, 0))) return rc;
   if ((rc = grow_keep(ctx, db->v1, rows * 4 + 4, 0))) return rc;
   if ((rc = grow_keep(ctx, db->v2, rows * 4 + 4, 0))) return rc;
   cudaStream_t st = ctx->stream;
+  const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (n_audio) {
-    TIR_CUDA(ctx, cudaMemcpyAsync(db->uuids.p, uuid, (size_t)n_audio * 16, cudaMemcpyHostToDevice, st));
-    TIR_CUDA(ctx, cudaMemcpyAsync(db->row_off.p, row_off, ((size_t)n_audio + 1) * 8, cudaMemcpyHostToDevice, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->uuids.p, uuid, (size_t)n_audio * 16, kind, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->row_off.p, row_off, ((size_t)n_audio + 1) * 8, kind, st));
     TIR_CUDA(ctx, cudaMemsetAsync(db->alive.p, 1, n_audio, st));
   }
   if (rows) {
-    TIR_CUDA(ctx, cudaMemcpyAsync(db->v1.p, v1, rows * 4, cudaMemcpyHostToDevice, st));
-    TIR_CUDA(ctx, cudaMemcpyAsync(db->v2.p, v2, rows * 4, cudaMemcpyHostToDevice, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->v1.p, v1, rows * 4, kind, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->v2.p, v2, rows * 4, kind, st));
+  }
+  // host mirrors of the small per-audio arrays (stats, add/remove)
+  db->h_row_off.assign((size_t)n_audio + 1, 0);
+  db->h_uuids.assign((size_t)n_audio * 16, 0);
+  if (n_audio) {
+    const cudaMemcpyKind back = from_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->h_row_off.data(), row_off, ((size_t)n_audio + 1) * 8, back, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(db->h_uuids.data(), uuid, (size_t)n_audio * 16, back, st));
   }
   TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  if (n_audio && (db->h_row_off[0] != 0 || db->h_row_off[n_audio] != rows))
+    return tir_fail(ctx, TIR_ERR_ARG, "row_off must start at 0 and end at the row count");
   db->n_audio = n_audio, db->n_rows = rows, db->n_alive = n_audio;
-  db->h_row_off.assign(row_off ? row_off : nullptr, row_off ? row_off + n_audio + 1 : nullptr);
-  if (!n_audio) db->h_row_off.assign(1, 0);
   db->h_alive.assign(n_audio, 1);
-  db->h_uuids.assign((const uint8_t *)uuid, (const uint8_t *)uuid + (size_t)n_audio * 16);
   db->by_uuid.clear(), db->lookup_ready = false;
   db->dirty = true;
   return db_build_index(ctx, db);
+}
+
+int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off, const int32_t *v1,
+                const int32_t *v2) {
+  if (!ctx || (n_audio && (!uuid || !row_off))) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  const uint64_t rows = n_audio ? row_off[n_audio] : 0;
+  if (rows && (!v1 || !v2)) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  return db_load_common(ctx, n_audio, uuid, row_off, v1, v2, rows, false);
+}
+
+int tir_db_load_dev(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*d_uuid)[16], const uint64_t *d_row_off,
+                    const int32_t *d_v1, const int32_t *d_v2, uint64_t n_rows) {
+  if (!ctx || (n_audio && (!d_uuid || !d_row_off)) || (n_rows && (!d_v1 || !d_v2)))
+    return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return db_load_common(ctx, n_audio, d_uuid, d_row_off, d_v1, d_v2, n_rows, true);
 }
 
 static void ensure_lookup(TirDb *db) {

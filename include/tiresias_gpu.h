@@ -98,6 +98,10 @@ int tir_get_tables(tir_ctx *ctx, float *window /*[win]*/, float *filters /*[n_fi
  * v1/v2[row_off[a] .. row_off[a+1]) in frame_idx order.  Replaces the current contents. */
 int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off,
                 const int32_t *v1, const int32_t *v2);
+/* Same from DEVICE arrays (uuid bytes, row offsets, micro-unit values already on this GPU, e.g. the
+ * output of tir_extract_dev); the library keeps its own copy. */
+int tir_db_load_dev(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*d_uuid)[16], const uint64_t *d_row_off,
+                    const int32_t *d_v1, const int32_t *d_v2, uint64_t n_rows);
 /* create_audio_fingerprint_info(): the rows of one new audio, src/fp_handler.c:538-575 */
 int tir_db_add(tir_ctx *ctx, const uint8_t uuid[16], const int32_t *v1, const int32_t *v2, uint32_t n_rows);
 /* delete from audio_fingerprint where audio_uuid=..., src/fp_handler.c:147 */
@@ -145,9 +149,13 @@ int tir_merge_hits_dev(tir_ctx *ctx, const tir_hit *d_gathered, uint32_t n_shard
 /* which shard (0..n_shards-1) owns a uuid */
 uint32_t tir_shard_of(const uint8_t uuid[16], uint32_t n_shards);
 
-/* bookkeeping for the benches: kernels launched by this context so far, and the device time of
- * the last tir_extract*() / tir_match*() kernels measured with CUDA events on ctx's stream (ms) */
+/* bookkeeping for the benches: kernels launched by this context so far; with profiling switched on
+ * the main extraction / match kernels are bracketed by CUDA events on ctx's stream and
+ * tir_last_kernel_ms() returns the device time of the most recent one (which: 0 = extraction
+ * kernel, 1 = match kernel; waits for it to finish; < 0 if none was recorded). */
 uint64_t tir_launch_count(tir_ctx *ctx);
+void tir_set_profiling(tir_ctx *ctx, int on);
+float tir_last_kernel_ms(tir_ctx *ctx, int which);
 
 #ifdef __cplusplus
 }
