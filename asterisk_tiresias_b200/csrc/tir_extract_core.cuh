@@ -38,7 +38,7 @@ struct TirMelParams {
   int16_t woff[TIR_MAX_FILTERS];    // offset into w[], multiple of 4
   uint8_t warp_nf[TIR_MEL_WARPS];   // filters handled by mel warp w
   uint8_t warp_filters[TIR_MEL_WARPS][TIR_MAX_FILTERS];
-  float4 w4[TIR_MAX_NNZ / 4];       // 0.5 * aubio filter weight (the 0.5 of the scaled FFT)
+  float4 w4[TIR_MAX_NNZ / 4];       // 2^-33 * aubio filter weight (scaled FFT and scaled sqrt)
   float dct[TIR_MAX_COEFS][TIR_MAX_FILTERS];
   float log_clamp;                  // (float)2e-42 : aubio VERY_SMALL_NUMBER
   int n_filters, n_coefs;
@@ -195,15 +195,17 @@ TIR_DEV void tir_pass2_load(const TirSmem<WIN> &sm, int tid, TirPass2Regs &rg) {
   }
 }
 
-// one untangle slot: U=Z[k], V=Z[M-k] (k <= M/2), -> |2X[k]|, |2X[M-k]|
+// one untangle slot: U=Z[k], V=Z[M-k] (k <= M/2), -> 2^32*|2X[k]|, 2^32*|2X[M-k]|
+// (the 2^32 of the scaled square root and the 2 of the scaled FFT are folded, exactly, into the
+// mel weights: w4 = filter * 2^-33)
 TIR_DEV void tir_untangle_mag(TirCpx U, TirCpx V, float2 w, float &mk, float &mmk) {
   TirCpx E2 = {TIR_FADD(U.r, V.r), TIR_FSUB(U.i, V.i)};
   TirCpx O2 = {TIR_FADD(U.i, V.i), TIR_FSUB(V.r, U.r)};
   TirCpx Tt = tir_cmul(O2, w.x, w.y);
   float pr = TIR_FADD(E2.r, Tt.r), pi = TIR_FADD(E2.i, Tt.i);
   float qr = TIR_FSUB(E2.r, Tt.r), qi = TIR_FSUB(E2.i, Tt.i);
-  mk = TIR_FSQRT(TIR_FADD(TIR_FMUL(pr, pr), TIR_FMUL(pi, pi)));
-  mmk = TIR_FSQRT(TIR_FADD(TIR_FMUL(qr, qr), TIR_FMUL(qi, qi)));
+  mk = TIR_FSQRT_SCALED64(TIR_FADD(TIR_FMUL(pr, pr), TIR_FMUL(pi, pi)));
+  mmk = TIR_FSQRT_SCALED64(TIR_FADD(TIR_FMUL(qr, qr), TIR_FMUL(qi, qi)));
 }
 
 template <int WIN>

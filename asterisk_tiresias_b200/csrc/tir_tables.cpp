@@ -159,7 +159,8 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
     if (nnz + len4 > TIR_MAX_NNZ) return false;
     mp.start[f] = (int16_t)(first < 0 ? 0 : first), mp.len[f] = (int16_t)len, mp.woff[f] = (int16_t)nnz;
     float *wdst = reinterpret_cast<float *>(mp.w4) + nnz;
-    for (int b = 0; b < len; b++) wdst[b] = 0.5f * filt[first + b];
+    // magnitudes arrive as 2^33 * |X[k]| (FFT scaled by 2, sqrt by 2^32); power-of-two scaling is exact
+    for (int b = 0; b < len; b++) wdst[b] = filt[first + b] * (1.0f / 8589934592.0f);
     nnz += len4;
   }
   for (int j = 0; j < n_coefs; j++)
