@@ -11,6 +11,9 @@ LIB = os.path.join(HERE, "libtiresias_gpu.so")
 SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_tables.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 unless told not to; every fused
+    # multiply-add of the extraction path is written explicitly (tir_fp.cuh)
+    "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-Xptxas", "-v",
 ]
 

@@ -74,9 +74,9 @@ uint64_t tir_n_frames(uint64_t n_samples, int hop) {
   return (n_samples + (uint64_t)hop - 1) / (uint64_t)hop;
 }
 
-static int upload(tir_ctx *ctx, float2 **dst, const std::vector<float2> &src) {
-  TIR_CUDA(ctx, cudaMalloc((void **)dst, src.size() * sizeof(float2)));
-  TIR_CUDA(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(float2), cudaMemcpyHostToDevice));
+static int upload(tir_ctx *ctx, float4 **dst, const std::vector<float4> &src) {
+  TIR_CUDA(ctx, cudaMalloc((void **)dst, src.size() * sizeof(float4)));
+  TIR_CUDA(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(float4), cudaMemcpyHostToDevice));
   return TIR_OK;
 }
 
@@ -108,10 +108,9 @@ int tir_open(const tir_cfg *cfg, tir_ctx **out) {
     ctx->own_stream = true;
   }
   int rc;
-  if ((rc = upload(ctx, &ctx->d_win2, ctx->tab.win2))) return rc;
-  if ((rc = upload(ctx, &ctx->d_tw_pass, ctx->tab.tw_pass))) return rc;
-  if ((rc = upload(ctx, &ctx->d_tw_unt, ctx->tab.tw_unt))) return rc;
-  if ((rc = upload(ctx, &ctx->d_tw32, ctx->tab.tw32))) return rc;
+  if ((rc = upload(ctx, &ctx->d_win4, ctx->tab.win4))) return rc;
+  if ((rc = upload(ctx, &ctx->d_twp4, ctx->tab.twp4))) return rc;
+  if ((rc = upload(ctx, &ctx->d_twu4, ctx->tab.twu4))) return rc;
   for (int w = 0; w < 2; w++)
     for (int e = 0; e < 2; e++) TIR_CUDA(ctx, cudaEventCreate(&ctx->ev[w][e]));
   return TIR_OK;
@@ -124,7 +123,7 @@ void tir_close(tir_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   }
   if (ctx->db) tir_db_destroy(ctx->db);
-  cudaFree(ctx->d_win2), cudaFree(ctx->d_tw_pass), cudaFree(ctx->d_tw_unt), cudaFree(ctx->d_tw32);
+  cudaFree(ctx->d_win4), cudaFree(ctx->d_twp4), cudaFree(ctx->d_twu4);
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
   free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y);
   if (ctx->h_meta.p) cudaFreeHost(ctx->h_meta.p);

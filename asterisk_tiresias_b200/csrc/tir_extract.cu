@@ -24,11 +24,12 @@ struct __align__(16) TirTile {
 struct TirExtractArgs {
   const int16_t *pcm;
   const TirTile *tiles; // [n_tiles]
-  const float2 *win2, *tw_pass, *tw_unt;
+  const float4 *win4, *twp4, *twu4;
   float *coef;
   int32_t *vq;
   uint32_t n_tiles;
-  uint32_t pcm_aligned16; // base pointer is 16-byte aligned
+  uint32_t pcm_aligned8; // base pointer is 8-byte aligned
+  float2 neg_zero;       // (-0, -0): see tir_pmulx
 };
 
 __device__ const double2 k_logf_tab[16] = TIR_LOGF_TAB_INIT;
@@ -66,116 +67,132 @@ __device__ __forceinline__ TirTile tir_load_tile_desc(const TirTile *p) {
   return t;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// P0: (T+1) hops of the clip -> buf (asynchronously where the 16-byte vector lies inside the clip);
-// samples outside the clip are zeros (the first hop of a clip sees the all-zero pvoc history, the
-// last hop is zero padded: new_aubio_pvoc / aubio_source_do)
+// P0: (T+1) hops of the clip -> buf, 8 bytes (4 samples) per copy, asynchronously where the four
+// samples lie inside the clip and are 8-byte aligned; samples outside the clip are zeros (the first
+// hop of a clip sees the all-zero pvoc history, the last hop is zero padded: new_aubio_pvoc /
+// aubio_source_do).  Hop chunk c of the tile lands at buf[c * PCH ...]: lane = frame reads of P1
+// then have a stride of PCH 8-byte units = 2 banks (mod 32), conflict free.
+// Thread tid copies unit p = tid % UPC of chunks tid / UPC, + NT / UPC, ...
 template <int WIN>
-__device__ __forceinline__ void tir_issue_tile_load(uint32_t *buf, const int16_t *__restrict__ pcm, const TirTile &td,
+__device__ __forceinline__ void tir_issue_tile_load(uint2 *buf, const int16_t *__restrict__ pcm, const TirTile &td,
                                                     bool base_aligned, int tid) {
   using C = TirCfg<WIN>;
-  constexpr int VPC = C::HOP / 8; // 16-byte vectors per hop chunk
-  constexpr int TOTAL = (C::T + 1) * VPC;
+  constexpr int UPC = C::HOP / 4;       // 8-byte units per hop chunk
+  constexpr int CSTEP = C::NT / UPC;    // chunks advanced per iteration (4)
+  static_assert(C::NT % UPC == 0, "thread <-> unit mapping");
   const int16_t *clip = pcm + td.c0;
-  const bool aligned = base_aligned && ((td.c0 & 7) == 0);
+  const bool aligned = base_aligned && ((td.c0 & 3) == 0);
   const int64_t nsamp = td.nsamp;
-  const int64_t s_first = ((int64_t)td.f0 - 1) * C::HOP;
-#pragma unroll 1
-  for (int v = tid; v < TOTAL; v += C::NT) {
-    const int chunk = v / VPC, iv = v % VPC;
-    const int64_t s = s_first + (int64_t)chunk * C::HOP + iv * 8;
-    uint32_t *dst = buf + chunk * C::PCM_STRIDE_W + iv * 4;
-    if (aligned && s >= 0 && s + 8 <= nsamp) {
-      cp_async16(dst, clip + s);
-    } else {
-      uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (s + 8 > 0 && s < nsamp) {
-        uint32_t h[8];
+  const int p = tid % UPC;
+  int chunk = tid / UPC;
+  int64_t s = ((int64_t)td.f0 - 1 + chunk) * C::HOP + 4 * p;
+  uint2 *dst = buf + chunk * C::PCH + p;
+  const bool interior = aligned && td.f0 >= 1 && ((int64_t)td.f0 + C::T) * C::HOP <= nsamp; // CTA-uniform
+  if (interior) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
+    for (int i = 0; i < (C::T + 1 + CSTEP - 1) / CSTEP; i++) {
+      if (chunk + i * CSTEP <= C::T) cp_async8(dst + i * CSTEP * C::PCH, clip + s + (int64_t)i * CSTEP * C::HOP);
+    }
+  } else {
+#pragma unroll 1
+    for (; chunk <= C::T; chunk += CSTEP, s += (int64_t)CSTEP * C::HOP, dst += CSTEP * C::PCH) {
+      if (aligned && s >= 0 && s + 4 <= nsamp) {
+        cp_async8(dst, clip + s);
+      } else {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
           const int64_t i = s + e;
           h[e] = (i >= 0 && i < nsamp) ? (uint32_t)(uint16_t)__ldg(clip + i) : 0u;
         }
-        val = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+        *dst = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
       }
-      *reinterpret_cast<uint4 *>(dst) = val;
     }
   }
   cp_async_commit();
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(TirCfg<WIN>::NT, 2)
+__device__ __forceinline__ void tir_pass1(TirSmem<WIN> &sm, const uint2 *pcm, int role, int lane, TirP2 nz) {
+  if constexpr (WIN == 512) tir_pass1_512(sm, pcm, role, lane, nz);
+  else tir_pass1_1024(sm, pcm, role, lane, nz);
+}
+
+// Per tile: P1 | sync | P2 load | sync | P2 compute | sync | P3 (+ wait for the next tile's PCM) |
+// sync | P4 (coefficient warps only, no barrier after it: it overlaps the next tile's P1).
+template <int WIN>
+__global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     tir_extract_kernel(const __grid_constant__ TirExtractArgs a, const __grid_constant__ TirMelParams mp) {
   using C = TirCfg<WIN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TirSmem<WIN> &sm = *reinterpret_cast<TirSmem<WIN> *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler
-  const bool base_aligned = a.pcm_aligned16 != 0;
+  const bool base_aligned = a.pcm_aligned8 != 0;
+  const TirP2 nz = tir_pmk(a.neg_zero.x, a.neg_zero.y);
 
   uint32_t tile = blockIdx.x; // grid <= n_tiles
   TirTile cur = tir_load_tile_desc(a.tiles + tile);
   tir_issue_tile_load<WIN>(sm.pcm[0], a.pcm, cur, base_aligned, tid);
-  TirTile nxt = cur;
   bool have_nxt = tile + gridDim.x < a.n_tiles;
+  TirTile nxt = cur;
   if (have_nxt) nxt = tir_load_tile_desc(a.tiles + tile + gridDim.x);
 
-  for (int i = tid; i < C::M; i += C::NT) sm.win2[i] = a.win2[i];
-  for (int i = tid; i < C::N1 * 16; i += C::NT) sm.tw_pass[i] = a.tw_pass[i];
-  for (int i = tid; i < 16 * C::TPF; i += C::NT) sm.tw_unt[i] = a.tw_unt[i];
+  for (int i = tid; i < 16 * C::NW; i += C::NT) sm.win4[i] = a.win4[i], sm.twp4[i] = a.twp4[i];
+  for (int i = tid; i < C::NW * 8; i += C::NT) sm.twu4[i] = a.twu4[i];
   if (tid < 16) sm.logtab[tid] = k_logf_tab[tid];
-  // pad words of the exchange buffer are never written by P1 but may be read (times a zero
-  // weight) by the padded mel loop: make sure they are finite
+  // rows of the magnitude buffer that P2 never writes (bins 0, M and the rows the zero padded mel
+  // loop may touch beyond M) must hold finite values
   for (int i = tid; i < TirSmem<WIN>::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
+  cp_async_wait_all();
+  __syncthreads();
 
   int b = 0;
   for (;;) {
-    cp_async_wait_all();
-    __syncthreads(); // pcm[b] is complete; the previous tile's log-mel values (in pcm[b^1]) are consumed
-    TirTile nn = nxt;
-    bool have_nn = false;
-    if (have_nxt) {
-      tir_issue_tile_load<WIN>(sm.pcm[b ^ 1], a.pcm, nxt, base_aligned, tid); // streams in under P1..P4
-      have_nn = tile + 2 * gridDim.x < a.n_tiles;
-      if (have_nn) nn = tir_load_tile_desc(a.tiles + tile + 2 * gridDim.x);
-    }
-    tir_pass1<WIN>(sm, sm.pcm[b], tid);
+    // pcm[b] holds the current tile; pcm[b^1] was consumed by the previous tile's P1
+    if (have_nxt) tir_issue_tile_load<WIN>(sm.pcm[b ^ 1], a.pcm, nxt, base_aligned, tid); // streams in under P1..P3
+    tir_pass1<WIN>(sm, sm.pcm[b], warp, lane, nz);
     __syncthreads();
     TirPass2Regs rg;
-    tir_pass2_load<WIN>(sm, tid, rg);
+    tir_pass2_load<WIN>(sm, warp, lane, rg);
     __syncthreads(); // the magnitudes overwrite the exchange buffer
-    tir_pass2_compute<WIN>(sm, tid, rg);
+    if (warp == 0) tir_pass2_compute<WIN, true>(sm, warp, lane, rg, nz);
+    else tir_pass2_compute<WIN, false>(sm, warp, lane, rg, nz);
     __syncthreads();
-    float *lg = reinterpret_cast<float *>(sm.pcm[b]); // P1 is done with this buffer
-    tir_mel_phase(sm.xch, lg, sm.logtab, mp, warp, lane);
-    __syncthreads();
+    tir_mel_phase(sm.xch, sm.lg, sm.logtab, mp, warp, lane, nz);
+    cp_async_wait_all();
+    __syncthreads(); // log-mel values complete; the next tile's PCM has landed
     if (warp < mp.n_coefs && lane < cur.nvalid) {
       float c;
       int32_t v;
-      tir_dct_phase(lg, mp, warp, tir_col_of_frame<WIN>(lane), c, v);
+      tir_dct_phase(sm.lg, mp, warp, lane, c, v);
       const uint64_t o = (cur.out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
       if (a.coef) a.coef[o] = c;
       if (a.vq) a.vq[o] = v;
     }
     if (!have_nxt) break;
-    cur = nxt, nxt = nn, have_nxt = have_nn, tile += gridDim.x, b ^= 1;
+    tile += gridDim.x;
+    cur = nxt, b ^= 1;
+    have_nxt = tile + gridDim.x < a.n_tiles;
+    if (have_nxt) nxt = tir_load_tile_desc(a.tiles + tile + gridDim.x);
   }
 }
 
-size_t tir_extract_smem_bytes(int win) { return win == 512 ? sizeof(TirSmem<512>) : 0; }
+size_t tir_extract_smem_bytes(int win) {
+  return win == 512 ? sizeof(TirSmem<512>) : win == 1024 ? sizeof(TirSmem<1024>) : 0;
+}
 
-int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
-                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames) {
-  (void)total_samples;
-  if (ctx->cfg.win != 512) return tir_fail(ctx, TIR_ERR_ARG, "extraction kernel is built for win 512 / hop 256");
-  using C = TirCfg<512>;
+template <int WIN>
+static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,
+                                float *d_coef, int32_t *d_vq, uint64_t *n_frames) {
+  using C = TirCfg<WIN>;
   // ---- host-side tile bookkeeping (metadata only) -> one pinned staging buffer -> device
   const size_t nc1 = (size_t)n_clips + 1;
   std::vector<uint64_t> frame_off(nc1);
@@ -216,21 +233,22 @@ int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_sample
   TirExtractArgs a;
   a.pcm = d_pcm;
   a.tiles = d_tiles;
-  a.win2 = ctx->d_win2, a.tw_pass = ctx->d_tw_pass, a.tw_unt = ctx->d_tw_unt;
+  a.win4 = ctx->d_win4, a.twp4 = ctx->d_twp4, a.twu4 = ctx->d_twu4;
   a.coef = d_coef, a.vq = d_vq;
   a.n_tiles = n_tiles;
-  a.pcm_aligned16 = (((uintptr_t)d_pcm) & 15) == 0;
+  a.pcm_aligned8 = (((uintptr_t)d_pcm) & 7) == 0;
+  a.neg_zero = make_float2(-0.0f, -0.0f);
 
-  const size_t smem = sizeof(TirSmem<512>);
+  const size_t smem = sizeof(TirSmem<WIN>);
   static bool attr_set = false;
   if (!attr_set) {
-    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_extract_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_extract_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const uint32_t resident = (uint32_t)ctx->num_sms * 2u;
+  const uint32_t resident = (uint32_t)ctx->num_sms * (uint32_t)C::CTAS_PER_SM;
   const uint32_t grid = n_tiles < resident ? n_tiles : resident;
   if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], ctx->stream));
-  tir_extract_kernel<512><<<grid, C::NT, smem, ctx->stream>>>(a, ctx->tab.mel);
+  tir_extract_kernel<WIN><<<grid, C::NT, smem, ctx->stream>>>(a, ctx->tab.mel);
   TIR_CUDA(ctx, cudaGetLastError());
   if (ctx->profiling) {
     TIR_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], ctx->stream));
@@ -238,4 +256,12 @@ int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_sample
   }
   ctx->launches++;
   return TIR_OK;
+}
+
+int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
+                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames) {
+  (void)total_samples;
+  if (ctx->cfg.win == 512) return tir_extract_launch_t<512>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames);
+  if (ctx->cfg.win == 1024) return tir_extract_launch_t<1024>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames);
+  return tir_fail(ctx, TIR_ERR_ARG, "extraction kernels exist for win 512 / hop 256 and win 1024 / hop 512");
 }

@@ -4,278 +4,314 @@
 // (src/fp_handler.c:632-661): aubio_source_do -> aubio_pvoc_do -> aubio_mfcc_do ->
 // 10*log10(fabs(c)) -> "%f" (src/db_ctx_handler.c:480).
 //
-// One CTA works on a TILE of T consecutive frames of one clip.  Phases (a __syncthreads()
-// between each; the phase bodies below are written per thread so that the CPU tests can run the
-// very same code thread by thread, tests/emul):
-//   P0 load     (T+1) hops of PCM16 -> shared memory (each sample is read from HBM once)
-//   P1 pass1    TPF threads per frame: s16 -> f32, hanningz window, fvec_shift (an index
-//               permutation), even/odd packing, DFT_N1 over n1 in registers, twiddle, -> exchange
-//   P2 pass2    load two rows (k1, N1-k1) of the exchange buffer into registers         [sync]
-//               DFT16 x2, real untangling in registers, sqrt(re^2+im^2) -> magnitudes (aliases
-//               the exchange buffer)
-//   P3 mel      lane = frame, warp = filter list: banded Slaney matvec (sequential float adds in
-//               bin order, like fmat_vecmul), clamp 2e-42, glibc-exact log10f
-//   P4 dct      lane = frame, warp = coefficient: sequential 40-term DCT row, 10*log10|c| in
-//               double, "%f" quantisation, store
+// One CTA works on a TILE of 32 consecutive frames of one clip.  In every phase LANE = FRAME and
+// WARP = ROLE (a column pair / a row pair / a filter list), so table values are warp-uniform
+// broadcasts, every shared-memory access has lane stride 1 (or one 8-byte unit) and is bank-conflict
+// free without padding, and the one irregular role (FFT rows 0 and N1/2) is a warp-uniform code
+// path instead of per-lane selects.  Phases (a __syncthreads() between each; the bodies below are
+// written per (role, lane) so that the CPU tests can run the very same code, tests/emul):
+//   P0 load     33 hops of PCM16 -> shared memory (each sample is read from HBM once)
+//   P1 pass1    role = column pair (win 512) / column (win 1024): s16 -> f32, hanningz window,
+//               fvec_shift (an index permutation), even/odd packing, DFT_N1 over n1 in registers,
+//               twiddle W_M^(n2*k1) -> exchange buffer
+//   P2 pass2    role = row pair (k1, N1-k1): load both rows into registers             [sync]
+//               DFT16 over n2, real untangling, sqrt(re^2+im^2) -> magnitudes (alias the exchange)
+//   P3 mel      role = list of filter pairs: banded Slaney matvec (sequential float adds in bin
+//               order, like fmat_vecmul), clamp 2e-42, glibc-exact log10f
+//   P4 dct      role = coefficient: sequential 40-term DCT row, 10*log10|c| in double, "%f"
+// All float32 arithmetic of P1..P3 runs on TirP2 pairs (FADD2/FMUL2/FFMA2, tir_fp.cuh); the two
+// lanes of a pair are two columns (P1), two rows (P2), two untangle slots (P2) or two filters (P3).
 // The float32 FFT is "TIR-FFT" (operation order documented in DESIGN.md, and restated
 // independently by the CPU oracle).
 #pragma once
 #include "tir_fp.cuh"
 
 #define TIR_MAX_FILTERS 40
+#define TIR_MAX_PAIRS 20
 #define TIR_MAX_COEFS 2
-#define TIR_MAX_NNZ 2048
-#define TIR_MEL_WARPS 8
+#define TIR_MAX_W4 768
+#define TIR_MAX_WARPS 16
+#define TIR_TILE 32 // frames per tile == lanes per warp
 
-struct TirCpx {
-  float r, i;
+struct TirC2 { // two complex numbers: lane lo and lane hi
+  TirP2 r, i;
 };
 
-// ---- kernel-parameter block (lives in the constant bank; warp-uniform reads are free operands)
+// ---- kernel-parameter block (lives in the constant bank; warp-uniform reads are cheap LDCs)
 struct TirMelParams {
-  int16_t start[TIR_MAX_FILTERS];   // first bin with non-zero weight
-  int16_t len[TIR_MAX_FILTERS];     // number of bins (weights are zero padded to a multiple of 4)
-  int16_t woff[TIR_MAX_FILTERS];    // offset into w[], multiple of 4
-  uint8_t warp_nf[TIR_MEL_WARPS];   // filters handled by mel warp w
-  uint8_t warp_filters[TIR_MEL_WARPS][TIR_MAX_FILTERS];
-  float4 w4[TIR_MAX_NNZ / 4];       // 2^-33 * aubio filter weight (scaled FFT and scaled sqrt)
+  int16_t start_a[TIR_MAX_PAIRS], start_b[TIR_MAX_PAIRS]; // first bin with non-zero weight of filter a / b
+  int16_t steps[TIR_MAX_PAIRS];                           // float4 weight records (two bins each)
+  int16_t woff[TIR_MAX_PAIRS];                            // first record in w4[]
+  int8_t filt_a[TIR_MAX_PAIRS], filt_b[TIR_MAX_PAIRS];    // filter ids (b = -1: none)
+  uint8_t warp_np[TIR_MAX_WARPS];                         // pairs handled by mel warp w
+  uint8_t warp_pairs[TIR_MAX_WARPS][TIR_MAX_PAIRS];
+  // (wa[b], wb[b], wa[b+1], wb[b+1]) * 2^-33 : aubio filter weights of the two filters of a pair,
+  // zero padded; 2^-33 undoes the scaled FFT (2x) and the scaled square root (2^32 x), exactly
+  float4 w4[TIR_MAX_W4];
   float dct[TIR_MAX_COEFS][TIR_MAX_FILTERS];
-  float log_clamp;                  // (float)2e-42 : aubio VERY_SMALL_NUMBER
-  int n_filters, n_coefs;
+  float log_clamp; // (float)2e-42 : aubio VERY_SMALL_NUMBER
+  int n_filters, n_coefs, n_pairs;
 };
 
 static_assert(sizeof(float4) == 16 && alignof(float4) == 16 && alignof(float2) == 8 && alignof(double2) == 16,
               "vector types must have the CUDA layout in every translation unit");
 static_assert(sizeof(TirMelParams) % 16 == 0, "TirMelParams layout");
 
-template <int WIN>
-struct TirCfg;
-
-template <>
-struct TirCfg<512> {
-  static constexpr int WIN = 512, HOP = 256, M = 256, N1 = 16, TPF = 8;
-  static constexpr int T = 32;                 // frames per tile
-  static constexpr int NT = T * TPF;           // threads per CTA (256)
-  static constexpr int PCM_STRIDE_W = 136;     // 32-bit words per hop chunk (128 + 8 pad)
-  static constexpr int XCH_ROW = 17;           // float2 per k1 row (16 + 1 pad)
-  static constexpr int XCH_FRAME_W = 560;      // words per frame (N1*XCH_ROW*2 = 544, +16)
-  static constexpr int NORM_STRIDE = 33;       // words per bin row of the magnitude buffer (32 frames + 1 pad)
+template <int WIN_>
+struct TirCfg {
+  static_assert(WIN_ == 512 || WIN_ == 1024, "plans: 512/256 and 1024/512 (src/fp_handler.c:33-36)");
+  static constexpr int WIN = WIN_, HOP = WIN_ / 2, M = WIN_ / 2;
+  static constexpr int N1 = M / 16;            // FFT_M = N1 x 16: n = 16*n1 + n2, k = k1 + N1*k2
+  static constexpr int NW = N1 / 2;            // warps per CTA = roles per phase (8 / 16)
+  static constexpr int T = TIR_TILE;           // frames per tile
+  static constexpr int NT = NW * 32;           // threads per CTA
+  static constexpr int PCH = HOP / 4 + 1;      // 8-byte units per hop chunk (+1: lane stride 2 banks mod 32)
+  static constexpr int CTAS_PER_SM = WIN_ == 512 ? 2 : 1;
 };
 
 template <int WIN>
 struct TirSmem {
   using C = TirCfg<WIN>;
-  static constexpr int PCM_WORDS = ((C::T + 1) * C::PCM_STRIDE_W + 3) & ~3; // keep what follows 16-byte aligned
-  static constexpr int XCH_WORDS = C::T * C::XCH_FRAME_W;
-  static constexpr int NORM_WORDS = (C::M + 1) * C::NORM_STRIDE;
-  static_assert(NORM_WORDS <= XCH_WORDS, "magnitudes alias the exchange buffer");
-  static_assert(XCH_WORDS % 4 == 0 && C::XCH_FRAME_W % 2 == 0, "float2 / double2 alignment of the members below");
-  static_assert(TIR_MAX_FILTERS * 32 <= PCM_WORDS, "log-mel values alias the consumed PCM buffer");
-  uint32_t pcm[2][PCM_WORDS];   // double buffered: tile N+1 streams in (cp.async) while tile N computes
+  static constexpr int PCM_UNITS = (C::T + 1) * C::PCH;
+  static constexpr int XCH_WORDS = 2 * C::N1 * 16 * 32; // [plane re/im][k1][n2][frame]
+  static_assert((C::M + 1 + 64) * 32 <= XCH_WORDS, "magnitudes (+ padded mel reads) alias the exchange buffer");
+  uint2 pcm[2][PCM_UNITS];   // double buffered: tile N+1 streams in (cp.async) while tile N computes
   float xch[XCH_WORDS];
-  float2 win2[C::M];            // window pairs in z[] order, pre-scaled by 2^-15
-  float2 tw_pass[C::N1 * 16];   // [k1][n2]  W_M^(n2*k1)
-  float2 tw_unt[16 * C::TPF];   // [slot][t] W_{2M}^k
+  float lg[TIR_MAX_FILTERS * 32];
+  float4 win4[16 * C::NW];   // window pairs of the two lanes, pre-scaled by 2^-15
+  float4 twp4[16 * C::NW];   // pass-1 twiddles of the two lanes
+  float4 twu4[C::NW * 8];    // untangle twiddles [role][slot pair]
   double2 logtab[16];
 };
 
-// ---- complex helpers, TIR-FFT operation order -------------------------------------------------
-TIR_DEV TirCpx tir_cmul(TirCpx x, float wr, float wi) {
-  TirCpx o;
-  o.r = TIR_FFMA(-x.i, wi, TIR_FMUL(x.r, wr));
-  o.i = TIR_FFMA(x.i, wr, TIR_FMUL(x.r, wi));
+#define TIR_XI(N1, plane, k1, n2, f) ((((plane) * (N1) + (k1)) * 16 + (n2)) * 32 + (f))
+#define TIR_NORM_IDX(bin, f) ((bin) * 32 + (f))
+
+// ---- complex helpers, TIR-FFT operation order, two lanes at a time -----------------------------
+TIR_DEV TirC2 tir_cmul(TirC2 x, TirP2 wr, TirP2 wi) {
+  TirC2 o;
+  o.r = tir_pfma(tir_pneg(x.i), wi, tir_pmul(x.r, wr));
+  o.i = tir_pfma(x.i, wr, tir_pmul(x.r, wi));
   return o;
 }
 
-TIR_DEV void tir_dft4(TirCpx a0, TirCpx a1, TirCpx a2, TirCpx a3, TirCpx &A0, TirCpx &A1, TirCpx &A2,
-                      TirCpx &A3) {
-  TirCpx s0 = {TIR_FADD(a0.r, a2.r), TIR_FADD(a0.i, a2.i)}, d0 = {TIR_FSUB(a0.r, a2.r), TIR_FSUB(a0.i, a2.i)};
-  TirCpx s1 = {TIR_FADD(a1.r, a3.r), TIR_FADD(a1.i, a3.i)}, d1 = {TIR_FSUB(a1.r, a3.r), TIR_FSUB(a1.i, a3.i)};
-  A0.r = TIR_FADD(s0.r, s1.r), A0.i = TIR_FADD(s0.i, s1.i);
-  A2.r = TIR_FSUB(s0.r, s1.r), A2.i = TIR_FSUB(s0.i, s1.i);
-  A1.r = TIR_FADD(d0.r, d1.i), A1.i = TIR_FSUB(d0.i, d1.r);
-  A3.r = TIR_FSUB(d0.r, d1.i), A3.i = TIR_FADD(d0.i, d1.r);
+TIR_DEV void tir_dft4(TirC2 a0, TirC2 a1, TirC2 a2, TirC2 a3, TirC2 &A0, TirC2 &A1, TirC2 &A2, TirC2 &A3) {
+  TirC2 s0 = {tir_padd(a0.r, a2.r), tir_padd(a0.i, a2.i)}, d0 = {tir_psub(a0.r, a2.r), tir_psub(a0.i, a2.i)};
+  TirC2 s1 = {tir_padd(a1.r, a3.r), tir_padd(a1.i, a3.i)}, d1 = {tir_psub(a1.r, a3.r), tir_psub(a1.i, a3.i)};
+  A0.r = tir_padd(s0.r, s1.r), A0.i = tir_padd(s0.i, s1.i);
+  A2.r = tir_psub(s0.r, s1.r), A2.i = tir_psub(s0.i, s1.i);
+  A1.r = tir_padd(d0.r, d1.i), A1.i = tir_psub(d0.i, d1.r);
+  A3.r = tir_psub(d0.r, d1.i), A3.i = tir_padd(d0.i, d1.r);
 }
 
 #define TIR_C1 0.92387953251128674f
 #define TIR_S1 0.38268343236508977f
 #define TIR_H 0.70710678118654752f
 
-// in-place 16-point DFT, x[n] -> X[k], natural order in and out
-TIR_DEV void tir_dft16(TirCpx (&x)[16]) {
-  TirCpx y[4][4];
+// in-place 16-point DFT of both lanes, x[n] -> X[k], natural order in and out
+TIR_DEV void tir_dft16(TirC2 (&x)[16], TirP2 nz) {
+  TirC2 y[4][4];
 #pragma unroll
   for (int n2 = 0; n2 < 4; n2++) tir_dft4(x[n2], x[n2 + 4], x[n2 + 8], x[n2 + 12], y[n2][0], y[n2][1], y[n2][2], y[n2][3]);
-  TirCpx v;
+  TirC2 v;
+  const TirP2 h = tir_pbc(TIR_H);
   // W16^(n2*k1)
-  y[1][1] = tir_cmul(y[1][1], TIR_C1, -TIR_S1);
-  v = y[1][2], y[1][2].r = TIR_FMUL(TIR_FADD(v.r, v.i), TIR_H), y[1][2].i = TIR_FMUL(TIR_FSUB(v.i, v.r), TIR_H);
-  y[1][3] = tir_cmul(y[1][3], TIR_S1, -TIR_C1);
-  v = y[2][1], y[2][1].r = TIR_FMUL(TIR_FADD(v.r, v.i), TIR_H), y[2][1].i = TIR_FMUL(TIR_FSUB(v.i, v.r), TIR_H);
-  v = y[2][2], y[2][2].r = v.i, y[2][2].i = -v.r;
-  v = y[2][3], y[2][3].r = TIR_FMUL(TIR_FSUB(v.i, v.r), TIR_H), y[2][3].i = -TIR_FMUL(TIR_FADD(v.r, v.i), TIR_H);
-  y[3][1] = tir_cmul(y[3][1], TIR_S1, -TIR_C1);
-  v = y[3][2], y[3][2].r = TIR_FMUL(TIR_FSUB(v.i, v.r), TIR_H), y[3][2].i = -TIR_FMUL(TIR_FADD(v.r, v.i), TIR_H);
-  y[3][3] = tir_cmul(y[3][3], -TIR_C1, TIR_S1);
+  y[1][1] = tir_cmul(y[1][1], tir_pbc(TIR_C1), tir_pbc(-TIR_S1));
+  v = y[1][2], y[1][2].r = tir_pmulx(tir_padd(v.r, v.i), h, nz), y[1][2].i = tir_pmulx(tir_psub(v.i, v.r), h, nz);
+  y[1][3] = tir_cmul(y[1][3], tir_pbc(TIR_S1), tir_pbc(-TIR_C1));
+  v = y[2][1], y[2][1].r = tir_pmulx(tir_padd(v.r, v.i), h, nz), y[2][1].i = tir_pmulx(tir_psub(v.i, v.r), h, nz);
+  v = y[2][2], y[2][2].r = v.i, y[2][2].i = tir_pneg(v.r);
+  v = y[2][3], y[2][3].r = tir_pmulx(tir_psub(v.i, v.r), h, nz), y[2][3].i = tir_pneg(tir_pmulx(tir_padd(v.r, v.i), h, nz));
+  y[3][1] = tir_cmul(y[3][1], tir_pbc(TIR_S1), tir_pbc(-TIR_C1));
+  v = y[3][2], y[3][2].r = tir_pmulx(tir_psub(v.i, v.r), h, nz), y[3][2].i = tir_pneg(tir_pmulx(tir_padd(v.r, v.i), h, nz));
+  y[3][3] = tir_cmul(y[3][3], tir_pbc(-TIR_C1), tir_pbc(TIR_S1));
 #pragma unroll
   for (int k1 = 0; k1 < 4; k1++) tir_dft4(y[0][k1], y[1][k1], y[2][k1], y[3][k1], x[k1], x[k1 + 4], x[k1 + 8], x[k1 + 12]);
 }
 
-// ---- thread <-> work mapping -------------------------------------------------------------------
-// warp w, lane l: t = l % TPF, q = l / TPF, frame slot fl = (32/TPF)*w + q (consecutive frames in a
-// warp).  The magnitude / log-mel buffers are indexed by the permuted slot col = (NT/32)*q + w, which
-// together with the strides (PCM chunk 136 words, exchange frame 560 words, magnitude row 33 words)
-// makes every shared-memory access of P1..P4 bank-conflict free.
-template <int WIN>
-TIR_DEV int tir_frame_of(int tid) { return tid / TirCfg<WIN>::TPF; }
-template <int WIN>
-TIR_DEV int tir_t_of(int tid) { return tid % TirCfg<WIN>::TPF; }
-template <int WIN>
-TIR_DEV int tir_col_of_frame(int fl) {
-  using C = TirCfg<WIN>;
-  constexpr int FPW = 32 / C::TPF; // frames per warp
-  return (C::NT / 32) * (fl % FPW) + fl / FPW;
+TIR_DEV float tir_s16lo(uint32_t w) { return (float)(int16_t)(w & 0xffffu); }
+TIR_DEV float tir_s16hi(uint32_t w) { return (float)(int16_t)(w >> 16); }
+
+// ---- P1, win 512 --------------------------------------------------------------------------------
+// role w = columns n2 = 2w (lane lo) and 2w+1 (lane hi); lane f = frame of the tile.
+// z[n], n = 16*n1 + n2, is the complex point (x[2n], x[2n+1]) of the windowed, fvec_shift'ed frame:
+// sample index (2n + WIN/2) mod WIN, i.e. hop chunk f + 1 - (n1 >> 3), 32-bit word 16*(n1 & 7) + n2.
+TIR_DEV void tir_pass1_512(TirSmem<512> &sm, const uint2 *pcm, int w, int f, TirP2 nz) {
+  using C = TirCfg<512>;
+  TirC2 x[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; n1++) {
+    const uint2 u = pcm[(f + 1 - (n1 >> 3)) * C::PCH + 8 * (n1 & 7) + w];
+    const float4 wv = sm.win4[n1 * C::NW + w];
+    x[n1].r = tir_pmulx(tir_pmk(tir_s16lo(u.x), tir_s16lo(u.y)), tir_pmk(wv.x, wv.y), nz);
+    x[n1].i = tir_pmulx(tir_pmk(tir_s16hi(u.x), tir_s16hi(u.y)), tir_pmk(wv.z, wv.w), nz);
+  }
+  tir_dft16(x, nz);
+  float *xr = sm.xch + TIR_XI(C::N1, 0, 0, 2 * w, f), *xi = sm.xch + TIR_XI(C::N1, 1, 0, 2 * w, f);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; k1++) {
+    TirC2 o = x[k1];
+    if (k1 > 0) { // row 0 is stored as it is; the table holds (1, 0) where n2*k1 == 0
+      const float4 tw = sm.twp4[k1 * C::NW + w];
+      o = tir_cmul(o, tir_pmk(tw.x, tw.y), tir_pmk(tw.z, tw.w));
+    }
+    xr[k1 * 512] = o.r.lo, xr[k1 * 512 + 32] = o.r.hi;
+    xi[k1 * 512] = o.i.lo, xi[k1 * 512 + 32] = o.i.hi;
+  }
 }
 
-// magnitude buffer: bin-major rows of 33 words, frame slot within the row
-#define TIR_NORM_IDX(bin, fl) ((bin) * 33 + (fl))
+// ---- P1, win 1024 -------------------------------------------------------------------------------
+// role c = column n2 = c; the DFT32 over n1 is TIR-FFT's "DFT16 of the even and of the odd inputs,
+// then X[k] = E + W32^k O, X[k+16] = E - W32^k O": lane lo = even n1 = 2m, lane hi = odd n1 = 2m+1.
+// Sample words: hop chunk f + 1 - (n1 >> 4), word 16*(n1 & 15) + c.
+#define TIR_W32R(k)                                                                                             \
+  ((k) == 1 ? 0x1.f6297cp-1f : (k) == 2 ? 0x1.d906bcp-1f : (k) == 3 ? 0x1.a9b662p-1f : (k) == 4 ? 0x1.6a09e6p-1f \
+   : (k) == 5 ? 0x1.1c73b4p-1f : (k) == 6 ? 0x1.87de2ap-2f : (k) == 7 ? 0x1.8f8b84p-3f                          \
+   : (k) == 9 ? -0x1.8f8b84p-3f : (k) == 10 ? -0x1.87de2ap-2f : (k) == 11 ? -0x1.1c73b4p-1f                     \
+   : (k) == 12 ? -0x1.6a09e6p-1f : (k) == 13 ? -0x1.a9b662p-1f : (k) == 14 ? -0x1.d906bcp-1f : -0x1.f6297cp-1f)
+#define TIR_W32I(k)                                                                                               \
+  ((k) == 1 ? -0x1.8f8b84p-3f : (k) == 2 ? -0x1.87de2ap-2f : (k) == 3 ? -0x1.1c73b4p-1f : (k) == 4 ? -0x1.6a09e6p-1f \
+   : (k) == 5 ? -0x1.a9b662p-1f : (k) == 6 ? -0x1.d906bcp-1f : (k) == 7 ? -0x1.f6297cp-1f                          \
+   : (k) == 9 ? -0x1.f6297cp-1f : (k) == 10 ? -0x1.d906bcp-1f : (k) == 11 ? -0x1.a9b662p-1f                        \
+   : (k) == 12 ? -0x1.6a09e6p-1f : (k) == 13 ? -0x1.1c73b4p-1f : (k) == 14 ? -0x1.87de2ap-2f : -0x1.8f8b84p-3f)
 
-// ---- P1 ---------------------------------------------------------------------------------------
-// `frames_valid`: frames of this tile that exist; threads of other frames still run (zeros).
-template <int WIN>
-TIR_DEV void tir_pass1(TirSmem<WIN> &sm, const uint32_t *pcm, int tid) {
-  using C = TirCfg<WIN>;
-  const int fl = tir_frame_of<WIN>(tid), t = tir_t_of<WIN>(tid);
-  float2 *xch = reinterpret_cast<float2 *>(sm.xch) + (size_t)fl * (C::XCH_FRAME_W / 2);
-  static_assert(C::N1 == 16, "pass1 is written for N1 == 16 (win 512)");
-#pragma unroll 1
-  for (int j = 0; j < 2; j++) {
-    const int n2 = t + 8 * j;
-    TirCpx x[16];
+TIR_DEV void tir_pass1_1024(TirSmem<1024> &sm, const uint2 *pcm, int c, int f, TirP2 nz) {
+  using C = TirCfg<1024>;
+  const uint32_t *pcm32 = reinterpret_cast<const uint32_t *>(pcm);
+  TirC2 x[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-      // z[n], n = 16*n1 + n2, after fvec_shift: sample index (2n + WIN/2) mod WIN
-      const int chunk = fl + 1 - (n1 >> 3);
-      const uint32_t word = pcm[chunk * C::PCM_STRIDE_W + 16 * (n1 & 7) + n2];
-      const float2 w = sm.win2[16 * n1 + n2];
-      x[n1].r = TIR_FMUL((float)(int16_t)(word & 0xffffu), w.x);
-      x[n1].i = TIR_FMUL((float)(int16_t)(word >> 16), w.y);
-    }
-    tir_dft16(x);
+  for (int m = 0; m < 16; m++) {
+    const uint32_t *p = pcm32 + (f + 1 - (m >> 3)) * (2 * C::PCH) + 32 * (m & 7) + c;
+    const uint32_t ue = p[0], uo = p[16];
+    const float4 wv = sm.win4[m * C::NW + c];
+    x[m].r = tir_pmulx(tir_pmk(tir_s16lo(ue), tir_s16lo(uo)), tir_pmk(wv.x, wv.y), nz);
+    x[m].i = tir_pmulx(tir_pmk(tir_s16hi(ue), tir_s16hi(uo)), tir_pmk(wv.z, wv.w), nz);
+  }
+  tir_dft16(x, nz); // lane lo: E[k], lane hi: O[k]
+  float *xr = sm.xch + TIR_XI(C::N1, 0, 0, c, f), *xi = sm.xch + TIR_XI(C::N1, 1, 0, c, f);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) {
-      TirCpx o = x[k1];
-      if (k1 > 0) {
-        const float2 w = sm.tw_pass[k1 * 16 + n2];
-        o = tir_cmul(o, w.x, w.y);
-      }
-      float2 st;
-      st.x = o.r, st.y = o.i;
-      xch[k1 * C::XCH_ROW + n2] = st;
+  for (int k = 0; k < 16; k++) {
+    float tr, ti;
+    if (k == 0) {
+      tr = x[k].r.hi, ti = x[k].i.hi;
+    } else if (k == 8) {
+      tr = x[k].i.hi, ti = -x[k].r.hi;
+    } else {
+      tr = TIR_FFMA(-x[k].i.hi, TIR_W32I(k), TIR_FMUL(x[k].r.hi, TIR_W32R(k)));
+      ti = TIR_FFMA(x[k].i.hi, TIR_W32R(k), TIR_FMUL(x[k].r.hi, TIR_W32I(k)));
     }
+    // rows k1 = k (lane lo) and k + 16 (lane hi)
+    TirC2 o;
+    o.r = tir_pmk(TIR_FADD(x[k].r.lo, tr), TIR_FSUB(x[k].r.lo, tr));
+    o.i = tir_pmk(TIR_FADD(x[k].i.lo, ti), TIR_FSUB(x[k].i.lo, ti));
+    const float4 tw = sm.twp4[k * C::NW + c]; // (1, 0) where c*k1 == 0
+    TirC2 q = tir_cmul(o, tir_pmk(tw.x, tw.y), tir_pmk(tw.z, tw.w));
+    if (k == 0) q.r.lo = o.r.lo, q.i.lo = o.i.lo; // row 0 is stored as it is
+    xr[k * 512] = q.r.lo, xr[(k + 16) * 512] = q.r.hi;
+    xi[k * 512] = q.i.lo, xi[(k + 16) * 512] = q.i.hi;
   }
 }
 
 // ---- P2 ---------------------------------------------------------------------------------------
+// role t: rows kA = t (lane lo) and kB = N1 - t (lane hi); role 0: rows 0 and N1/2.
 struct TirPass2Regs {
-  TirCpx A[16], B[16];
+  TirC2 X[16];
 };
 
 template <int WIN>
-TIR_DEV void tir_pass2_load(const TirSmem<WIN> &sm, int tid, TirPass2Regs &rg) {
+TIR_DEV void tir_pass2_load(const TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg) {
   using C = TirCfg<WIN>;
-  const int fl = tir_frame_of<WIN>(tid), t = tir_t_of<WIN>(tid);
-  const float2 *xch = reinterpret_cast<const float2 *>(sm.xch) + (size_t)fl * (C::XCH_FRAME_W / 2);
   const int kA = t, kB = t ? C::N1 - t : C::N1 / 2;
+  const float *ar = sm.xch + TIR_XI(C::N1, 0, kA, 0, f), *ai = sm.xch + TIR_XI(C::N1, 1, kA, 0, f);
+  const float *br = sm.xch + TIR_XI(C::N1, 0, kB, 0, f), *bi = sm.xch + TIR_XI(C::N1, 1, kB, 0, f);
 #pragma unroll
   for (int n2 = 0; n2 < 16; n2++) {
-    float2 a = xch[kA * C::XCH_ROW + n2], b = xch[kB * C::XCH_ROW + n2];
-    rg.A[n2].r = a.x, rg.A[n2].i = a.y;
-    rg.B[n2].r = b.x, rg.B[n2].i = b.y;
+    rg.X[n2].r = tir_pmk(ar[n2 * 32], br[n2 * 32]);
+    rg.X[n2].i = tir_pmk(ai[n2 * 32], bi[n2 * 32]);
   }
 }
 
-// one untangle slot: U=Z[k], V=Z[M-k] (k <= M/2), -> 2^32*|2X[k]|, 2^32*|2X[M-k]|
-// (the 2^32 of the scaled square root and the 2 of the scaled FFT are folded, exactly, into the
-// mel weights: w4 = filter * 2^-33)
-TIR_DEV void tir_untangle_mag(TirCpx U, TirCpx V, float2 w, float &mk, float &mmk) {
-  TirCpx E2 = {TIR_FADD(U.r, V.r), TIR_FSUB(U.i, V.i)};
-  TirCpx O2 = {TIR_FADD(U.i, V.i), TIR_FSUB(V.r, U.r)};
-  TirCpx Tt = tir_cmul(O2, w.x, w.y);
-  float pr = TIR_FADD(E2.r, Tt.r), pi = TIR_FADD(E2.i, Tt.i);
-  float qr = TIR_FSUB(E2.r, Tt.r), qi = TIR_FSUB(E2.i, Tt.i);
-  mk = TIR_FSQRT_SCALED64(TIR_FADD(TIR_FMUL(pr, pr), TIR_FMUL(pi, pi)));
-  mmk = TIR_FSQRT_SCALED64(TIR_FADD(TIR_FMUL(qr, qr), TIR_FMUL(qi, qi)));
+// Two untangle slots at a time.  With Z[k] = U = (a, b), Z[M-k] = V = (c, d), k <= M/2:
+//   E2 = (a+c, b-d), O2 = (b+d, c-a), T = W_{2M}^k O2, 2X[k] = E2 + T, 2X[M-k] = conj(E2 - T)
+// -> mk = 2^32 |2X[k]|, mmk = 2^32 |2X[M-k]| (the 2^33 is folded, exactly, into the mel weights).
+// E2 / O2 mix the two rows (U of one lane meets V of the other row), so these eight additions are
+// scalar; everything after them runs on both slots at once.
+TIR_DEV void tir_untangle_mag2(float ulr, float uli, float vlr, float vli, float uhr, float uhi, float vhr, float vhi,
+                               float4 w, TirP2 nz, TirP2 &mk, TirP2 &mmk) {
+  TirC2 E2, O2;
+  E2.r = tir_pmk(TIR_FADD(ulr, vlr), TIR_FADD(uhr, vhr));
+  E2.i = tir_pmk(TIR_FSUB(uli, vli), TIR_FSUB(uhi, vhi));
+  O2.r = tir_pmk(TIR_FADD(uli, vli), TIR_FADD(uhi, vhi));
+  O2.i = tir_pmk(TIR_FSUB(vlr, ulr), TIR_FSUB(vhr, uhr));
+  const TirC2 Tt = tir_cmul(O2, tir_pmk(w.x, w.y), tir_pmk(w.z, w.w));
+  const TirP2 pr = tir_padd(E2.r, Tt.r), pi = tir_padd(E2.i, Tt.i);
+  const TirP2 qr = tir_psub(E2.r, Tt.r), qi = tir_psub(E2.i, Tt.i);
+  mk = tir_psqrt_scaled64(tir_padd(tir_pmulx(pr, pr, nz), tir_pmulx(pi, pi, nz)));
+  mmk = tir_psqrt_scaled64(tir_padd(tir_pmulx(qr, qr, nz), tir_pmulx(qi, qi, nz)));
 }
 
-template <int WIN>
-TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int tid, TirPass2Regs &rg) {
+// T0 = (role == 0): warp-uniform, so the irregular pairing of rows 0 and N1/2 costs no selects.
+//   role t >= 1, slot pair s:  lane lo  k = t + N1 s         U = A[s]    V = B[15-s]
+//                              lane hi  k = (N1-t) + N1 s    U = B[s]    V = A[15-s]
+//   role 0:                    lane lo  k = N1 (s+1)         U = A[s+1]  V = A[15-s]   (row 0)
+//                              lane hi  k = N1/2 + N1 s      U = B[s]    V = B[15-s]   (row N1/2)
+//   (role 0, s = 7, lane lo is k = M/2 paired with itself; bins 0 and M are never produced: no mel
+//   filter has weight there)
+template <int WIN, bool T0>
+TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg, TirP2 nz) {
   using C = TirCfg<WIN>;
-  static_assert(C::NORM_STRIDE == 33, "TIR_NORM_IDX");
-  const int fl = tir_col_of_frame<WIN>(tir_frame_of<WIN>(tid)), t = tir_t_of<WIN>(tid);
-  const bool t0 = (t == 0);
-  tir_dft16(rg.A); // A[k2] = Z[kA + N1*k2]
-  tir_dft16(rg.B); // B[k2] = Z[kB + N1*k2]
-  // rows: t >= 1: kA = t, kB = N1-t ; t == 0: kA = 0, kB = N1/2.  Sixteen (k, M-k) pairs per thread:
-  //   slots s=0..7   k = (t ? t : N1/2) + N1*s   U = t ? A[s] : B[s]      V = B[15-s]
-  //   slots 8+i      k = (N1 - t) + N1*i         U = t ? B[i] : A[i+1]    V = A[15-i]
-  // (for t == 0 the last slot is k = M/2 paired with itself: U = V = A[8])
-  float *nlo = sm.xch + TIR_NORM_IDX(t0 ? C::N1 / 2 : t, fl);
-  float *nhi = sm.xch + TIR_NORM_IDX(C::M - (t0 ? C::N1 / 2 : t), fl);
+  tir_dft16(rg.X, nz); // lane lo: Z[kA + N1 k2], lane hi: Z[kB + N1 k2]
+  float *mags = sm.xch + f;
+  const int klo0 = T0 ? C::N1 : t, khi0 = T0 ? C::N1 / 2 : C::N1 - t;
 #pragma unroll
   for (int s = 0; s < 8; s++) {
-    TirCpx U, V = rg.B[15 - s];
-    U.r = t0 ? rg.B[s].r : rg.A[s].r, U.i = t0 ? rg.B[s].i : rg.A[s].i;
-    float mk, mmk;
-    tir_untangle_mag(U, V, sm.tw_unt[s * C::TPF + t], mk, mmk);
-    nlo[TIR_NORM_IDX(C::N1 * s, 0)] = mk;
-    nhi[-TIR_NORM_IDX(C::N1 * s, 0)] = mmk;
-  }
-  nlo = sm.xch + TIR_NORM_IDX(C::N1 - t, fl);
-  nhi = sm.xch + TIR_NORM_IDX(C::M - (C::N1 - t), fl);
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    TirCpx U, V = rg.A[15 - i];
-    U.r = t0 ? rg.A[i + 1].r : rg.B[i].r, U.i = t0 ? rg.A[i + 1].i : rg.B[i].i;
-    float mk, mmk;
-    tir_untangle_mag(U, V, sm.tw_unt[(8 + i) * C::TPF + t], mk, mmk);
-    nlo[TIR_NORM_IDX(C::N1 * i, 0)] = mk;
-    nhi[-TIR_NORM_IDX(C::N1 * i, 0)] = mmk;
+    const TirC2 &Xs = rg.X[s], &Xr = rg.X[15 - s], &Xn = rg.X[s + 1];
+    TirP2 mk, mmk;
+    const float4 w = sm.twu4[t * 8 + s];
+    if (T0)
+      tir_untangle_mag2(Xn.r.lo, Xn.i.lo, Xr.r.lo, Xr.i.lo, Xs.r.hi, Xs.i.hi, Xr.r.hi, Xr.i.hi, w, nz, mk, mmk);
+    else
+      tir_untangle_mag2(Xs.r.lo, Xs.i.lo, Xr.r.hi, Xr.i.hi, Xs.r.hi, Xs.i.hi, Xr.r.lo, Xr.i.lo, w, nz, mk, mmk);
+    const int klo = klo0 + C::N1 * s, khi = khi0 + C::N1 * s;
+    mags[klo * 32] = mk.lo;
+    if (!(T0 && s == 7)) mags[(C::M - klo) * 32] = mmk.lo;
+    mags[khi * 32] = mk.hi;
+    mags[(C::M - khi) * 32] = mmk.hi;
   }
 }
 
 // ---- P3 ---------------------------------------------------------------------------------------
-// warp `w` (0..TIR_MEL_WARPS-1, warp-uniform), lane = permuted frame slot (tir_col_of_frame)
-TIR_DEV void tir_mel_phase(const float *norm, float *lg, const double2 *logtab, const TirMelParams &mp, int w,
-                           int lane) {
-  const int nf = mp.warp_nf[w];
-  for (int q = 0; q < nf; q++) {
-    const int f = mp.warp_filters[w][q];
-    const int n4 = (mp.len[f] + 3) >> 2;
-    const float *p = norm + TIR_NORM_IDX(mp.start[f], lane);
-    const float4 *wp = mp.w4 + (mp.woff[f] >> 2);
-    float acc = 0.f;
-    // zero padded weights: acc + x*0 == acc (x is finite: a magnitude, or stale exchange data above
-    // the last bin row, which lies inside sm.xch)
+// role w (warp-uniform) = a list of filter pairs, lane f = frame.  Zero padded weights: acc + x*0 ==
+// acc (x is finite: a magnitude, or stale exchange data beyond the last bin row, inside sm.xch).
+TIR_DEV void tir_mel_phase(const float *norm, float *lg, const double2 *logtab, const TirMelParams &mp, int w, int f,
+                           TirP2 nz) {
+  const int np = mp.warp_np[w];
+  for (int q = 0; q < np; q++) {
+    const int p = mp.warp_pairs[w][q];
+    const int n = mp.steps[p];
+    const float *pa = norm + TIR_NORM_IDX(mp.start_a[p], f), *pb = norm + TIR_NORM_IDX(mp.start_b[p], f);
+    const float4 *wp = mp.w4 + mp.woff[p];
+    TirP2 acc = tir_pbc(0.f);
 #pragma unroll 2
-    for (int b = 0; b < n4; b++) {
-      const float4 w = wp[b];
-      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 0, 0)], w.x));
-      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 1, 0)], w.y));
-      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 2, 0)], w.z));
-      acc = TIR_FADD(acc, TIR_FMUL(p[TIR_NORM_IDX(4 * b + 3, 0)], w.w));
+    for (int b = 0; b < n; b++) {
+      const float4 wv = wp[b];
+      acc = tir_padd(acc, tir_pmulx(tir_pmk(pa[64 * b], pb[64 * b]), tir_pmk(wv.x, wv.y), nz));
+      acc = tir_padd(acc, tir_pmulx(tir_pmk(pa[64 * b + 32], pb[64 * b + 32]), tir_pmk(wv.z, wv.w), nz));
     }
-    const float v = acc < mp.log_clamp ? mp.log_clamp : acc;
-    lg[f * 32 + lane] = tir_log10f_glibc(v, logtab);
+    const float va = acc.lo < mp.log_clamp ? mp.log_clamp : acc.lo;
+    lg[mp.filt_a[p] * 32 + f] = tir_log10f_glibc(va, logtab);
+    if (mp.filt_b[p] >= 0) {
+      const float vb = acc.hi < mp.log_clamp ? mp.log_clamp : acc.hi;
+      lg[mp.filt_b[p] * 32 + f] = tir_log10f_glibc(vb, logtab);
+    }
   }
 }
 
 // ---- P4 ---------------------------------------------------------------------------------------
-// `col` = permuted slot of the frame this thread finishes
-TIR_DEV void tir_dct_phase(const float *lg, const TirMelParams &mp, int j, int col, float &c, int32_t &vq) {
+TIR_DEV void tir_dct_phase(const float *lg, const TirMelParams &mp, int j, int f, float &c, int32_t &vq) {
   float acc = 0.f;
 #pragma unroll 8
-  for (int f = 0; f < mp.n_filters; f++) acc = TIR_FADD(acc, TIR_FMUL(lg[f * 32 + col], mp.dct[j][f]));
+  for (int i = 0; i < mp.n_filters; i++) acc = TIR_FADD(acc, TIR_FMUL(lg[i * 32 + f], mp.dct[j][i]));
   c = acc;
   vq = tir_quantize_micro(tir_coef_to_y(acc));
 }

@@ -31,7 +31,7 @@ struct tir_ctx {
   bool ev_valid[2] = {false, false};
   TirHostTables tab;
   // device copies of the kernel-layout tables
-  float2 *d_win2 = nullptr, *d_tw_pass = nullptr, *d_tw_unt = nullptr, *d_tw32 = nullptr;
+  float4 *d_win4 = nullptr, *d_twp4 = nullptr, *d_twu4 = nullptr;
   // reusable device scratch
   DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y;
   // pinned staging for small metadata

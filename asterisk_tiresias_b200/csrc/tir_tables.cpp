@@ -89,10 +89,9 @@ void build_dct(int n_filters, int n_coefs, std::vector<float> &dct) {
 }
 } // namespace
 
-int tir_untangle_bin(int N1, int M, int slot, int t) {
-  (void)M;
-  if (slot < 8) return (t ? t : N1 / 2) + N1 * slot;
-  return (N1 - t) + N1 * (slot - 8);
+void tir_untangle_bins(int N1, int t, int s, int &k_lo, int &k_hi) {
+  k_lo = (t ? t : N1) + N1 * s;
+  k_hi = (t ? N1 - t : N1 / 2) + N1 * s;
 }
 
 bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplerate, TirHostTables &o) {
@@ -100,80 +99,107 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
         n_coefs >= 1 && n_coefs <= TIR_MAX_COEFS && samplerate > 0))
     return false;
   o.win = win, o.hop = hop, o.samplerate = samplerate, o.n_filters = n_filters, o.n_coefs = n_coefs;
-  o.M = win / 2, o.N1 = o.M / 16, o.TPF = o.N1 / 2, o.L = win / 2 + 1;
+  o.M = win / 2, o.N1 = o.M / 16, o.NW = o.N1 / 2, o.L = win / 2 + 1;
   build_window(win, o.window);
   build_filterbank(n_filters, o.L, samplerate, o.filters, o.edges);
   build_dct(n_filters, n_coefs, o.dct);
 
-  const int M = o.M, N1 = o.N1, TPF = o.TPF;
+  const int M = o.M, N1 = o.N1, NW = o.NW;
   o.win2.resize(M);
   for (int n = 0; n < M; n++) {
     // 2^-15 folds aubio_source's sample/32768 into the window: fl((x*2^-15)*w) == fl(x*(w*2^-15))
     o.win2[n].x = o.window[(2 * n + win / 2) % win] * (1.0f / 32768.0f);
     o.win2[n].y = o.window[(2 * n + 1 + win / 2) % win] * (1.0f / 32768.0f);
   }
-  o.tw_pass.resize((size_t)N1 * 16);
-  for (int k1 = 0; k1 < N1; k1++)
-    for (int n2 = 0; n2 < 16; n2++) {
-      const int m = n2 * k1;
-      float2 w;
-      if (m == 0) {
-        w.x = 1.f, w.y = 0.f; // multiply by one: exact (up to the sign of a zero)
-      } else {
-        w.x = (float)cos(2.0 * kPi * m / M);
-        w.y = (float)(-sin(2.0 * kPi * m / M));
-      }
-      o.tw_pass[(size_t)k1 * 16 + n2] = w;
+  auto twM = [&](int m, float &wr, float &wi) {
+    if (m == 0) {
+      wr = 1.f, wi = 0.f; // multiply by one: exact (up to the sign of a zero)
+    } else {
+      wr = (float)cos(2.0 * kPi * m / M);
+      wi = (float)(-sin(2.0 * kPi * m / M));
     }
-  o.tw_unt.resize((size_t)16 * TPF);
-  for (int s = 0; s < 16; s++)
-    for (int t = 0; t < TPF; t++) {
-      const int k = tir_untangle_bin(N1, M, s, t);
-      float2 w;
-      w.x = (float)cos(2.0 * kPi * k / (2 * M));
-      w.y = (float)(-sin(2.0 * kPi * k / (2 * M)));
-      o.tw_unt[(size_t)s * TPF + t] = w;
+  };
+  o.win4.assign((size_t)16 * NW, float4{0, 0, 0, 0});
+  o.twp4.assign((size_t)16 * NW, float4{0, 0, 0, 0});
+  for (int i = 0; i < 16; i++)
+    for (int r = 0; r < NW; r++) {
+      // win 512: i = n1, role r = columns (2r, 2r+1), lanes = the two columns, rows k1 = i
+      // win 1024: i = m / k, role r = column r, lanes = n1 (2m, 2m+1) resp. rows k1 (k, k+16)
+      const int n_lo = win == 512 ? 16 * i + 2 * r : 16 * (2 * i) + r;
+      const int n_hi = win == 512 ? 16 * i + 2 * r + 1 : 16 * (2 * i + 1) + r;
+      o.win4[(size_t)i * NW + r] = float4{o.win2[n_lo].x, o.win2[n_hi].x, o.win2[n_lo].y, o.win2[n_hi].y};
+      const int m_lo = win == 512 ? (2 * r) * i : r * i;
+      const int m_hi = win == 512 ? (2 * r + 1) * i : r * (i + 16);
+      float4 t;
+      twM(m_lo, t.x, t.z), twM(m_hi, t.y, t.w);
+      o.twp4[(size_t)i * NW + r] = t;
     }
-  o.tw32.resize(16);
-  for (int k = 0; k < 16; k++) {
-    o.tw32[k].x = (float)cos(2.0 * kPi * k / 32);
-    o.tw32[k].y = (float)(-sin(2.0 * kPi * k / 32));
-  }
+  o.twu4.assign((size_t)NW * 8, float4{0, 0, 0, 0});
+  for (int t = 0; t < NW; t++)
+    for (int s = 0; s < 8; s++) {
+      int k_lo, k_hi;
+      tir_untangle_bins(N1, t, s, k_lo, k_hi);
+      float4 w;
+      w.x = (float)cos(2.0 * kPi * k_lo / (2 * M)), w.z = (float)(-sin(2.0 * kPi * k_lo / (2 * M)));
+      w.y = (float)cos(2.0 * kPi * k_hi / (2 * M)), w.w = (float)(-sin(2.0 * kPi * k_hi / (2 * M)));
+      o.twu4[(size_t)t * 8 + s] = w;
+    }
 
-  // banded mel weights
+  // banded mel weights, two filters (of similar length) per record
   TirMelParams &mp = o.mel;
   std::memset(&mp, 0, sizeof(mp));
   mp.n_filters = n_filters, mp.n_coefs = n_coefs;
   mp.log_clamp = (float)2.e-42; // aubio_priv.h VERY_SMALL_NUMBER, as the float log10f receives
-  int nnz = 0;
+  std::vector<int> first(n_filters, 0), len(n_filters, 0);
   for (int f = 0; f < n_filters; f++) {
     const float *filt = o.filters.data() + (size_t)f * o.L;
-    int first = -1, last = -2;
-    for (int b = 0; b < o.L; b++)
-      if (filt[b] != 0.f) {
-        if (first < 0) first = b;
-        last = b;
+    int a = -1, b = -2;
+    for (int i = 0; i < o.L; i++)
+      if (filt[i] != 0.f) {
+        if (a < 0) a = i;
+        b = i;
       }
-    const int len = first < 0 ? 0 : last - first + 1;
-    const int len4 = (len + 3) & ~3; // zero padded to whole float4s
-    if (nnz + len4 > TIR_MAX_NNZ) return false;
-    mp.start[f] = (int16_t)(first < 0 ? 0 : first), mp.len[f] = (int16_t)len, mp.woff[f] = (int16_t)nnz;
-    float *wdst = reinterpret_cast<float *>(mp.w4) + nnz;
-    // magnitudes arrive as 2^33 * |X[k]| (FFT scaled by 2, sqrt by 2^32); power-of-two scaling is exact
-    for (int b = 0; b < len; b++) wdst[b] = filt[first + b] * (1.0f / 8589934592.0f);
-    nnz += len4;
+    first[f] = a < 0 ? 0 : a, len[f] = a < 0 ? 0 : b - a + 1;
   }
-  for (int j = 0; j < n_coefs; j++)
-    for (int f = 0; f < n_filters; f++) mp.dct[j][f] = o.dct[(size_t)j * n_filters + f];
-  // longest-processing-time assignment of filters to the mel warps
   std::vector<int> order(n_filters);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return mp.len[a] > mp.len[b]; });
-  int load[TIR_MEL_WARPS] = {0};
-  for (int f : order) {
-    int w = (int)(std::min_element(load, load + TIR_MEL_WARPS) - load);
-    mp.warp_filters[w][mp.warp_nf[w]++] = (uint8_t)f;
-    load[w] += mp.len[f] + 24; // + fixed cost of the clamp/log10f per filter
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+  int n_pairs = 0, nrec = 0;
+  for (int i = 0; i < n_filters; i += 2) {
+    const int fa = order[i], fb = i + 1 < n_filters ? order[i + 1] : -1;
+    const int p = n_pairs++;
+    const int steps = (len[fa] + 1) / 2; // len[fa] >= len[fb]
+    if (nrec + steps > TIR_MAX_W4) return false;
+    mp.filt_a[p] = (int8_t)fa, mp.filt_b[p] = (int8_t)fb;
+    mp.start_a[p] = (int16_t)first[fa], mp.start_b[p] = (int16_t)(fb >= 0 ? first[fb] : first[fa]);
+    mp.steps[p] = (int16_t)steps, mp.woff[p] = (int16_t)nrec;
+    const float *fa_w = o.filters.data() + (size_t)fa * o.L + first[fa];
+    const float *fb_w = fb >= 0 ? o.filters.data() + (size_t)fb * o.L + first[fb] : nullptr;
+    // magnitudes arrive as 2^33 * |X[k]| (FFT scaled by 2, sqrt by 2^32); power-of-two scaling is exact
+    const float sc = 1.0f / 8589934592.0f;
+    for (int s = 0; s < steps; s++) {
+      float4 w{0, 0, 0, 0};
+      const int b0 = 2 * s, b1 = 2 * s + 1;
+      if (b0 < len[fa]) w.x = fa_w[b0] * sc;
+      if (b1 < len[fa]) w.z = fa_w[b1] * sc;
+      if (fb >= 0 && b0 < len[fb]) w.y = fb_w[b0] * sc;
+      if (fb >= 0 && b1 < len[fb]) w.w = fb_w[b1] * sc;
+      mp.w4[nrec + s] = w;
+    }
+    nrec += steps;
+  }
+  mp.n_pairs = n_pairs;
+  for (int j = 0; j < n_coefs; j++)
+    for (int f = 0; f < n_filters; f++) mp.dct[j][f] = o.dct[(size_t)j * n_filters + f];
+  // longest-processing-time assignment of the pairs to the NW mel warps
+  std::vector<int> porder(n_pairs);
+  std::iota(porder.begin(), porder.end(), 0);
+  std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return mp.steps[a] > mp.steps[b]; });
+  std::vector<int> load(NW, 0);
+  for (int p : porder) {
+    const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    mp.warp_pairs[w][mp.warp_np[w]++] = (uint8_t)p;
+    load[w] += 9 * mp.steps[p] + 2 * 40 + 12; // issue slots: mel steps + two clamp/log10f + loop set-up
   }
   return true;
 }

@@ -49,6 +49,7 @@ def emul():
         subprocess.check_call(["sh", os.path.join(ROOT, "tests", "emul", "build_emul.sh")])
     L = C.CDLL(so)
     L.emul_extract.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.emul_extract_win.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.emul_tables.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emul_log10f.restype = C.c_float
     L.emul_log10f.argtypes = [C.c_float]

@@ -3,6 +3,7 @@
 // barriers of the kernel turned into loop boundaries, so that the CPU test-suite can check the
 // kernel's arithmetic and shared-memory indexing against the oracle without a GPU.
 // This is not a fallback: it is built only by tests/ and is never linked into libtiresias_gpu.so.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -11,47 +12,71 @@
 #include "../../asterisk_tiresias_b200/csrc/tir_extract_core.cuh"
 #include "../../asterisk_tiresias_b200/csrc/tir_tables.h"
 
-extern "C" int emul_extract(const int16_t *pcm, uint64_t n_samples, int samplerate, float *coef, int32_t *vq) {
-  using C = TirCfg<512>;
+template <int WIN>
+static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate, float *coef, int32_t *vq) {
+  using C = TirCfg<WIN>;
   TirHostTables tab;
-  if (!tir_build_tables(512, 256, 40, 2, samplerate, tab)) return -1;
-  auto *sm = new TirSmem<512>();
+  if (!tir_build_tables(WIN, WIN / 2, 40, 2, samplerate, tab)) return -1;
+  auto *sm = new TirSmem<WIN>();
   std::memset(sm, 0, sizeof(*sm));
-  std::memcpy(sm->win2, tab.win2.data(), sizeof(sm->win2));
-  std::memcpy(sm->tw_pass, tab.tw_pass.data(), sizeof(sm->tw_pass));
-  std::memcpy(sm->tw_unt, tab.tw_unt.data(), sizeof(sm->tw_unt));
+  std::memcpy(sm->win4, tab.win4.data(), sizeof(sm->win4));
+  std::memcpy(sm->twp4, tab.twp4.data(), sizeof(sm->twp4));
+  std::memcpy(sm->twu4, tab.twu4.data(), sizeof(sm->twu4));
   const double2 lt[16] = TIR_LOGF_TAB_INIT;
   std::memcpy(sm->logtab, lt, sizeof(lt));
   const int64_t nsamp = (int64_t)n_samples;
   const int64_t nframes = (nsamp + C::HOP - 1) / C::HOP;
   std::vector<TirPass2Regs> regs(C::NT);
-  for (int64_t f0 = 0; f0 < nframes; f0 += C::T) {
+  const TirP2 nz = tir_pbc(-0.0f);
+  int b = 0;
+  for (int64_t f0 = 0; f0 < nframes; f0 += C::T, b ^= 1) {
     const int nvalid = (int)std::min<int64_t>(C::T, nframes - f0);
-    // P0
+    // P0 (same placement as tir_issue_tile_load: chunk c, 8-byte unit p -> pcm[c * PCH + p])
     for (int chunk = 0; chunk <= C::T; chunk++)
-      for (int i = 0; i < C::HOP; i += 2) {
-        int64_t s = (f0 - 1 + chunk) * C::HOP + i;
-        uint32_t lo = (s >= 0 && s < nsamp) ? (uint16_t)pcm[s] : 0;
-        uint32_t hi = (s + 1 >= 0 && s + 1 < nsamp) ? (uint16_t)pcm[s + 1] : 0;
-        sm->pcm[0][chunk * C::PCM_STRIDE_W + i / 2] = lo | (hi << 16);
+      for (int p = 0; p < C::HOP / 4; p++) {
+        uint32_t h[4];
+        for (int e = 0; e < 4; e++) {
+          int64_t s = (f0 - 1 + chunk) * C::HOP + 4 * p + e;
+          h[e] = (s >= 0 && s < nsamp) ? (uint16_t)pcm[s] : 0;
+        }
+        sm->pcm[b][chunk * C::PCH + p].x = h[0] | (h[1] << 16);
+        sm->pcm[b][chunk * C::PCH + p].y = h[2] | (h[3] << 16);
       }
-    for (int tid = 0; tid < C::NT; tid++) tir_pass1<512>(*sm, sm->pcm[0], tid);
-    for (int tid = 0; tid < C::NT; tid++) tir_pass2_load<512>(*sm, tid, regs[tid]);
-    for (int tid = 0; tid < C::NT; tid++) tir_pass2_compute<512>(*sm, tid, regs[tid]);
-    float *lg = reinterpret_cast<float *>(sm->pcm[0]); // as in the kernel: aliases the consumed PCM buffer
-    for (int w = 0; w < TIR_MEL_WARPS; w++)
-      for (int lane = 0; lane < 32; lane++) tir_mel_phase(sm->xch, lg, sm->logtab, tab.mel, w, lane);
+    for (int w = 0; w < C::NW; w++)
+      for (int lane = 0; lane < 32; lane++) {
+        if constexpr (WIN == 512) tir_pass1_512(*sm, sm->pcm[b], w, lane, nz);
+        else tir_pass1_1024(*sm, sm->pcm[b], w, lane, nz);
+      }
+    for (int w = 0; w < C::NW; w++)
+      for (int lane = 0; lane < 32; lane++) tir_pass2_load<WIN>(*sm, w, lane, regs[w * 32 + lane]);
+    for (int w = 0; w < C::NW; w++)
+      for (int lane = 0; lane < 32; lane++) {
+        if (w == 0) tir_pass2_compute<WIN, true>(*sm, w, lane, regs[w * 32 + lane], nz);
+        else tir_pass2_compute<WIN, false>(*sm, w, lane, regs[w * 32 + lane], nz);
+      }
+    for (int w = 0; w < C::NW; w++)
+      for (int lane = 0; lane < 32; lane++) tir_mel_phase(sm->xch, sm->lg, sm->logtab, tab.mel, w, lane, nz);
     for (int j = 0; j < 2; j++)
       for (int lane = 0; lane < nvalid; lane++) {
         float c;
         int32_t v;
-        tir_dct_phase(lg, tab.mel, j, tir_col_of_frame<512>(lane), c, v);
+        tir_dct_phase(sm->lg, tab.mel, j, lane, c, v);
         coef[(f0 + lane) * 2 + j] = c;
         vq[(f0 + lane) * 2 + j] = v;
       }
   }
   delete sm;
   return 0;
+}
+
+extern "C" int emul_extract(const int16_t *pcm, uint64_t n_samples, int samplerate, float *coef, int32_t *vq) {
+  return emul_extract_t<512>(pcm, n_samples, samplerate, coef, vq);
+}
+extern "C" int emul_extract_win(int win, const int16_t *pcm, uint64_t n_samples, int samplerate, float *coef,
+                                int32_t *vq) {
+  if (win == 512) return emul_extract_t<512>(pcm, n_samples, samplerate, coef, vq);
+  if (win == 1024) return emul_extract_t<1024>(pcm, n_samples, samplerate, coef, vq);
+  return -1;
 }
 
 extern "C" int emul_tables(int win, int hop, int samplerate, float *window, float *filters, float *dct) {

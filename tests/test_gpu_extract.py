@@ -58,6 +58,58 @@ def test_unaligned_and_edge_clips(gpu_ctx, oracle):
     assert c0.shape == (0, 2) and v0.shape == (0, 2)
 
 
+@pytest.mark.parametrize("win,sr", [(1024, 16000), (512, 16000), (1024, 8000)])
+def test_wideband_plans(oracle, win, sr):
+    """BASELINE config[3]: 16 kHz audio with the larger window/hop (the commented alternative of
+    src/fp_handler.c:35-36), plus the other (win, rate) combinations a WAV directory can produce."""
+    from asterisk_tiresias_b200 import capi
+    ctx = capi.Context(device=0, win=win, hop=win // 2, samplerate=sr)
+    try:
+        plan = oracle.Plan(win=win, hop=win // 2, samplerate=sr)
+        pcm, off = synth.make_corpus(12, 3.0, samplerate=sr, first_index=700)
+        coef, vq = ctx.extract(pcm, off)
+        oc, _, ov = plan.extract_batch(pcm, off, n_threads=8)
+        check(coef, vq, oc, ov)
+        # ragged, unaligned clip starts (odd offsets take the synchronous edge path of P0)
+        rng = np.random.default_rng(win + sr)
+        lens = [0, 1, win // 2 - 1, win // 2, win // 2 + 1, win + 3, 33 * (win // 2) + 7, 5, 40001, 2, 70003]
+        clips = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
+        clips[6][50:9000] = 0
+        off = np.zeros(len(lens) + 1, np.uint64); off[1:] = np.cumsum(lens)
+        pcm = np.concatenate(clips)
+        coef, vq = ctx.extract(pcm, off)
+        oc, _, ov = plan.extract_batch(pcm, off)
+        check(coef, vq, oc, ov)
+        w, fb, d = ctx.tables()
+        assert np.array_equal(fb.view(np.uint32), plan.filters.view(np.uint32))
+    finally:
+        ctx.close()
+
+
+def test_clip_alignment_paths(gpu_ctx, oracle):
+    """clip starts at every residue mod 4 samples (8-byte cp.async path vs the edge path) and a
+    device buffer that is itself misaligned."""
+    import torch
+    rng = np.random.default_rng(11)
+    lens = [9000 + r for r in (0, 1, 2, 3, 4, 5, 6, 7)] + [8192 * 2, 12345]
+    clips = [rng.integers(-30000, 30000, n).astype(np.int16) for n in lens]
+    off = np.zeros(len(lens) + 1, np.uint64); off[1:] = np.cumsum(lens)
+    pcm = np.concatenate(clips)
+    oc, _, ov = oracle.Plan().extract_batch(pcm, off)
+    coef, vq = gpu_ctx.extract(pcm, off)
+    check(coef, vq, oc, ov)
+    F = gpu_ctx.n_frames(off)
+    for shift in (0, 1, 2, 3):
+        d_buf = torch.zeros(pcm.size + 8, dtype=torch.int16, device="cuda")
+        d_buf[shift:shift + pcm.size] = torch.from_numpy(pcm).cuda()
+        d_coef = torch.zeros((F, 2), dtype=torch.float32, device="cuda")
+        d_vq = torch.zeros((F, 2), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()  # the context runs on its own stream
+        gpu_ctx.extract_dev(d_buf.data_ptr() + 2 * shift, off, d_coef.data_ptr(), d_vq.data_ptr())
+        torch.cuda.synchronize()
+        check(d_coef.cpu().numpy(), d_vq.cpu().numpy(), oc, ov)
+
+
 def test_device_buffer_entry_point(gpu_ctx, oracle):
     import torch
     pcm, off = synth.make_corpus(5, 1.5, first_index=40)

@@ -35,6 +35,25 @@ def test_kernel_phases_on_host_match_oracle(oracle, emul, idx, kind, sec):
     assert np.array_equal(vq, v2)
 
 
+WIDE = [(512, 16000, 0, "tone", 1.5), (512, 16000, 1, "noise", 1.0), (1024, 16000, 0, "tone", 3.0),
+        (1024, 16000, 1, "noise", 3.0), (1024, 16000, 2, "chirp", 3.0), (1024, 16000, 3, "composite", 2.77),
+        (1024, 16000, 4, "silence", 1.0), (1024, 16000, 5, None, 0.01), (1024, 16000, 7, None, 4.1),
+        (1024, 8000, 6, None, 2.0), (512, 44100, 8, None, 0.7)]
+
+
+@pytest.mark.parametrize("win,sr,idx,kind,sec", WIDE)
+def test_kernel_phases_other_plans(oracle, emul, win, sr, idx, kind, sec):
+    """win 1024 / hop 512 (the commented alternative, src/fp_handler.c:35-36) and other sample rates."""
+    p = oracle.Plan(win=win, hop=win // 2, samplerate=sr)
+    pcm = synth.make_clip(idx, sec, samplerate=sr, kind=kind, ulaw=(idx % 2 == 1))
+    co, y, vq = p.extract(pcm)
+    F = co.shape[0]
+    c2 = np.zeros((F, 2), np.float32); v2 = np.zeros((F, 2), np.int32)
+    assert emul.emul_extract_win(win, pcm.ctypes.data, pcm.size, sr, c2.ctypes.data, v2.ctypes.data) == 0
+    assert np.array_equal(co.view(np.uint32), c2.view(np.uint32))
+    assert np.array_equal(vq, v2)
+
+
 def test_log10f_model_equals_libm(emul):
     # strided sweep over every binade of the positive floats incl. subnormals (the exhaustive
     # 2^31 sweep was run once: 0 mismatches, see DESIGN.md)
