@@ -125,8 +125,21 @@ __device__ __forceinline__ void tir_pass1(TirSmem<WIN> &sm, const uint2 *pcm, in
   else tir_pass1_1024(sm, pcm, role, lane, nz);
 }
 
-// Per tile: P1 | sync | P2 load | sync | P2 compute | sync | P3 (+ wait for the next tile's PCM) |
-// sync | P4 (coefficient warps only, no barrier after it: it overlaps the next tile's P1).
+// coefficient warps: DCT row `warp` of the tile described by `td`, from its finished log-mel values
+__device__ __forceinline__ void tir_emit_coefs(const float *lg, const TirMelParams &mp, const TirExtractArgs &a,
+                                               const TirTile &td, int warp, int lane) {
+  if (lane < td.nvalid) {
+    float c;
+    int32_t v;
+    tir_dct_phase(lg, mp, warp, lane, c, v);
+    const uint64_t o = (td.out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
+    if (a.coef) a.coef[o] = c;
+    if (a.vq) a.vq[o] = v;
+  }
+}
+
+// Per tile: P1 | sync | P2 load | sync | P2 compute | sync | P3a sweep (coefficient warps: P4 of the
+// previous tile) + wait for the next tile's PCM | sync | P3b logs -- no barrier before the next P1.
 template <int WIN>
 __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     tir_extract_kernel(const __grid_constant__ TirExtractArgs a, const __grid_constant__ TirMelParams mp) {
@@ -142,22 +155,28 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   TirTile cur = tir_load_tile_desc(a.tiles + tile);
   tir_issue_tile_load<WIN>(sm.pcm[0], a.pcm, cur, base_aligned, tid);
   bool have_nxt = tile + gridDim.x < a.n_tiles;
-  TirTile nxt = cur;
+  TirTile nxt = cur, prev = cur;
   if (have_nxt) nxt = tir_load_tile_desc(a.tiles + tile + gridDim.x);
 
   for (int i = tid; i < 16 * C::NW; i += C::NT) sm.win4[i] = a.win4[i], sm.twp4[i] = a.twp4[i];
   for (int i = tid; i < C::NW * 8; i += C::NT) sm.twu4[i] = a.twu4[i];
   if (tid < 16) sm.logtab[tid] = k_logf_tab[tid];
-  // rows of the magnitude buffer that P2 never writes (bins 0, M and the rows the zero padded mel
-  // loop may touch beyond M) must hold finite values
+  // bins 0 and M of the magnitude buffer are never written; keep the whole buffer finite
   for (int i = tid; i < TirSmem<WIN>::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
   cp_async_wait_all();
   __syncthreads();
 
   int b = 0;
+  bool first = true;
   for (;;) {
     // pcm[b] holds the current tile; pcm[b^1] was consumed by the previous tile's P1
-    if (have_nxt) tir_issue_tile_load<WIN>(sm.pcm[b ^ 1], a.pcm, nxt, base_aligned, tid); // streams in under P1..P3
+    TirTile nn = nxt;
+    bool have_nn = false;
+    if (have_nxt) {
+      tir_issue_tile_load<WIN>(sm.pcm[b ^ 1], a.pcm, nxt, base_aligned, tid); // streams in under P1..P3a
+      have_nn = tile + 2 * gridDim.x < a.n_tiles;
+      if (have_nn) nn = tir_load_tile_desc(a.tiles + tile + 2 * gridDim.x); // needed one tile from now
+    }
     tir_pass1<WIN>(sm, sm.pcm[b], warp, lane, nz);
     __syncthreads();
     TirPass2Regs rg;
@@ -166,23 +185,20 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     if (warp == 0) tir_pass2_compute<WIN, true>(sm, warp, lane, rg, nz);
     else tir_pass2_compute<WIN, false>(sm, warp, lane, rg, nz);
     __syncthreads();
-    tir_mel_phase(sm.xch, sm.lg, sm.logtab, mp, warp, lane, nz);
-    cp_async_wait_all();
-    __syncthreads(); // log-mel values complete; the next tile's PCM has landed
-    if (warp < mp.n_coefs && lane < cur.nvalid) {
-      float c;
-      int32_t v;
-      tir_dct_phase(sm.lg, mp, warp, lane, c, v);
-      const uint64_t o = (cur.out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
-      if (a.coef) a.coef[o] = c;
-      if (a.vq) a.vq[o] = v;
+    if (warp < mp.n_coefs) {
+      if (!first) tir_emit_coefs(sm.lg[b ^ 1], mp, a, prev, warp, lane);
+    } else {
+      tir_mel_sweep(sm.xch, sm.lg[b], mp, warp - mp.n_coefs, lane, nz);
     }
+    cp_async_wait_all();
+    __syncthreads(); // raw mel sums complete; the next tile's PCM has landed
+    tir_log_phase<C::NW>(sm.lg[b], sm.logtab, mp, warp, lane);
     if (!have_nxt) break;
     tile += gridDim.x;
-    cur = nxt, b ^= 1;
-    have_nxt = tile + gridDim.x < a.n_tiles;
-    if (have_nxt) nxt = tir_load_tile_desc(a.tiles + tile + gridDim.x);
+    prev = cur, cur = nxt, nxt = nn, have_nxt = have_nn, b ^= 1, first = false;
   }
+  __syncthreads();
+  if (warp < mp.n_coefs) tir_emit_coefs(sm.lg[b], mp, a, cur, warp, lane);
 }
 
 size_t tir_extract_smem_bytes(int win) {

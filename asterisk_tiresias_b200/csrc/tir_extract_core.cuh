@@ -16,20 +16,22 @@
 //               twiddle W_M^(n2*k1) -> exchange buffer
 //   P2 pass2    role = row pair (k1, N1-k1): load both rows into registers             [sync]
 //               DFT16 over n2, real untangling, sqrt(re^2+im^2) -> magnitudes (alias the exchange)
-//   P3 mel      role = list of filter pairs: banded Slaney matvec (sequential float adds in bin
-//               order, like fmat_vecmul), clamp 2e-42, glibc-exact log10f
+//   P3a mel     role = segment of the filter bank: one sweep over its bins, even filters in lane lo,
+//               odd ones in lane hi (sequential float adds in bin order, like fmat_vecmul);
+//               the coefficient warps run P4 of the PREVIOUS tile here instead
+//   P3b log     every thread: clamp 2e-42 and glibc-exact log10f of ceil(40/NW) mel values [no sync after]
 //   P4 dct      role = coefficient: sequential 40-term DCT row, 10*log10|c| in double, "%f"
 // All float32 arithmetic of P1..P3 runs on TirP2 pairs (FADD2/FMUL2/FFMA2, tir_fp.cuh); the two
-// lanes of a pair are two columns (P1), two rows (P2), two untangle slots (P2) or two filters (P3).
+// lanes of a pair are two columns (P1), two rows (P2), two untangle slots (P2) or the even and the odd mel filter covering a bin (P3).
 // The float32 FFT is "TIR-FFT" (operation order documented in DESIGN.md, and restated
 // independently by the CPU oracle).
 #pragma once
 #include "tir_fp.cuh"
 
 #define TIR_MAX_FILTERS 40
-#define TIR_MAX_PAIRS 20
 #define TIR_MAX_COEFS 2
-#define TIR_MAX_W4 768
+#define TIR_MAX_RUNS 64
+#define TIR_MAX_W2 1536
 #define TIR_MAX_WARPS 16
 #define TIR_TILE 32 // frames per tile == lanes per warp
 
@@ -38,19 +40,26 @@ struct TirC2 { // two complex numbers: lane lo and lane hi
 };
 
 // ---- kernel-parameter block (lives in the constant bank; warp-uniform reads are cheap LDCs)
+// Mel sweep: the Slaney triangles of filters f and f+2 never overlap, so ONE pass over the bins
+// with the even filters accumulated in lane lo and the odd ones in lane hi computes every filter,
+// each bin being loaded once and broadcast to both lanes.  The live filters are cut into
+// contiguous SEGMENTS, one per sweep warp; a segment is a list of RUNS: `run_bins` bins to
+// accumulate, then filter `run_emit` is complete (its sum leaves its lane, the lane restarts at 0).
 struct TirMelParams {
-  int16_t start_a[TIR_MAX_PAIRS], start_b[TIR_MAX_PAIRS]; // first bin with non-zero weight of filter a / b
-  int16_t steps[TIR_MAX_PAIRS];                           // float4 weight records (two bins each)
-  int16_t woff[TIR_MAX_PAIRS];                            // first record in w4[]
-  int8_t filt_a[TIR_MAX_PAIRS], filt_b[TIR_MAX_PAIRS];    // filter ids (b = -1: none)
-  uint8_t warp_np[TIR_MAX_WARPS];                         // pairs handled by mel warp w
-  uint8_t warp_pairs[TIR_MAX_WARPS][TIR_MAX_PAIRS];
-  // (wa[b], wb[b], wa[b+1], wb[b+1]) * 2^-33 : aubio filter weights of the two filters of a pair,
-  // zero padded; 2^-33 undoes the scaled FFT (2x) and the scaled square root (2^32 x), exactly
-  float4 w4[TIR_MAX_W4];
+  int16_t seg_bin0[TIR_MAX_WARPS];  // first bin of the segment
+  int16_t seg_run0[TIR_MAX_WARPS];  // first run
+  int16_t seg_nruns[TIR_MAX_WARPS];
+  int16_t seg_woff[TIR_MAX_WARPS];  // first weight record
+  int16_t run_bins[TIR_MAX_RUNS];
+  int8_t run_emit[TIR_MAX_RUNS];    // filter id completed by the run
+  uint8_t dead[TIR_MAX_FILTERS];    // filter has no non-zero weight: its log-mel value is lg_dead
+  // (w_even[bin], w_odd[bin]) * 2^-33 : aubio weights of the even / odd filter active at a bin of the
+  // segment (0 when none); 2^-33 undoes the scaled FFT (2x) and the scaled square root (2^32 x), exactly
+  float2 w2[TIR_MAX_W2];
   float dct[TIR_MAX_COEFS][TIR_MAX_FILTERS];
   float log_clamp; // (float)2e-42 : aubio VERY_SMALL_NUMBER
-  int n_filters, n_coefs, n_pairs;
+  float lg_dead;   // log10f(log_clamp)
+  int n_filters, n_coefs, n_segs, pad_;
 };
 
 static_assert(sizeof(float4) == 16 && alignof(float4) == 16 && alignof(float2) == 8 && alignof(double2) == 16,
@@ -77,7 +86,7 @@ struct TirSmem {
   static_assert((C::M + 1 + 64) * 32 <= XCH_WORDS, "magnitudes (+ padded mel reads) alias the exchange buffer");
   uint2 pcm[2][PCM_UNITS];   // double buffered: tile N+1 streams in (cp.async) while tile N computes
   float xch[XCH_WORDS];
-  float lg[TIR_MAX_FILTERS * 32];
+  float lg[2][TIR_MAX_FILTERS * 32]; // log-mel values of this and of the previous tile (P4 lags by one)
   float4 win4[16 * C::NW];   // window pairs of the two lanes, pre-scaled by 2^-15
   float4 twp4[16 * C::NW];   // pass-1 twiddles of the two lanes
   float4 twu4[C::NW * 8];    // untangle twiddles [role][slot pair]
@@ -280,29 +289,43 @@ TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg,
   }
 }
 
-// ---- P3 ---------------------------------------------------------------------------------------
-// role w (warp-uniform) = a list of filter pairs, lane f = frame.  Zero padded weights: acc + x*0 ==
-// acc (x is finite: a magnitude, or stale exchange data beyond the last bin row, inside sm.xch).
-TIR_DEV void tir_mel_phase(const float *norm, float *lg, const double2 *logtab, const TirMelParams &mp, int w, int f,
-                           TirP2 nz) {
-  const int np = mp.warp_np[w];
-  for (int q = 0; q < np; q++) {
-    const int p = mp.warp_pairs[w][q];
-    const int n = mp.steps[p];
-    const float *pa = norm + TIR_NORM_IDX(mp.start_a[p], f), *pb = norm + TIR_NORM_IDX(mp.start_b[p], f);
-    const float4 *wp = mp.w4 + mp.woff[p];
-    TirP2 acc = tir_pbc(0.f);
-#pragma unroll 2
+// ---- P3a: mel sweep -----------------------------------------------------------------------------
+// role = segment `seg` (warp-uniform), lane f = frame.  fmat_vecmul order: every filter's sum runs
+// over its bins in ascending order from 0.f; bins where a lane's weight is 0 add +0 (x is finite: a
+// magnitude).  Writes the raw sums to lg.
+TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, int seg, int f, TirP2 nz) {
+  const float *m = norm + TIR_NORM_IDX(mp.seg_bin0[seg], f);
+  const float2 *wp = mp.w2 + mp.seg_woff[seg];
+  const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
+  TirP2 acc = tir_pbc(0.f);
+  for (int r = 0; r < nr; r++) {
+    const int n = mp.run_bins[r0 + r];
+#pragma unroll 4
     for (int b = 0; b < n; b++) {
-      const float4 wv = wp[b];
-      acc = tir_padd(acc, tir_pmulx(tir_pmk(pa[64 * b], pb[64 * b]), tir_pmk(wv.x, wv.y), nz));
-      acc = tir_padd(acc, tir_pmulx(tir_pmk(pa[64 * b + 32], pb[64 * b + 32]), tir_pmk(wv.z, wv.w), nz));
+      const float2 wv = wp[b];
+      acc = tir_padd(acc, tir_pmulx(tir_pbc(m[32 * b]), tir_pmk(wv.x, wv.y), nz));
     }
-    const float va = acc.lo < mp.log_clamp ? mp.log_clamp : acc.lo;
-    lg[mp.filt_a[p] * 32 + f] = tir_log10f_glibc(va, logtab);
-    if (mp.filt_b[p] >= 0) {
-      const float vb = acc.hi < mp.log_clamp ? mp.log_clamp : acc.hi;
-      lg[mp.filt_b[p] * 32 + f] = tir_log10f_glibc(vb, logtab);
+    m += 32 * n, wp += n;
+    const int fe = mp.run_emit[r0 + r];
+    if (fe & 1) lg[fe * 32 + f] = acc.hi, acc.hi = 0.f;
+    else lg[fe * 32 + f] = acc.lo, acc.lo = 0.f;
+  }
+}
+
+// ---- P3b: clamp + log10f, in place ----------------------------------------------------------------
+// role w takes filters w, w + NW, ...: the same number of logarithms for every thread.
+template <int NW>
+TIR_DEV void tir_log_phase(float *lg, const double2 *logtab, const TirMelParams &mp, int w, int f) {
+#pragma unroll
+  for (int q = 0; q < (TIR_MAX_FILTERS + NW - 1) / NW; q++) {
+    const int i = w + NW * q;
+    if (i < mp.n_filters) {
+      float *p = lg + i * 32 + f;
+      if (mp.dead[i]) {
+        *p = mp.lg_dead;
+      } else {
+        *p = tir_log10f_glibc(fmaxf(*p, mp.log_clamp), logtab); // sums are >= +0, never NaN
+      }
     }
   }
 }

@@ -145,12 +145,18 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
       o.twu4[(size_t)t * 8 + s] = w;
     }
 
-  // banded mel weights, two filters (of similar length) per record
+  // mel sweep tables (TirMelParams)
   TirMelParams &mp = o.mel;
   std::memset(&mp, 0, sizeof(mp));
   mp.n_filters = n_filters, mp.n_coefs = n_coefs;
   mp.log_clamp = (float)2.e-42; // aubio_priv.h VERY_SMALL_NUMBER, as the float log10f receives
-  std::vector<int> first(n_filters, 0), len(n_filters, 0);
+  {
+    const double2 lt[16] = TIR_LOGF_TAB_INIT;
+    mp.lg_dead = tir_log10f_glibc(mp.log_clamp, lt);
+  }
+  for (int j = 0; j < n_coefs; j++)
+    for (int f = 0; f < n_filters; f++) mp.dct[j][f] = o.dct[(size_t)j * n_filters + f];
+  std::vector<int> first(n_filters, 0), last(n_filters, -1), live;
   for (int f = 0; f < n_filters; f++) {
     const float *filt = o.filters.data() + (size_t)f * o.L;
     int a = -1, b = -2;
@@ -159,47 +165,78 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
         if (a < 0) a = i;
         b = i;
       }
-    first[f] = a < 0 ? 0 : a, len[f] = a < 0 ? 0 : b - a + 1;
+    if (a < 0) {
+      mp.dead[f] = 1;
+    } else {
+      first[f] = a, last[f] = b;
+      live.push_back(f);
+    }
   }
-  std::vector<int> order(n_filters);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
-  int n_pairs = 0, nrec = 0;
-  for (int i = 0; i < n_filters; i += 2) {
-    const int fa = order[i], fb = i + 1 < n_filters ? order[i + 1] : -1;
-    const int p = n_pairs++;
-    const int steps = (len[fa] + 1) / 2; // len[fa] >= len[fb]
-    if (nrec + steps > TIR_MAX_W4) return false;
-    mp.filt_a[p] = (int8_t)fa, mp.filt_b[p] = (int8_t)fb;
-    mp.start_a[p] = (int16_t)first[fa], mp.start_b[p] = (int16_t)(fb >= 0 ? first[fb] : first[fa]);
-    mp.steps[p] = (int16_t)steps, mp.woff[p] = (int16_t)nrec;
-    const float *fa_w = o.filters.data() + (size_t)fa * o.L + first[fa];
-    const float *fb_w = fb >= 0 ? o.filters.data() + (size_t)fb * o.L + first[fb] : nullptr;
+  // the sweep needs: completion order == filter order, and same-parity filters disjoint
+  for (size_t i = 0; i + 1 < live.size(); i++)
+    if (last[live[i]] > last[live[i + 1]] || first[live[i]] > first[live[i + 1]]) return false;
+  for (size_t i = 0; i < live.size(); i++)
+    for (size_t j = i + 1; j < live.size(); j++)
+      if (((live[i] ^ live[j]) & 1) == 0 && first[live[j]] <= last[live[i]]) return false;
+  // contiguous segments of live filters for the NW - n_coefs sweep warps, balanced on issue slots
+  const int n_sweep = NW - n_coefs;
+  auto seg_cost = [&](int ia, int ib) { // live[ia..ib)
+    return 21 * (last[live[ib - 1]] - first[live[ia]] + 1) / 4 + 26 * (ib - ia) + 20; // measured (ncu) issue slots
+  };
+  const int nl = (int)live.size();
+  std::vector<int> cut(n_sweep + 1, nl);
+  cut[0] = 0;
+  if (nl > 0) {
+    // smallest bottleneck by bisection on the cost bound, greedy fill
+    int lo = 0, hi = seg_cost(0, nl);
+    auto fits = [&](int bound, std::vector<int> *out) {
+      int i = 0;
+      for (int s = 0; s < n_sweep; s++) {
+        int j = i;
+        while (j < nl && seg_cost(i, j + 1) <= bound) j++;
+        if (out) (*out)[s + 1] = j;
+        i = j;
+      }
+      return i == nl;
+    };
+    while (lo < hi) {
+      const int mid = (lo + hi) / 2;
+      if (fits(mid, nullptr)) hi = mid; else lo = mid + 1;
+    }
+    fits(lo, &cut);
+  }
+  int nruns = 0, nw2 = 0, nsegs = 0;
+  for (int s = 0; s < n_sweep; s++) {
+    const int ia = cut[s], ib = cut[s + 1];
+    const int seg = nsegs++;
+    mp.seg_run0[seg] = (int16_t)nruns, mp.seg_woff[seg] = (int16_t)nw2;
+    if (ia >= ib) {
+      mp.seg_bin0[seg] = 0, mp.seg_nruns[seg] = 0;
+      continue;
+    }
+    const int b0 = first[live[ia]], b1 = last[live[ib - 1]];
+    if (nw2 + (b1 - b0 + 1) > TIR_MAX_W2 || nruns + (ib - ia) > TIR_MAX_RUNS) return false;
+    mp.seg_bin0[seg] = (int16_t)b0;
     // magnitudes arrive as 2^33 * |X[k]| (FFT scaled by 2, sqrt by 2^32); power-of-two scaling is exact
     const float sc = 1.0f / 8589934592.0f;
-    for (int s = 0; s < steps; s++) {
-      float4 w{0, 0, 0, 0};
-      const int b0 = 2 * s, b1 = 2 * s + 1;
-      if (b0 < len[fa]) w.x = fa_w[b0] * sc;
-      if (b1 < len[fa]) w.z = fa_w[b1] * sc;
-      if (fb >= 0 && b0 < len[fb]) w.y = fb_w[b0] * sc;
-      if (fb >= 0 && b1 < len[fb]) w.w = fb_w[b1] * sc;
-      mp.w4[nrec + s] = w;
+    for (int bin = b0; bin <= b1; bin++) {
+      float2 w{0.f, 0.f};
+      for (int i = ia; i < ib; i++) {
+        const int f = live[i];
+        if (bin < first[f] || bin > last[f]) continue;
+        const float v = o.filters[(size_t)f * o.L + bin] * sc;
+        if (f & 1) w.y = v; else w.x = v;
+      }
+      mp.w2[nw2++] = w;
     }
-    nrec += steps;
+    int done = b0; // bins [b0, done) are already covered by earlier runs
+    for (int i = ia; i < ib; i++) {
+      const int f = live[i];
+      mp.run_bins[nruns] = (int16_t)(last[f] + 1 - done), mp.run_emit[nruns] = (int8_t)f;
+      done = last[f] + 1, nruns++;
+    }
+    mp.seg_nruns[seg] = (int16_t)(ib - ia);
   }
-  mp.n_pairs = n_pairs;
-  for (int j = 0; j < n_coefs; j++)
-    for (int f = 0; f < n_filters; f++) mp.dct[j][f] = o.dct[(size_t)j * n_filters + f];
-  // longest-processing-time assignment of the pairs to the NW mel warps
-  std::vector<int> porder(n_pairs);
-  std::iota(porder.begin(), porder.end(), 0);
-  std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return mp.steps[a] > mp.steps[b]; });
-  std::vector<int> load(NW, 0);
-  for (int p : porder) {
-    const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-    mp.warp_pairs[w][mp.warp_np[w]++] = (uint8_t)p;
-    load[w] += 9 * mp.steps[p] + 2 * 40 + 12; // issue slots: mel steps + two clamp/log10f + loop set-up
-  }
+  mp.n_segs = nsegs;
   return true;
 }

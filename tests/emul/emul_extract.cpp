@@ -54,13 +54,15 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
         if (w == 0) tir_pass2_compute<WIN, true>(*sm, w, lane, regs[w * 32 + lane], nz);
         else tir_pass2_compute<WIN, false>(*sm, w, lane, regs[w * 32 + lane], nz);
       }
+    for (int w = tab.mel.n_coefs; w < C::NW; w++)
+      for (int lane = 0; lane < 32; lane++) tir_mel_sweep(sm->xch, sm->lg[b], tab.mel, w - tab.mel.n_coefs, lane, nz);
     for (int w = 0; w < C::NW; w++)
-      for (int lane = 0; lane < 32; lane++) tir_mel_phase(sm->xch, sm->lg, sm->logtab, tab.mel, w, lane, nz);
+      for (int lane = 0; lane < 32; lane++) tir_log_phase<C::NW>(sm->lg[b], sm->logtab, tab.mel, w, lane);
     for (int j = 0; j < 2; j++)
       for (int lane = 0; lane < nvalid; lane++) {
         float c;
         int32_t v;
-        tir_dct_phase(sm->lg, tab.mel, j, lane, c, v);
+        tir_dct_phase(sm->lg[b], tab.mel, j, lane, c, v);
         coef[(f0 + lane) * 2 + j] = c;
         vq[(f0 + lane) * 2 + j] = v;
       }

