@@ -68,12 +68,13 @@ struct TirDb {
   uint32_t n_blocks = 0;
   uint64_t n_indexed = 0;
   DevBuf order, key1, uid, key2, block_start;
+  DevBuf pattern; // u32 per uuid rank: windows of the current batch that hold a row of it (all zero between batches)
 };
 
 void tir_db_destroy(TirDb *db) {
   if (!db) return;
   for (DevBuf *b : {&db->uuids, &db->row_off, &db->v1, &db->v2, &db->alive, &db->order, &db->key1, &db->uid, &db->key2,
-                    &db->block_start})
+                    &db->block_start, &db->pattern})
     if (b->p) cudaFree(b->p);
   delete db;
 }
@@ -173,6 +174,9 @@ static int db_build_index(tir_ctx *ctx, TirDb *db) {
   int rc;
   if ((rc = tir_reserve(ctx, db->order, (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
   if ((rc = tir_reserve(ctx, db->block_start, ((size_t)db->n_blocks + 1) * 8))) return rc;
+  const size_t pat_bytes = ((size_t)db->n_blocks * TIR_BLOCK_UUIDS + 16) * 4; // whole blocks, whole uint4
+  if ((rc = tir_reserve(ctx, db->pattern, pat_bytes))) return rc;
+  TIR_CUDA(ctx, cudaMemsetAsync(db->pattern.p, 0, pat_bytes, st));
   if (n == 0 || rows == 0) {
     TIR_CUDA(ctx, cudaMemsetAsync(db->block_start.p, 0, ((size_t)db->n_blocks + 1) * 8, st));
     db->dirty = false;
@@ -359,22 +363,179 @@ __device__ __forceinline__ uint64_t tir_warp_bound(const int32_t *__restrict__ k
   return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
-// grid (n_blocks, n_queries).  Votes of one query into the uuids of one index block.
+// ---- shared-window path -------------------------------------------------------------------------
+// The query side truncates max1 to an integer (src/fp_handler.c:290), so with coefs == 1 all the
+// frames of all the queries of a batch probe a handful of DISTINCT windows (one per integer value of
+// max1 that occurs).  "uuid has a row in window k" does not depend on the query, so the batch scans
+// every distinct window ONCE, leaves a bit pattern per uuid, reduces "greatest uuid rank per
+// pattern", and each query then only weighs the patterns:
+//     match_count(q, uuid) = sum_k weight(q, k) * [bit k of pattern(uuid)]
+// -- the same votes, the same winner and tie rule as the per-query path, for a cost that is
+// independent of the number of queries.  Batches with more than TIR_MAX_SHARED distinct windows
+// (coefs == 2: the max2 bounds are real numbers) take the per-query kernel below; the choice is
+// made on the device (TirBatch::use_general), nothing is read back.
+#define TIR_MAX_SHARED 12
+struct TirBatch {
+  uint32_t n_distinct, use_general;
+  TirWindow distinct[TIR_MAX_SHARED];
+};
+
+// one CTA: distinct windows of the whole batch; every folded window learns its bit (TirWindow::pad).
+// Rounds: every thread walks its queries' windows while they are in the list; the lowest thread
+// that is stuck on an unknown window appends it; at most TIR_MAX_SHARED + 1 rounds.
+__global__ void __launch_bounds__(1024)
+    tir_batch_windows_kernel(TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
+                             const uint64_t *__restrict__ frame_off, uint32_t n_queries, TirBatch *__restrict__ batch) {
+  __shared__ TirWindow s_w[TIR_MAX_SHARED];
+  __shared__ uint32_t s_n, s_cand;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  uint32_t q = tid, i = 0;
+  bool over = false;
+  for (;;) {
+    const uint32_t n = s_n;
+    TirWindow w;
+    bool stuck = false;
+    while (q < n_queries) { // advance while the current window is known
+      if (i >= n_windows[q]) { q += blockDim.x, i = 0; continue; }
+      TirWindow *wp = windows + frame_off[q] + i;
+      w = *wp;
+      uint32_t bit = 0xffffffffu;
+      for (uint32_t k = 0; k < n; k++)
+        if (s_w[k].lo1 == w.lo1 && s_w[k].hi1 == w.hi1 && s_w[k].lo2 == w.lo2 && s_w[k].hi2 == w.hi2) { bit = k; break; }
+      if (bit == 0xffffffffu) { stuck = true; break; }
+      wp->pad = bit, i++;
+    }
+    __syncthreads();
+    if (tid == 0) s_cand = 0xffffffffu;
+    __syncthreads();
+    if (stuck) atomicMin(&s_cand, tid);
+    __syncthreads();
+    const uint32_t cand = s_cand;
+    if (cand == 0xffffffffu) break;                 // every window has its bit
+    if (n >= TIR_MAX_SHARED) { over = true; break; } // too many distinct windows: per-query path
+    if (tid == cand) s_w[n] = w;
+    __syncthreads();
+    if (tid == 0) s_n = n + 1;
+    __syncthreads();
+  }
+  const uint32_t n = s_n;
+  if (tid < TIR_MAX_SHARED && tid < n) batch->distinct[tid] = s_w[tid];
+  if (tid == 0) batch->n_distinct = over ? 0 : n, batch->use_general = over ? 1u : 0u;
+}
+
+// grid (n_blocks, TIR_MAX_SHARED): rows of distinct window k in index block blk -> pattern bits
+template <int COEFS>
+__global__ void __launch_bounds__(TIR_MATCH_THREADS)
+    tir_pattern_scan_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
+                            const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
+                            const TirBatch *__restrict__ batch, uint32_t *__restrict__ pattern) {
+  const uint32_t blk = blockIdx.x, k = blockIdx.y;
+  if (batch->use_general || k >= batch->n_distinct) return;
+  __shared__ uint64_t s_range[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
+  if (bs == be) return;
+  const TirWindow w = batch->distinct[k];
+  if (warp == 0) {
+    const uint64_t r = tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
+    if (lane == 0) s_range[0] = r;
+  } else if (warp == 1) {
+    const uint64_t r = tir_warp_bound<true>(key1, bs, be, w.hi1, lane);
+    if (lane == 0) s_range[1] = r;
+  }
+  __syncthreads();
+  const uint64_t r0 = s_range[0], r1 = s_range[1];
+  uint32_t *pat = pattern + (size_t)blk * TIR_BLOCK_UUIDS;
+  for (uint64_t r = r0 + tid; r < r1; r += TIR_MATCH_THREADS) {
+    if (COEFS >= 2) {
+      const int32_t k2 = __ldg(key2 + r);
+      if (k2 < w.lo2 || k2 > w.hi2) continue;
+    }
+    atomicOr(pat + __ldg(uid + r), 1u << k); // group by audio_uuid: a bit, not a count
+  }
+}
+
+// greatest rank (+1) per pattern; clears the patterns for the next batch.  Warp-aggregated through
+// a shared-memory table, one global atomicMax per CTA and occupied pattern.
+__global__ void __launch_bounds__(256)
+    tir_pattern_reduce_kernel(uint32_t *__restrict__ pattern, uint32_t n_audio, const TirBatch *__restrict__ batch,
+                              uint32_t *__restrict__ max_rank1) {
+  if (batch->use_general || batch->n_distinct == 0) return;
+  __shared__ uint32_t s_max[1 << TIR_MAX_SHARED];
+  for (int i = threadIdx.x; i < (1 << TIR_MAX_SHARED); i += blockDim.x) s_max[i] = 0;
+  __syncthreads();
+  const uint32_t n4 = (n_audio + 3) / 4; // the buffer is padded to whole uint4
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    uint4 p = reinterpret_cast<uint4 *>(pattern)[i];
+    if (p.x | p.y | p.z | p.w) {
+      if (p.x) atomicMax(&s_max[p.x], 4 * i + 1);
+      if (p.y) atomicMax(&s_max[p.y], 4 * i + 2);
+      if (p.z) atomicMax(&s_max[p.z], 4 * i + 3);
+      if (p.w) atomicMax(&s_max[p.w], 4 * i + 4);
+      reinterpret_cast<uint4 *>(pattern)[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();
+  const uint32_t np = 1u << batch->n_distinct;
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
+    if (s_max[i]) atomicMax(max_rank1 + i, s_max[i]);
+}
+
+// one warp per query: weigh the occupied patterns
+__global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
+                                           const uint64_t *__restrict__ frame_off, uint32_t n_queries,
+                                           const TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
+                                           unsigned long long *__restrict__ best) {
+  if (batch->use_general) return;
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= n_queries) return;
+  const uint32_t K = batch->n_distinct, nw = n_windows[q];
+  const TirWindow *wq = windows + frame_off[q];
+  uint32_t wk = 0; // lane k holds weight(q, k)
+  for (uint32_t i = 0; i < nw; i++) {
+    const TirWindow w = wq[i];
+    if (w.pad == lane) wk += w.weight;
+  }
+  unsigned long long bestv = 0;
+  const uint32_t np = K ? (1u << K) : 0;
+  for (uint32_t p0 = 0; p0 < np; p0 += 32) {
+    const uint32_t p = p0 + lane;
+    const uint32_t r1 = p < np ? __ldg(max_rank1 + p) : 0;
+    uint32_t score = 0;
+    for (uint32_t k = 0; k < K; k++) {
+      const uint32_t w = __shfl_sync(0xffffffffu, wk, k);
+      if ((p >> k) & 1u) score += w;
+    }
+    if (r1 && score) bestv = max(bestv, ((unsigned long long)score << 32) | (unsigned long long)(r1 - 1));
+  }
+  for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
+  if (lane == 0) best[q] = bestv;
+}
+
+// ---- per-query path -------------------------------------------------------------------------------
+// persistent grid over (index block, query) items.  Votes of one query into the uuids of one block.
 template <int COEFS>
 __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_match_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
                      const uint64_t *__restrict__ block_start, const TirWindow *__restrict__ windows,
                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
-                     unsigned long long *__restrict__ best, uint32_t q_base) {
+                     unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
+                     const TirBatch *__restrict__ batch) {
+  if (!batch->use_general) return;
   __shared__ uint32_t s_cnt[TIR_BLOCK_UUIDS / 2];  // u16 vote counters, two per word
   __shared__ uint32_t s_seen[TIR_BLOCK_UUIDS / 32]; // per-window "uuid already voted" bits
   __shared__ uint64_t s_range[2];
   __shared__ unsigned long long s_best[TIR_MATCH_THREADS / 32];
-  const uint32_t blk = blockIdx.x, q = q_base + blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t n_items = (uint64_t)n_blocks * n_queries;
+  for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const uint32_t blk = (uint32_t)(item % n_blocks), q = (uint32_t)(item / n_blocks);
+  __syncthreads(); // the previous item is done with the shared arrays
   const uint64_t bs = block_start[blk], be = block_start[blk + 1];
   const uint32_t nw = n_windows[q];
-  if (bs == be || nw == 0) return;
+  if (bs == be || nw == 0) continue;
   const TirWindow *wq = windows + frame_off[q];
   uint16_t *cnt16 = reinterpret_cast<uint16_t *>(s_cnt);
   for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) s_cnt[i] = 0;
@@ -421,6 +582,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     if (bestv) atomicMax(best + q, bestv);
   }
   (void)any;
+  } // items
 }
 
 __global__ void tir_finalize_kernel(const unsigned long long *__restrict__ best, const uint32_t *__restrict__ order,
@@ -482,9 +644,11 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   for (uint32_t q = 0; q < n_queries; q++)
     if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 65535)
       return tir_fail(ctx, TIR_ERR_ARG, "a query may have at most 65535 frames (u16 vote counters)");
-  // scratch: frame_off (device) | n_windows | best | windows
+  // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | windows
   const size_t o_foff = 0, o_nw = o_foff + ((size_t)n_queries + 1) * 8, o_best = (o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
-  const size_t o_win = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  const size_t o_batch = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  const size_t o_maxr = (o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
+  const size_t o_win = o_maxr + ((size_t)4 << TIR_MAX_SHARED);
   const size_t bytes = o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
   if ((rc = tir_reserve(ctx, ctx->d_qmeta, bytes))) return rc;
   if ((rc = tir_reserve_host(ctx, ctx->h_meta, ((size_t)n_queries + 1) * 8))) return rc;
@@ -492,7 +656,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   TIR_CUDA(ctx, cudaStreamSynchronize(st));
   std::memcpy(ctx->h_meta.p, frame_off, ((size_t)n_queries + 1) * 8);
   TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, ctx->h_meta.p, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
-  TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, (size_t)n_queries * 8, st));
+  TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_win - o_best, st)); // best, batch, max_rank1
   TirMatchParams mp;
   mp.coefs = coefs;
   mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
@@ -502,6 +666,8 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
   unsigned long long *d_best = (unsigned long long *)(d + o_best);
+  TirBatch *d_batch = (TirBatch *)(d + o_batch);
+  uint32_t *d_maxr = (uint32_t *)(d + o_maxr);
   TirWindow *d_win = (TirWindow *)(d + o_win);
   if (d_coef)
     tir_qprep_kernel<true><<<n_queries, 128, 0, st>>>(nullptr, d_coef, d_foff, mp, d_win, d_nw);
@@ -509,19 +675,31 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     tir_qprep_kernel<false><<<n_queries, 128, 0, st>>>(d_y, nullptr, d_foff, mp, d_win, d_nw);
   ctx->launches++;
   if (db->n_blocks && db->n_indexed) {
+    const int32_t *k1 = (const int32_t *)db->key1.p, *k2 = (const int32_t *)db->key2.p;
+    const uint16_t *uid = (const uint16_t *)db->uid.p;
+    const uint64_t *bst = (const uint64_t *)db->block_start.p;
+    uint32_t *pat = (uint32_t *)db->pattern.p;
+    const uint32_t n_ranks = db->n_blocks * TIR_BLOCK_UUIDS;
     if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    for (uint32_t q0 = 0; q0 < n_queries; q0 += 32768) { // grid.y limit
-      dim3 grid(db->n_blocks, std::min<uint32_t>(32768, n_queries - q0));
-      if (coefs >= 2)
-        tir_match_kernel<2><<<grid, TIR_MATCH_THREADS, 0, st>>>((const int32_t *)db->key1.p, (const uint16_t *)db->uid.p,
-                                                                (const int32_t *)db->key2.p, (const uint64_t *)db->block_start.p,
-                                                                d_win, d_nw, d_foff, d_best, q0);
-      else
-        tir_match_kernel<1><<<grid, TIR_MATCH_THREADS, 0, st>>>((const int32_t *)db->key1.p, (const uint16_t *)db->uid.p,
-                                                                (const int32_t *)db->key2.p, (const uint64_t *)db->block_start.p,
-                                                                d_win, d_nw, d_foff, d_best, q0);
-      ctx->launches++;
-    }
+    tir_batch_windows_kernel<<<1, 1024, 0, st>>>(d_win, d_nw, d_foff, n_queries, d_batch);
+    // shared-window path (no-ops when the batch has too many distinct windows) ...
+    const dim3 pgrid(db->n_blocks, TIR_MAX_SHARED);
+    if (coefs >= 2) tir_pattern_scan_kernel<2><<<pgrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_batch, pat);
+    else tir_pattern_scan_kernel<1><<<pgrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_batch, pat);
+    const uint32_t rgrid = std::min<uint32_t>((n_ranks / 4 + 255) / 256, (uint32_t)ctx->num_sms * 4);
+    tir_pattern_reduce_kernel<<<rgrid, 256, 0, st>>>(pat, n_ranks, d_batch, d_maxr);
+    tir_pattern_resolve_kernel<<<(n_queries * 32 + 255) / 256, 256, 0, st>>>(d_win, d_nw, d_foff, n_queries, d_batch, d_maxr,
+                                                                           d_best);
+    // ... per-query path (returns at once otherwise): persistent over (block, query) items
+    const uint64_t items = (uint64_t)db->n_blocks * n_queries;
+    const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 6);
+    if (coefs >= 2)
+      tir_match_kernel<2><<<ggrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_win, d_nw, d_foff, d_best, db->n_blocks,
+                                                               n_queries, d_batch);
+    else
+      tir_match_kernel<1><<<ggrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_win, d_nw, d_foff, d_best, db->n_blocks,
+                                                               n_queries, d_batch);
+    ctx->launches += 5;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
       ctx->ev_valid[1] = true;

@@ -71,6 +71,37 @@ def test_differential_vs_sqlite(gpu_ctx, oracle, n_audio, null_frac, seed):
             assert gpu_result(h) == sql_result(exp), (coefs, tol, lo, hi)
 
 
+def test_shared_window_and_per_query_paths_agree(gpu_ctx, oracle):
+    """The engine has two evaluation orders for the same votes: a batch with few distinct windows is
+    scanned once for all its queries (shared-window path), a batch with many takes the per-query
+    kernel.  Same DB, same queries through both (one call per query vs one call for all) and SQLite."""
+    rng = np.random.default_rng(5)
+    db = synth_db.make_db(4000, 5, 30, seed=31, lo=-22.0, hi=42.0, near_int_frac=0.5)
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    ys = []
+    for qi in range(36):                      # every query: <= 4 integer values of max1, batch: ~60
+        base = -20 + (qi * 7) % 58
+        ys.append(synth_db.random_y(rng, int(rng.integers(3, 80)), lo=base, hi=base + 3.99, near_int_frac=0.6))
+    ys.append(db[17][1].copy())
+    ys.append(np.zeros((0, 2)))
+    foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    for coefs, tol in ((1, 0.001), (1, 0.02), (2, 1.5)):
+        batch = gpu_ctx.match(np.concatenate(ys), foff, coefs, tol)
+        for qi, y in enumerate(ys):
+            single = gpu_ctx.match(y, None, coefs, tol)[0] if y.shape[0] else batch[qi]
+            assert gpu_result(single) == gpu_result(batch[qi]), (coefs, tol, qi)
+            if qi % 3 == 0 and y.shape[0]:
+                assert gpu_result(batch[qi]) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, qi)
+    # exactly TIR_MAX_SHARED (12) and 13 distinct windows in one batch
+    for n_int in (12, 13):
+        y = np.stack([np.arange(n_int) + 10.2, np.zeros(n_int)], axis=1)
+        h = gpu_ctx.match(y, None, 1, 0.3)[0]
+        assert gpu_result(h) == sql_result(sq.search(y, 1, 0.3)), n_int
+
+
 def test_ties_resolve_to_greatest_uuid(gpu_ctx, oracle):
     # many audios with identical rows, spread over several index blocks (> 16384 uuids)
     n = 40000
