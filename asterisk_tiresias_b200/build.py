@@ -8,7 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtiresias_gpu.so")
-SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_tables.cpp"]
+TOOL = os.path.join(HERE, "..", "tools", "tir_concurrent_bench.bin")
+SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_tables.cpp", "tir_batcher.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 unless told not to; every fused
@@ -52,6 +53,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    # C++ driver of the concurrent-channel bench (plain C ABI client; tools/tir_concurrent_bench.cpp)
+    tool_src = os.path.join(HERE, "..", "tools", "tir_concurrent_bench.cpp")
+    if os.path.exists(tool_src):
+        r = subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", tool_src, "-o", TOOL, "-L" + HERE, "-ltiresias_gpu",
+                            "-Wl,-rpath,$ORIGIN/../asterisk_tiresias_b200"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building tools/tir_concurrent_bench failed")
     with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -75,6 +75,16 @@ def lib():
             L.tir_merge_hits_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
             L.tir_shard_of.restype = C.c_uint32
             L.tir_shard_of.argtypes = [vp, C.c_uint32]
+            L.tir_batcher_start.argtypes = [vp, C.c_uint32, C.c_uint32]
+            L.tir_batcher_stop.argtypes = [vp]
+            L.tir_search_one.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_batcher_stats.argtypes = [vp, u64p, u64p, u64p]
+            L.tir_stream_open.argtypes = [vp, C.POINTER(vp)]
+            L.tir_stream_feed.argtypes = [vp, vp, C.c_uint32]
+            L.tir_stream_samples.restype = C.c_uint64
+            L.tir_stream_samples.argtypes = [vp]
+            L.tir_stream_finish.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_stream_close.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -229,6 +239,29 @@ class Context:
                                    int(freq_ignore_high), _p(hits)))
         return hits
 
+    # ---- concurrent front-end ---------------------------------------------------------------
+    def batcher_start(self, max_batch=1024, max_wait_us=200):
+        self._chk(lib().tir_batcher_start(self._h, max_batch, max_wait_us))
+
+    def batcher_stop(self):
+        self._chk(lib().tir_batcher_stop(self._h))
+
+    def batcher_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._chk(lib().tir_batcher_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    def search_one(self, pcm, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
+        """Blocking single-recording search (ctypes releases the GIL: callable from many threads)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        hit = np.zeros(1, HIT_DTYPE)
+        self._chk(lib().tir_search_one(self._h, _p(pcm), pcm.size, coefs, float(tolerance), int(freq_ignore_low),
+                                       int(freq_ignore_high), _p(hit)))
+        return hit[0]
+
+    def stream(self):
+        return Stream(self)
+
     def merge_hits_dev(self, d_gathered_ptr, n_shards, n_queries, d_out_ptr):
         self._chk(lib().tir_merge_hits_dev(self._h, C.c_void_p(d_gathered_ptr), n_shards, n_queries,
                                            C.c_void_p(d_out_ptr)))
@@ -237,3 +270,33 @@ class Context:
 def shard_of(uuid16, n_shards: int) -> int:
     u = np.ascontiguousarray(uuid16, dtype=np.uint8)
     return int(lib().tir_shard_of(_p(u), n_shards))
+
+
+class Stream:
+    """tir_stream wrapper: feed slinear chunks as they arrive, finish() searches the recording."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+        self._s = C.c_void_p()
+        ctx._chk(lib().tir_stream_open(ctx._h, C.byref(self._s)))
+
+    def feed(self, chunk):
+        chunk = np.ascontiguousarray(chunk, dtype=np.int16)
+        self._ctx._chk(lib().tir_stream_feed(self._s, _p(chunk), chunk.size))
+
+    @property
+    def samples(self):
+        return int(lib().tir_stream_samples(self._s))
+
+    def finish(self, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
+        hit = np.zeros(1, HIT_DTYPE)
+        self._ctx._chk(lib().tir_stream_finish(self._s, coefs, float(tolerance), int(freq_ignore_low), int(freq_ignore_high),
+                                               _p(hit)))
+        return hit[0]
+
+    def close(self):
+        if self._s:
+            lib().tir_stream_close(self._s)
+            self._s = C.c_void_p()
+
+    __del__ = close

@@ -118,6 +118,7 @@ int tir_open(const tir_cfg *cfg, tir_ctx **out) {
 
 void tir_close(tir_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->batcher) tir_batcher_destroy(ctx->batcher), ctx->batcher = nullptr; // serves what is queued, then joins
   if (ctx->num_sms) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);

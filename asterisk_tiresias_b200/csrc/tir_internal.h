@@ -11,7 +11,8 @@
 #include "../../include/tiresias_gpu.h"
 #include "tir_tables.h"
 
-struct TirDb; // tir_match.cu
+struct TirDb;      // tir_match.cu
+struct TirBatcher; // tir_batcher.cpp
 
 struct DevBuf {
   void *p = nullptr;
@@ -37,6 +38,7 @@ struct tir_ctx {
   // pinned staging for small metadata
   DevBuf h_meta;
   TirDb *db = nullptr;
+  TirBatcher *batcher = nullptr;
 };
 
 int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...);
@@ -58,3 +60,6 @@ size_t tir_extract_smem_bytes(int win);
 
 // tir_match.cu
 void tir_db_destroy(TirDb *db);
+
+// tir_batcher.cpp
+void tir_batcher_destroy(TirBatcher *b);

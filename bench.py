@@ -164,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -252,6 +252,7 @@ def match_bench(ctx, args, rank, world, device, dist):
     # headline: coefs = 1, what the dialplan application passes (src/application_handler.c:180)
     ms, kernel_ms, launches = timed(1, Q, max(args.steps, 5))
     hits = d_final.cpu().numpy().view(capi.HIT_DTYPE)
+    search_e2e = search_bench(ctx, args, rank, world, device, dist, Q)
     # verification on rank 0 / single GPU: brute-force restatement of the vote for a few queries
     verified = None
     if world == 1:
@@ -272,11 +273,63 @@ def match_bench(ctx, args, rank, world, device, dist):
            "per_query_path_coefs2": {"value": nq2 / (ms2 * 1e-3), "unit": "queries/s", "ms_per_batch": ms2, "queries_per_batch": nq2,
                                      "kernel_ms_rank0": k_ms2, "coefs": 2, "tolerance": 0.001},
            "self_matches_top": int((hits["match_count"][: Q // 10] > 0).sum()), "verified_queries": verified,
+           "search_e2e": search_e2e,
            "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None,
                         "unit": "GB/s", "algorithmic_bytes_per_batch_this_rank": alg,
                         "note": "SURVEY 8d charge F_q*8 + sum_k(16 + 8*R_k) + 24 per QUERY; the shared-window path reads each distinct window once per BATCH (6 B per row in it) plus 4 B per uuid for the pattern sweep, so the charged figure can exceed the HBM peak"}}
     del uu, v1, v2
     return res
+
+
+def search_bench(ctx, args, rank, world, device, dist, Q):
+    """fp_search_fingerprint_info end to end through the C ABI (tir_search): Q query clips of 3 s
+    (the dialplan default, src/application_handler.c:60) in pinned HOST memory -> extraction ->
+    match against this rank's shard -> hits in host memory; with N ranks every rank searches its
+    shard and the per-query winners are merged after an all-gather."""
+    import ctypes as C
+    import torch
+    from asterisk_tiresias_b200 import capi, synth
+    n = 3 * SR
+    pool = np.stack([synth.make_clip(880000 + i, 3.0, SR, ulaw=True) for i in range(50)])
+    h_pcm = torch.from_numpy(pool[np.arange(Q) % 50].reshape(-1).copy()).pin_memory()
+    off = np.arange(Q + 1, dtype=np.uint64) * n
+    h_hits = torch.zeros(Q * 24, dtype=torch.uint8).pin_memory()
+    d_loc = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
+    d_all = torch.zeros(world * Q * 24, dtype=torch.uint8, device=device)
+    d_out = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
+    L = capi.lib()
+
+    def step():
+        rc = L.tir_search(ctx._h, C.c_void_p(h_pcm.data_ptr()), off.ctypes.data_as(C.c_void_p), Q, 1, C.c_double(0.001), -1, -1,
+                          C.c_void_p(h_hits.data_ptr()))
+        if rc != 0:
+            raise capi.TirError(rc, L.tir_last_error(ctx._h).decode())
+        if world > 1:
+            d_loc.copy_(h_hits, non_blocking=True)
+            dist.all_gather_into_tensor(d_all, d_loc)
+            ctx.merge_hits_dev(d_all.data_ptr(), world, Q, d_out.data_ptr())
+            h_hits.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(args.steps, 5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tt = torch.tensor([ms], device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+    hits = h_hits.numpy().view(capi.HIT_DTYPE)
+    return {"value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "queries_per_batch": Q, "seconds_per_query_clip": 3.0,
+            "h2d_bytes_per_step": int(h_pcm.numel() * 2), "d2h_bytes_per_step": Q * 24, "found": int((hits["match_count"] > 0).sum()),
+            "api": "tir_search (host PCM16 -> winner uuid / match_count / frame_count in host memory)"}
 
 
 def verify_match(hits, qv, v1, uu, n_check=4):
@@ -307,7 +360,27 @@ def verify_match(hits, qv, v1, uu, n_check=4):
 
 # ------------------------------------------------------------------------------------ our arm
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout; libraries (NCCL's version banner, ...) also write
+    there from C.  Point fd 1 at stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -317,6 +390,8 @@ def main():
     ap.add_argument("--match-fps", type=int, default=0, help="fingerprints (uuids) in the match DB, total over ranks; 0 = 10M")
     ap.add_argument("--match-queries", type=int, default=1000)
     ap.add_argument("--match-queries-coefs2", type=int, default=100, help="queries of the coefs=2 (per-query path) leg")
+    ap.add_argument("--channels", type=int, default=1000, help="concurrent channel threads of the config[4] leg")
+    ap.add_argument("--channels-db-fps", type=int, default=1_000_000)
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -474,15 +549,27 @@ def main():
             log("match leg failed:", repr(ex))
             match = {"error": str(ex)[:300]}
 
+    # ---- BASELINE config[4]: concurrent channels through the batcher (C++ client of the C ABI) ----
+    concurrent = None
+    tool = os.path.join(ROOT, "tools", "tir_concurrent_bench.bin")
+    if rank == 0 and world == 1 and not args.no_match and os.path.exists(tool):
+        try:
+            torch.cuda.empty_cache()
+            r = subprocess.run([tool, "--threads", str(args.channels), "--rounds", "5", "--db-fps", str(args.channels_db_fps),
+                                "--device", str(local_rank)], capture_output=True, text=True, timeout=600)
+            concurrent = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            concurrent = {"error": str(ex)[:300]}
+
     if rank == 0:
         line = {
             "metric": "audio_seconds_fingerprinted_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_clips), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "frames_per_second": world * F / (ms_step * 1e-3), "match": match,
+            "frames_per_second": world * F / (ms_step * 1e-3), "match": match, "concurrent_channels": concurrent,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

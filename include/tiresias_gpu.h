@@ -140,6 +140,30 @@ int tir_match_dev(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, 
 int tir_search(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
                double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits);
 
+/* ---- concurrent callers ------------------------------------------------------------------------
+ * The dialplan application runs fp_search_fingerprint_info() on one PBX thread per channel
+ * (src/application_handler.c:180); in the reference those threads serialise on the one SQLite
+ * connection (src/fp_handler.c:45).  With a batcher running, concurrent tir_search_one() callers
+ * that share (coefs, tolerance, freq_ignore_*) are served by ONE batched tir_search: a caller waits
+ * at most max_wait_us for company, a batch holds at most max_batch recordings.  Without a batcher
+ * tir_search_one() is a batch of one.  Results are those of tir_search on the same recording. */
+int tir_batcher_start(tir_ctx *ctx, uint32_t max_batch, uint32_t max_wait_us);
+int tir_batcher_stop(tir_ctx *ctx); /* serves the queued requests, then stops; tir_close() does it too */
+int tir_search_one(tir_ctx *ctx, const int16_t *pcm, uint64_t n_samples, int coefs, double tolerance,
+                   int freq_ignore_low, int freq_ignore_high, tir_hit *hit);
+int tir_batcher_stats(tir_ctx *ctx, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen);
+
+/* Streaming recording: replaces record_voice()'s /tmp/tiresias-<uuid>.wav round trip
+ * (src/application_handler.c:153-155,248-312).  Feed the channel's slinear frames as ast_read
+ * delivers them; tir_stream_finish() is tir_search_one() on everything fed so far. */
+typedef struct tir_stream tir_stream;
+int tir_stream_open(tir_ctx *ctx, tir_stream **out);
+int tir_stream_feed(tir_stream *s, const int16_t *pcm, uint32_t n_samples);
+uint64_t tir_stream_samples(const tir_stream *s);
+int tir_stream_finish(tir_stream *s, int coefs, double tolerance, int freq_ignore_low, int freq_ignore_high,
+                      tir_hit *hit);
+void tir_stream_close(tir_stream *s);
+
 /* Multi-GPU (DB sharded by uuid, one context per GPU): fold the per-shard winners of the same
  * queries into the global winner.  d_gathered is [n_shards][n_queries] tir_hit on this device
  * (e.g. the output of an NCCL all-gather of each rank's d_hits); result in d_out[n_queries]. */
