@@ -11,6 +11,8 @@
 // /tmp/tiresias-<uuid>.wav, src/application_handler.c:153-155,248-312, which
 // create_audio_fingerprints reopens): the channel's frames are appended to a host buffer as
 // ast_read delivers them and tir_stream_finish submits the recording to the batcher.
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -24,17 +26,31 @@
 namespace {
 
 struct Request {
-  const int16_t *pcm;
-  uint64_t n;
-  int coefs, ign_lo, ign_hi;
-  double tol;
-  tir_hit *hit;
+  uint64_t n = 0, off = 0;
+  tir_hit *hit = nullptr;
   int rc = TIR_OK;
   bool done = false;
-  std::string err;
-  bool same_params(const Request &o) const {
+};
+
+struct Params {
+  int coefs = 1, ign_lo = -1, ign_hi = -1;
+  double tol = 0.001;
+  bool operator==(const Params &o) const {
     return coefs == o.coefs && ign_lo == o.ign_lo && ign_hi == o.ign_hi && std::memcmp(&tol, &o.tol, sizeof tol) == 0;
   }
+};
+
+// One batch being assembled / in flight.  Callers copy their own recording into the pinned staging
+// buffer (in parallel, outside the lock); the dispatcher only launches.
+struct Slot {
+  int16_t *h_pcm = nullptr; // pinned
+  uint64_t cap = 0, used = 0;
+  std::vector<Request *> members;
+  Params params;
+  uint32_t copying = 0; // members that have not finished their memcpy yet
+  bool open = false;    // accepts members
+  bool sealed = false;  // somebody could not join: dispatch without waiting for max_wait
+  std::chrono::steady_clock::time_point t_first;
 };
 
 } // namespace
@@ -43,73 +59,57 @@ struct TirBatcher {
   tir_ctx *ctx = nullptr;
   uint32_t max_batch = 1024, max_wait_us = 200;
   std::mutex mu;
-  std::condition_variable cv_work, cv_done;
-  std::deque<Request *> queue;
+  std::condition_variable cv_work, cv_space, cv_done;
+  Slot slot[2];
+  int fill = 0;
   bool stop = false;
   std::thread worker;
   uint64_t n_requests = 0, n_batches = 0, max_seen = 0;
-  // staging (pinned, grows only)
-  int16_t *h_pcm = nullptr;
-  size_t h_cap = 0;
+  std::atomic<int> callers{0}; // threads inside tir_search_one / tir_batcher_stats
   std::vector<uint64_t> off;
   std::vector<tir_hit> hits;
+  std::string last_err;
 
   void run();
 };
 
 void TirBatcher::run() {
   std::unique_lock<std::mutex> lk(mu);
-  std::vector<Request *> batch;
   for (;;) {
-    cv_work.wait(lk, [&] { return stop || !queue.empty(); });
-    if (queue.empty()) {
+    Slot &s = slot[fill];
+    cv_work.wait(lk, [&] { return stop || !s.members.empty(); });
+    if (s.members.empty()) {
       if (stop) return;
       continue;
     }
-    // company for the first request: until max_batch are waiting or max_wait_us have passed
-    if (!stop && queue.size() < max_batch && max_wait_us)
-      cv_work.wait_for(lk, std::chrono::microseconds(max_wait_us), [&] { return stop || queue.size() >= max_batch; });
-    batch.clear();
-    Request *head = queue.front();
-    for (auto it = queue.begin(); it != queue.end() && batch.size() < max_batch;) {
-      if ((*it)->same_params(*head)) {
-        batch.push_back(*it);
-        it = queue.erase(it);
-      } else {
-        ++it;
-      }
-    }
+    // company for the first request: until the batch is full / sealed or max_wait_us have passed
+    const auto deadline = s.t_first + std::chrono::microseconds(max_wait_us);
+    cv_work.wait_until(lk, deadline, [&] { return stop || s.sealed || s.members.size() >= max_batch; });
+    s.open = false;
+    const int cur = fill;
+    fill ^= 1; // the other slot is idle: this thread is the only one that puts slots in flight
+    slot[fill].open = true, slot[fill].sealed = false, slot[fill].used = 0;
+    cv_space.notify_all();
+    cv_work.wait(lk, [&] { return s.copying == 0; });
     lk.unlock();
     // ---- one batched search (takes the context lock inside tir_search)
-    uint64_t total = 0;
-    off.assign(batch.size() + 1, 0);
-    for (size_t i = 0; i < batch.size(); i++) total += batch[i]->n, off[i + 1] = total;
-    int rc = TIR_OK;
-    std::string err;
-    if (total > h_cap) {
-      if (h_pcm) cudaFreeHost(h_pcm);
-      h_pcm = nullptr;
-      h_cap = total + total / 4 + 4096;
-      if (cudaMallocHost((void **)&h_pcm, h_cap * sizeof(int16_t)) != cudaSuccess) {
-        h_pcm = nullptr, h_cap = 0;
-        rc = TIR_ERR_NOMEM, err = "cudaMallocHost failed for the batch staging buffer";
-      }
-    }
-    if (rc == TIR_OK) {
-      for (size_t i = 0; i < batch.size(); i++)
-        if (batch[i]->n) std::memcpy(h_pcm + off[i], batch[i]->pcm, batch[i]->n * sizeof(int16_t));
-      hits.resize(batch.size());
-      rc = tir_search(ctx, h_pcm, off.data(), (uint32_t)batch.size(), head->coefs, head->tol, head->ign_lo, head->ign_hi,
-                      hits.data());
-      if (rc != TIR_OK) err = tir_last_error(ctx);
-    }
+    const size_t nb = s.members.size();
+    off.assign(nb + 1, 0);
+    for (size_t i = 0; i < nb; i++) off[i] = s.members[i]->off;
+    off[nb] = s.used; // members were appended in offset order
+    hits.resize(nb);
+    const int rc = tir_search(ctx, s.h_pcm, off.data(), (uint32_t)nb, s.params.coefs, s.params.tol, s.params.ign_lo,
+                              s.params.ign_hi, hits.data());
     lk.lock();
-    n_batches++, n_requests += batch.size();
-    if (batch.size() > max_seen) max_seen = batch.size();
-    for (size_t i = 0; i < batch.size(); i++) {
-      if (rc == TIR_OK) *batch[i]->hit = hits[i];
-      batch[i]->rc = rc, batch[i]->err = err, batch[i]->done = true;
+    if (rc != TIR_OK) last_err = tir_last_error(ctx);
+    n_batches++, n_requests += nb;
+    if (nb > max_seen) max_seen = nb;
+    for (size_t i = 0; i < nb; i++) {
+      if (rc == TIR_OK) *s.members[i]->hit = hits[i];
+      s.members[i]->rc = rc, s.members[i]->done = true;
     }
+    s.members.clear(), s.used = 0, s.sealed = false;
+    (void)cur;
     cv_done.notify_all();
   }
 }
@@ -121,8 +121,11 @@ void tir_batcher_destroy(TirBatcher *b) {
     b->stop = true;
   }
   b->cv_work.notify_all();
+  b->cv_space.notify_all();
   if (b->worker.joinable()) b->worker.join();
-  if (b->h_pcm) cudaFreeHost(b->h_pcm);
+  while (b->callers.load() != 0) std::this_thread::yield(); // callers on their way out
+  for (Slot &s : b->slot)
+    if (s.h_pcm) cudaFreeHost(s.h_pcm);
   delete b;
 }
 
@@ -135,11 +138,25 @@ extern "C" {
 
 int tir_batcher_start(tir_ctx *ctx, uint32_t max_batch, uint32_t max_wait_us) {
   if (!ctx || max_batch == 0) return tir_fail(ctx, TIR_ERR_ARG, "bad batcher arguments");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::mutex> lk(ctx->batcher_mu);
   if (ctx->batcher) return tir_fail(ctx, TIR_ERR_STATE, "batcher already running");
   TirBatcher *b = new (std::nothrow) TirBatcher();
   if (!b) return tir_fail(ctx, TIR_ERR_NOMEM, "out of memory");
   b->ctx = ctx, b->max_batch = max_batch, b->max_wait_us = max_wait_us;
+  // staging: room for max_batch recordings of 8 s at 8 kHz (4 s at 16 kHz) each, at least 4 M samples; a recording
+  // that does not fit an empty buffer is searched directly by its caller
+  cudaSetDevice(ctx->cfg.device);
+  const uint64_t cap = std::max<uint64_t>((uint64_t)max_batch * 65536ull, 4ull << 20);
+  for (Slot &s : b->slot) {
+    if (cudaMallocHost((void **)&s.h_pcm, cap * sizeof(int16_t)) != cudaSuccess) {
+      tir_batcher_destroy(b);
+      return tir_fail(ctx, TIR_ERR_NOMEM, "cudaMallocHost(%llu) for the batch staging buffers failed",
+                      (unsigned long long)(cap * sizeof(int16_t)));
+    }
+    s.cap = cap;
+    s.members.reserve(max_batch);
+  }
+  b->slot[0].open = true;
   b->worker = std::thread([b] {
     cudaSetDevice(b->ctx->cfg.device);
     b->run();
@@ -152,10 +169,10 @@ int tir_batcher_stop(tir_ctx *ctx) {
   if (!ctx) return TIR_ERR_ARG;
   TirBatcher *b;
   {
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    b = ctx->batcher, ctx->batcher = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->batcher_mu);
+    b = ctx->batcher, ctx->batcher = nullptr; // no new caller can reach it
   }
-  tir_batcher_destroy(b); // pending requests are served first (the worker drains the queue)
+  tir_batcher_destroy(b); // requests already admitted to a batch are served first
   return TIR_OK;
 }
 
@@ -164,29 +181,59 @@ int tir_search_one(tir_ctx *ctx, const int16_t *pcm, uint64_t n_samples, int coe
   if (!ctx || !hit || (!pcm && n_samples)) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
   // argument checks come first in the reference too (src/fp_handler.c:247)
   if (coefs < 1 || coefs > TIR_N_COEFS) return tir_fail(ctx, TIR_ERR_ARG, "Wrong coefs count. max[%d], coefs[%d]", TIR_N_COEFS, coefs);
-  TirBatcher *b = ctx->batcher;
-  if (!b) { // no dispatcher: a batch of one
-    const uint64_t off[2] = {0, n_samples};
-    return tir_search(ctx, pcm, off, 1, coefs, tolerance, freq_ignore_low, freq_ignore_high, hit);
+  TirBatcher *b;
+  {
+    std::lock_guard<std::mutex> g(ctx->batcher_mu);
+    b = ctx->batcher;
+    if (b) b->callers++;
   }
+  struct Leave {
+    TirBatcher *b;
+    ~Leave() { if (b) b->callers--; }
+  } leave{b};
+  const uint64_t direct_off[2] = {0, n_samples};
+  if (!b || n_samples > b->slot[0].cap) // no dispatcher (or an oversized recording): a batch of one
+    return tir_search(ctx, pcm, direct_off, 1, coefs, tolerance, freq_ignore_low, freq_ignore_high, hit);
+  Params p;
+  p.coefs = coefs, p.tol = tolerance, p.ign_lo = freq_ignore_low, p.ign_hi = freq_ignore_high;
   Request r;
-  r.pcm = pcm, r.n = n_samples, r.coefs = coefs, r.tol = tolerance, r.ign_lo = freq_ignore_low, r.ign_hi = freq_ignore_high;
-  r.hit = hit;
+  r.n = n_samples, r.hit = hit;
   std::unique_lock<std::mutex> lk(b->mu);
-  if (b->stop) return tir_fail(ctx, TIR_ERR_STATE, "batcher is stopping");
-  b->queue.push_back(&r);
-  b->cv_work.notify_one();
+  Slot *s = nullptr;
+  for (;;) {
+    if (b->stop) return tir_fail(ctx, TIR_ERR_STATE, "batcher is stopping");
+    s = &b->slot[b->fill];
+    if (s->open && (s->members.empty() || s->params == p) && s->members.size() < b->max_batch && s->used + n_samples <= s->cap) break;
+    if (s->open && !s->members.empty()) { // cannot join this batch: send it off now, take the next one
+      s->sealed = true;
+      b->cv_work.notify_all();
+    }
+    b->cv_space.wait(lk);
+  }
+  if (s->members.empty()) s->params = p, s->t_first = std::chrono::steady_clock::now();
+  r.off = s->used, s->used += n_samples;
+  s->members.push_back(&r);
+  s->copying++;
+  if (s->members.size() == 1 || s->members.size() >= b->max_batch) b->cv_work.notify_all();
+  int16_t *dst = s->h_pcm + r.off;
+  lk.unlock();
+  if (n_samples) std::memcpy(dst, pcm, n_samples * sizeof(int16_t)); // in parallel with the other callers
+  lk.lock();
+  if (--s->copying == 0) b->cv_work.notify_all();
   b->cv_done.wait(lk, [&] { return r.done; });
-  return r.rc;
+  if (r.rc != TIR_OK) return tir_fail(ctx, r.rc, "%s", b->last_err.c_str());
+  return TIR_OK;
 }
 
 int tir_batcher_stats(tir_ctx *ctx, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen) {
   if (!ctx) return TIR_ERR_ARG;
-  TirBatcher *b = ctx->batcher;
   uint64_t r = 0, n = 0, m = 0;
-  if (b) {
-    std::lock_guard<std::mutex> lk(b->mu);
-    r = b->n_requests, n = b->n_batches, m = b->max_seen;
+  {
+    std::lock_guard<std::mutex> g(ctx->batcher_mu);
+    if (TirBatcher *b = ctx->batcher) {
+      std::lock_guard<std::mutex> lk(b->mu);
+      r = b->n_requests, n = b->n_batches, m = b->max_seen;
+    }
   }
   if (n_requests) *n_requests = r;
   if (n_batches) *n_batches = n;

@@ -39,6 +39,7 @@ struct tir_ctx {
   DevBuf h_meta;
   TirDb *db = nullptr;
   TirBatcher *batcher = nullptr;
+  std::mutex batcher_mu; // guards `batcher` itself (never held across GPU work)
 };
 
 int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...);
