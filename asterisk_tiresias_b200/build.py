@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtiresias_gpu.so")
 TOOL = os.path.join(HERE, "..", "tools", "tir_concurrent_bench.bin")
-SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_tables.cpp", "tir_batcher.cpp"]
+SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_tables.cpp", "tir_batcher.cpp", "tir_sqlite.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 unless told not to; every fused
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lpthread"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lpthread", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

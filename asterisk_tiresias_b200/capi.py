@@ -75,6 +75,9 @@ def lib():
             L.tir_merge_hits_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
             L.tir_shard_of.restype = C.c_uint32
             L.tir_shard_of.argtypes = [vp, C.c_uint32]
+            L.tir_db_load_sqlite.argtypes = [vp, vp, u64p, u64p, u64p]
+            L.tir_db_load_sqlite_file.argtypes = [vp, C.c_char_p, u64p, u64p, u64p]
+            L.tir_sqlite_insert_fingerprints.argtypes = [vp, vp, C.c_char_p, C.c_char_p, vp, C.c_uint32]
             L.tir_batcher_start.argtypes = [vp, C.c_uint32, C.c_uint32]
             L.tir_batcher_stop.argtypes = [vp]
             L.tir_search_one.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int, vp]
@@ -239,6 +242,16 @@ class Context:
                                    int(freq_ignore_high), _p(hits)))
         return hits
 
+    # ---- SQLite mirror ------------------------------------------------------------------------
+    def db_load_sqlite(self, sqlite3_handle=None, path=None):
+        """-> (n_audio, n_rows, n_skipped)"""
+        a, r, k = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        if path is not None:
+            self._chk(lib().tir_db_load_sqlite_file(self._h, path.encode(), C.byref(a), C.byref(r), C.byref(k)))
+        else:
+            self._chk(lib().tir_db_load_sqlite(self._h, C.c_void_p(sqlite3_handle), C.byref(a), C.byref(r), C.byref(k)))
+        return int(a.value), int(r.value), int(k.value)
+
     # ---- concurrent front-end ---------------------------------------------------------------
     def batcher_start(self, max_batch=1024, max_wait_us=200):
         self._chk(lib().tir_batcher_start(self._h, max_batch, max_wait_us))
@@ -270,6 +283,15 @@ class Context:
 def shard_of(uuid16, n_shards: int) -> int:
     u = np.ascontiguousarray(uuid16, dtype=np.uint8)
     return int(lib().tir_shard_of(_p(u), n_shards))
+
+
+def sqlite_insert_fingerprints(sqlite3_handle, context, uuid_text, vq):
+    """tir_sqlite_insert_fingerprints without a context (CPU-only callers: it touches no GPU)."""
+    vq = np.ascontiguousarray(vq, dtype=np.int32).reshape(-1, 2)
+    rc = lib().tir_sqlite_insert_fingerprints(None, C.c_void_p(sqlite3_handle), context.encode(), uuid_text.encode(), _p(vq),
+                                              vq.shape[0])
+    if rc != OK:
+        raise TirError(rc, "tir_sqlite_insert_fingerprints failed")
 
 
 class Stream:

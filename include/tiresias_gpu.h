@@ -108,6 +108,22 @@ int tir_db_add(tir_ctx *ctx, const uint8_t uuid[16], const int32_t *v1, const in
 int tir_db_remove(tir_ctx *ctx, const uint8_t uuid[16]);
 int tir_db_stats(tir_ctx *ctx, uint64_t *n_audio, uint64_t *n_rows);
 
+/* ---- SQLite <-> device table -----------------------------------------------------------------
+ * SQLite stays the system of record (schema src/fp_handler.c:686-753).  `sqlite3_db` is the
+ * module's own connection (g_db_ctx->db, src/fp_handler.c:45); libsqlite3 is resolved at run time.
+ *
+ * tir_db_load_sqlite: mirror table audio_fingerprint into the device table, e.g. right after
+ * fp_init() restored the backup (src/fp_handler.c:82-88).  Rows whose audio_uuid is not a canonical
+ * uuid text are counted in n_skipped.  *_file opens a database file read-only instead. */
+int tir_db_load_sqlite(tir_ctx *ctx, void *sqlite3_db, uint64_t *n_audio, uint64_t *n_rows, uint64_t *n_skipped);
+int tir_db_load_sqlite_file(tir_ctx *ctx, const char *path, uint64_t *n_audio, uint64_t *n_rows, uint64_t *n_skipped);
+/* create_audio_fingerprint_info() (src/fp_handler.c:538-575): the frames of one audio into table
+ * audio_fingerprint in one transaction through one prepared statement; stores exactly what the
+ * reference's textual INSERTs store ("%f" values, NULL for TIR_NULL_V).  vq is [n_frames][2]
+ * micro-units as written by tir_extract. */
+int tir_sqlite_insert_fingerprints(tir_ctx *ctx, void *sqlite3_db, const char *context, const char *audio_uuid,
+                                   const int32_t *vq, uint32_t n_frames);
+
 /* ---- seam (B): match ------------------------------------------------------------------------- */
 
 typedef struct {

@@ -62,6 +62,11 @@ def lib():
         L.tiro_db_add_audio.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
         L.tiro_db_add_fingerprints.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
         L.tiro_db_delete_audio.argtypes = [C.c_void_p, C.c_char_p]
+        L.tiro_db_handle.restype = C.c_void_p
+        L.tiro_db_handle.argtypes = [C.c_void_p]
+        L.tiro_db_dump_audio.restype = C.c_long
+        L.tiro_db_dump_audio.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_char_p, C.c_size_t]
         L.tiro_db_count_rows.restype = C.c_long
         L.tiro_db_count_rows.argtypes = [C.c_void_p]
         L.tiro_db_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double,
@@ -193,6 +198,20 @@ class SqliteDB:
     def delete_audio(self, uuid):
         if lib().tiro_db_delete_audio(self._h, uuid.encode()):
             raise RuntimeError("sqlite oracle delete failed")
+
+    @property
+    def handle(self):
+        """the raw sqlite3* (int), as the module would pass g_db_ctx->db"""
+        return lib().tiro_db_handle(self._h)
+
+    def dump_audio(self, uuid, cap=100000):
+        """-> (frame_idx, max1, max2, type1, type2, context) of the rows of one audio, rowid order"""
+        fi = np.zeros(cap, np.int64); m1 = np.zeros(cap, np.float64); m2 = np.zeros(cap, np.float64)
+        t1 = np.zeros(cap, np.int32); t2 = np.zeros(cap, np.int32)
+        ctxbuf = C.create_string_buffer(512)
+        n = lib().tiro_db_dump_audio(self._h, uuid.encode(), cap, _p(fi), _p(m1), _p(m2), _p(t1), _p(t2), ctxbuf, 512)
+        assert 0 <= n <= cap
+        return fi[:n], m1[:n], m2[:n], t1[:n], t2[:n], ctxbuf.value.decode()
 
     def count_rows(self):
         return int(lib().tiro_db_count_rows(self._h))

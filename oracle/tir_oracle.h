@@ -86,6 +86,9 @@ int tiro_db_add_fingerprints(tiro_db *db, const char *context, const char *uuid,
                              size_t n_frames, int literal_autocommit);
 int tiro_db_delete_audio(tiro_db *db, const char *uuid); /* fp_handler.c:135,147 */
 long tiro_db_count_rows(tiro_db *db);
+void *tiro_db_handle(tiro_db *db); /* the sqlite3* itself (what the module holds in g_db_ctx->db) */
+long tiro_db_dump_audio(tiro_db *db, const char *uuid, long cap, long *frame_idx, double *max1, double *max2,
+                        int *type1, int *type2, char *context, size_t context_cap);
 
 typedef struct {
   int found;        /* 0 => reference returns NULL (TIRSTATUS=NOTFOUND) */

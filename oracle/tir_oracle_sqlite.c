@@ -33,6 +33,8 @@ int sqlite3_step(sqlite3_stmt *);
 int sqlite3_finalize(sqlite3_stmt *);
 const unsigned char *sqlite3_column_text(sqlite3_stmt *, int);
 int sqlite3_column_int(sqlite3_stmt *, int);
+double sqlite3_column_double(sqlite3_stmt *, int);
+int sqlite3_column_type(sqlite3_stmt *, int);
 int sqlite3_column_count(sqlite3_stmt *);
 const char *sqlite3_column_name(sqlite3_stmt *, int);
 int sqlite3_changes(sqlite3 *);
@@ -169,6 +171,40 @@ int tiro_db_delete_audio(tiro_db *d, const char *uuid) {
   rc |= exec_sql(d, sql);
   free(sql);
   return rc;
+}
+
+/* the raw connection, so that tests can hand it to code under test the way the module would hand
+ * over g_db_ctx->db (src/fp_handler.c:45) */
+void *tiro_db_handle(tiro_db *d) { return d ? (void *)d->db : NULL; }
+
+/* rows of one audio in rowid order: frame_idx, max1, max2 and the storage class of each value
+ * (sqlite3_column_type: 1 integer, 2 float, 3 text, 4 blob, 5 null) */
+long tiro_db_dump_audio(tiro_db *d, const char *uuid, long cap, long *frame_idx, double *max1, double *max2,
+                        int *type1, int *type2, char *context, size_t context_cap) {
+  char *sql = NULL;
+  if (asprintf(&sql, "select frame_idx, max1, max2, context from audio_fingerprint where audio_uuid='%s' order by rowid", uuid) < 0)
+    return -1;
+  sqlite3_stmt *st = NULL;
+  long n = 0;
+  if (sqlite3_prepare_v2(d->db, sql, -1, &st, NULL) != SQLITE_OK) {
+    free(sql);
+    return -1;
+  }
+  free(sql);
+  while (sqlite3_step(st) == SQLITE_ROW) {
+    if (n < cap) {
+      frame_idx[n] = sqlite3_column_int(st, 0);
+      type1[n] = sqlite3_column_type(st, 1), type2[n] = sqlite3_column_type(st, 2);
+      max1[n] = sqlite3_column_double(st, 1), max2[n] = sqlite3_column_double(st, 2);
+      if (n == 0 && context) {
+        const unsigned char *t = sqlite3_column_text(st, 3);
+        snprintf(context, context_cap, "%s", t ? (const char *)t : "");
+      }
+    }
+    n++;
+  }
+  sqlite3_finalize(st);
+  return n;
 }
 
 long tiro_db_count_rows(tiro_db *d) {
