@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtiresias_gpu.so")
 TOOL = os.path.join(HERE, "..", "tools", "tir_concurrent_bench.bin")
+HOST_LIB = os.path.join(HERE, "libtiresias_host.so")
 SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_tables.cpp", "tir_batcher.cpp", "tir_sqlite.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -30,7 +31,9 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "tiresias_gpu.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith((".o", ".log"))] + [
+        os.path.join(HERE, "..", "include", "tiresias_gpu.h"), os.path.join(HERE, "..", "include", "fp_handler_gpu.h"),
+        os.path.join(HERE, "host", "fp_handler_gpu.cpp"), os.path.join(HERE, "..", "tools", "tir_concurrent_bench.cpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -53,6 +56,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    # host-side mirror of src/fp_handler.h on top of the C ABI (asterisk_tiresias_b200/host)
+    host_src = os.path.join(HERE, "host", "fp_handler_gpu.cpp")
+    if os.path.exists(host_src):
+        r = subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", host_src, "-o", HOST_LIB, "-L" + HERE,
+                            "-ltiresias_gpu", "-lcrypto", "-ldl", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building libtiresias_host.so failed")
+        log.append(r.stderr)
     # C++ driver of the concurrent-channel bench (plain C ABI client; tools/tir_concurrent_bench.cpp)
     tool_src = os.path.join(HERE, "..", "tools", "tir_concurrent_bench.cpp")
     if os.path.exists(tool_src):

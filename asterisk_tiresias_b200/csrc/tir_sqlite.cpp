@@ -13,61 +13,15 @@
 //     a non-finite value never became a JSON real, its key is missing from the INSERT: NULL.
 // libsqlite3 is resolved at run time (the Asterisk process already has it loaded; its header is
 // not needed): dlopen with RTLD_NOLOAD first, then libsqlite3.so.0.
-#include <dlfcn.h>
-
 #include <cstring>
-#include <unordered_map>
 
 #include "tir_internal.h"
+#include "tir_sqlite_dl.h"
 
 namespace {
 
-struct Sqlite {
-  void *lib = nullptr;
-  int (*open_v2)(const char *, void **, int, const char *) = nullptr;
-  int (*close)(void *) = nullptr;
-  int (*exec)(void *, const char *, int (*)(void *, int, char **, char **), void *, char **) = nullptr;
-  int (*prepare_v2)(void *, const char *, int, void **, const char **) = nullptr;
-  int (*step)(void *) = nullptr;
-  int (*reset)(void *) = nullptr;
-  int (*finalize)(void *) = nullptr;
-  int (*bind_int64)(void *, int, long long) = nullptr;
-  int (*bind_double)(void *, int, double) = nullptr;
-  int (*bind_null)(void *, int) = nullptr;
-  int (*bind_text)(void *, int, const char *, int, void (*)(void *)) = nullptr;
-  const unsigned char *(*column_text)(void *, int) = nullptr;
-  double (*column_double)(void *, int) = nullptr;
-  int (*column_type)(void *, int) = nullptr;
-  const char *(*errmsg)(void *) = nullptr;
-  bool ok = false;
-};
-
-constexpr int kSqliteOk = 0, kSqliteRow = 100, kSqliteDone = 101, kSqliteNull = 5, kOpenReadOnly = 1;
-
-Sqlite &sq() {
-  static Sqlite s = [] {
-    Sqlite t;
-    for (const char *name : {"libsqlite3.so.0", "libsqlite3.so"}) {
-      t.lib = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
-      if (!t.lib) t.lib = dlopen(name, RTLD_NOW);
-      if (t.lib) break;
-    }
-    if (!t.lib) return t;
-    bool all = true;
-    auto sym = [&](auto &fn, const char *n) {
-      fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(t.lib, n));
-      all = all && fn != nullptr;
-    };
-    sym(t.open_v2, "sqlite3_open_v2"), sym(t.close, "sqlite3_close"), sym(t.exec, "sqlite3_exec");
-    sym(t.prepare_v2, "sqlite3_prepare_v2"), sym(t.step, "sqlite3_step"), sym(t.reset, "sqlite3_reset");
-    sym(t.finalize, "sqlite3_finalize"), sym(t.bind_int64, "sqlite3_bind_int64"), sym(t.bind_double, "sqlite3_bind_double");
-    sym(t.bind_null, "sqlite3_bind_null"), sym(t.bind_text, "sqlite3_bind_text"), sym(t.column_text, "sqlite3_column_text");
-    sym(t.column_double, "sqlite3_column_double"), sym(t.column_type, "sqlite3_column_type"), sym(t.errmsg, "sqlite3_errmsg");
-    t.ok = all;
-    return t;
-  }();
-  return s;
-}
+using Sqlite = TirSqlite;
+Sqlite &sq() { return tir_sqlite(); }
 
 int hexval(char c) {
   if (c >= '0' && c <= '9') return c - '0';
