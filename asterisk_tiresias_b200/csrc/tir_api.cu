@@ -131,6 +131,8 @@ void tir_close(tir_ctx *ctx) {
   for (int w = 0; w < 2; w++)
     for (int e = 0; e < 2; e++)
       if (ctx->ev[w][e]) cudaEventDestroy(ctx->ev[w][e]);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -176,25 +178,84 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
   TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
   const uint64_t base = clip_off[0], total = clip_off[n_clips] - base;
   uint64_t F = 0;
-  for (uint32_t c = 0; c < n_clips; c++) F += tir_n_frames(clip_off[c + 1] - clip_off[c], ctx->cfg.hop);
+  for (uint32_t c = 0; c < n_clips; c++) {
+    if (clip_off[c + 1] < clip_off[c]) return tir_fail(ctx, TIR_ERR_ARG, "clip_off must be non-decreasing");
+    F += tir_n_frames(clip_off[c + 1] - clip_off[c], ctx->cfg.hop);
+  }
   if (n_frames) *n_frames = F;
   if (F == 0) return TIR_OK;
   int rc;
   if ((rc = tir_reserve(ctx, ctx->d_pcm, total * sizeof(int16_t) + 16))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_coef, F * TIR_N_COEFS * sizeof(float)))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_vq, F * TIR_N_COEFS * sizeof(int32_t)))) return rc;
-  TIR_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcm.p, pcm + base, total * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-  // offsets relative to the staged copy
-  std::vector<uint64_t> rel((size_t)n_clips + 1);
-  for (uint32_t c = 0; c <= n_clips; c++) rel[c] = clip_off[c] - base;
-  if ((rc = tir_extract_launch(ctx, (const int16_t *)ctx->d_pcm.p, total, rel.data(), n_clips, (float *)ctx->d_coef.p,
-                               (int32_t *)ctx->d_vq.p, nullptr)))
-    return rc;
-  if (coef)
-    TIR_CUDA(ctx, cudaMemcpyAsync(coef, ctx->d_coef.p, F * TIR_N_COEFS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  if (vq)
-    TIR_CUDA(ctx, cudaMemcpyAsync(vq, ctx->d_vq.p, F * TIR_N_COEFS * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // The batch is cut into chunks of whole clips (~96 MB of PCM) that flow through three queues:
+  // copy-in stream -> ctx's stream (kernel) -> copy-out stream, so the PCIe transfers of one chunk
+  // overlap the kernel of another.
+  if (!ctx->s_in) {
+    TIR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    TIR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  struct Chunk { uint32_t c0, c1; uint64_t f0, f1; cudaEvent_t in, done; };
+  std::vector<Chunk> chunks;
+  const uint64_t target = 48ull << 20; // samples
+  for (uint32_t c = 0; c < n_clips;) {
+    Chunk k{c, c, 0, 0, nullptr, nullptr};
+    while (k.c1 < n_clips && (k.c1 == k.c0 || clip_off[k.c1 + 1] - clip_off[k.c0] <= target)) k.c1++;
+    chunks.push_back(k);
+    c = k.c1;
+  }
+  uint64_t f = 0;
+  for (Chunk &k : chunks) {
+    k.f0 = f;
+    for (uint32_t c = k.c0; c < k.c1; c++) f += tir_n_frames(clip_off[c + 1] - clip_off[c], ctx->cfg.hop);
+    k.f1 = f;
+    TIR_CUDA(ctx, cudaEventCreateWithFlags(&k.in, cudaEventDisableTiming));
+    TIR_CUDA(ctx, cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+  }
+  auto cleanup = [&] {
+    for (Chunk &k : chunks) {
+      if (k.in) cudaEventDestroy(k.in);
+      if (k.done) cudaEventDestroy(k.done);
+    }
+  };
+  int16_t *d_pcm = (int16_t *)ctx->d_pcm.p;
+  float *d_coef = (float *)ctx->d_coef.p;
+  int32_t *d_vq = (int32_t *)ctx->d_vq.p;
+  cudaError_t e = cudaSuccess;
+  // every host->device copy is queued up front: the copy engine never waits for the host
+  for (Chunk &k : chunks) {
+    const uint64_t s0 = clip_off[k.c0] - base, s1 = clip_off[k.c1] - base;
+    if (s1 > s0 && e == cudaSuccess)
+      e = cudaMemcpyAsync(d_pcm + s0, pcm + base + s0, (s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(k.in, ctx->s_in);
+  }
+  std::vector<uint64_t> rel;
+  for (Chunk &k : chunks) {
+    if (e != cudaSuccess) break;
+    e = cudaStreamWaitEvent(ctx->stream, k.in, 0);
+    if (e != cudaSuccess) break;
+    // offsets stay relative to the whole staged batch: a clip keeps the alignment it has in the caller's buffer
+    rel.assign((size_t)(k.c1 - k.c0) + 1, 0);
+    for (uint32_t c = k.c0; c <= k.c1; c++) rel[c - k.c0] = clip_off[c] - base;
+    if ((rc = tir_extract_launch(ctx, d_pcm, total, rel.data(), k.c1 - k.c0, d_coef + k.f0 * TIR_N_COEFS,
+                                 d_vq + k.f0 * TIR_N_COEFS, nullptr))) {
+      cudaDeviceSynchronize();
+      cleanup();
+      return rc;
+    }
+    e = cudaEventRecord(k.done, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_out, k.done, 0);
+    const size_t n = (size_t)(k.f1 - k.f0) * TIR_N_COEFS;
+    if (coef && n && e == cudaSuccess)
+      e = cudaMemcpyAsync(coef + k.f0 * TIR_N_COEFS, d_coef + k.f0 * TIR_N_COEFS, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out);
+    if (vq && n && e == cudaSuccess)
+      e = cudaMemcpyAsync(vq + k.f0 * TIR_N_COEFS, d_vq + k.f0 * TIR_N_COEFS, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_out);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) cudaDeviceSynchronize();
+  cleanup();
+  if (e != cudaSuccess) return tir_fail(ctx, TIR_ERR_CUDA, "tir_extract: %s", cudaGetErrorString(e));
   return TIR_OK;
 }
 

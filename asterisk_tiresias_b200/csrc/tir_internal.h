@@ -24,6 +24,7 @@ struct tir_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t s_in = nullptr, s_out = nullptr; // copy-in / copy-out queues of tir_extract's pipeline
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;

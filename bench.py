@@ -555,7 +555,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_match and os.path.exists(tool):
         try:
             torch.cuda.empty_cache()
-            r = subprocess.run([tool, "--threads", str(args.channels), "--rounds", "5", "--db-fps", str(args.channels_db_fps),
+            r = subprocess.run([tool, "--threads", str(args.channels), "--rounds", "20", "--wait-us", "1000", "--db-fps", str(args.channels_db_fps),
                                 "--device", str(local_rank)], capture_output=True, text=True, timeout=600)
             concurrent = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
         except Exception as ex:  # noqa: BLE001
