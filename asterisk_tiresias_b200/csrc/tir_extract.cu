@@ -33,6 +33,9 @@ struct TirExtractArgs {
 };
 
 __device__ const double2 k_logf_tab[16] = TIR_LOGF_TAB_INIT;
+#ifdef TIR_TRACE
+__device__ long long g_trace[64];
+#endif
 
 // tile descriptors from the per-clip prefix arrays (one thread per tile, binary search for its clip)
 template <int T, int HOP>
@@ -139,7 +142,7 @@ __device__ __forceinline__ void tir_emit_coefs(const float *lg, const TirMelPara
 }
 
 // Per tile: P1 | sync | P2 load | sync | P2 compute | sync | P3a sweep (coefficient warps: P4 of the
-// previous tile) + wait for the next tile's PCM | sync | P3b logs -- no barrier before the next P1.
+// previous tile first) + wait for the next tile's PCM | sync | P3b logs -- no barrier before the next P1.
 template <int WIN>
 __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     tir_extract_kernel(const __grid_constant__ TirExtractArgs a, const __grid_constant__ TirMelParams mp) {
@@ -163,6 +166,11 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   if (tid < 16) sm.logtab[tid] = k_logf_tab[tid];
   // bins 0 and M of the magnitude buffer are never written; keep the whole buffer finite
   for (int i = tid; i < TirSmem<WIN>::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
+  // filters without weights: log10f(clamp) once, nothing overwrites it
+  for (int i = tid; i < 2 * TIR_MAX_FILTERS * 32; i += C::NT) {
+    const int fidx = (i / 32) % TIR_MAX_FILTERS;
+    if (fidx < mp.n_filters && mp.dead[fidx]) (&sm.lg[0][0])[i] = mp.lg_dead;
+  }
   cp_async_wait_all();
   __syncthreads();
 
@@ -182,17 +190,37 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     TirPass2Regs rg;
     tir_pass2_load<WIN>(sm, warp, lane, rg);
     __syncthreads(); // the magnitudes overwrite the exchange buffer
+#ifndef TIR_ABLATE_P2
     if (warp == 0) tir_pass2_compute<WIN, true>(sm, warp, lane, rg, nz);
     else tir_pass2_compute<WIN, false>(sm, warp, lane, rg, nz);
+#else
+    if (rg.X[lane & 15].r.lo == 1234.5f) sm.xch[tid] = rg.X[3].i.hi; // keep the loads alive
+#endif
     __syncthreads();
-    if (warp < mp.n_coefs) {
-      if (!first) tir_emit_coefs(sm.lg[b ^ 1], mp, a, prev, warp, lane);
-    } else {
-      tir_mel_sweep(sm.xch, sm.lg[b], mp, warp - mp.n_coefs, lane, nz);
-    }
+#ifdef TIR_TRACE
+    long long tr0 = clock64();
+#endif
+#ifndef TIR_ABLATE_P3
+    if (warp < mp.n_coefs && !first) tir_emit_coefs(sm.lg[b ^ 1], mp, a, prev, warp, lane);
+    tir_mel_sweep(sm.xch, sm.lg[b], mp, warp, lane, nz);
+#endif
+#ifdef TIR_TRACE
+    long long tr1 = clock64();
+#endif
     cp_async_wait_all();
     __syncthreads(); // raw mel sums complete; the next tile's PCM has landed
+#ifdef TIR_TRACE
+    long long tr2 = clock64();
+#endif
+#ifndef TIR_ABLATE_P3B
     tir_log_phase<C::NW>(sm.lg[b], sm.logtab, mp, warp, lane);
+#endif
+#ifdef TIR_TRACE
+    if (blockIdx.x == 7 && lane == 0 && tile == blockIdx.x + 5 * gridDim.x) {
+      long long tr3 = clock64();
+      g_trace[warp * 4 + 0] = tr1 - tr0, g_trace[warp * 4 + 1] = tr2 - tr1, g_trace[warp * 4 + 2] = tr3 - tr2, g_trace[warp * 4 + 3] = tr0;
+    }
+#endif
     if (!have_nxt) break;
     tile += gridDim.x;
     prev = cur, cur = nxt, nxt = nn, have_nxt = have_nn, b ^= 1, first = false;
@@ -271,6 +299,15 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
     ctx->ev_valid[0] = true;
   }
   ctx->launches++;
+#ifdef TIR_TRACE
+  {
+    long long h[64];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpyFromSymbol(h, g_trace, sizeof h);
+    for (int w = 0; w < C::NW; w++)
+      fprintf(stderr, "trace warp %2d: P3a %6lld  wait-at-barrier %6lld  P3b %6lld  (start %lld)\n", w, h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3] - h[3]);
+  }
+#endif
   return TIR_OK;
 }
 

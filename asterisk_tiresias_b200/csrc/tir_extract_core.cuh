@@ -43,23 +43,25 @@ struct TirC2 { // two complex numbers: lane lo and lane hi
 // Mel sweep: the Slaney triangles of filters f and f+2 never overlap, so ONE pass over the bins
 // with the even filters accumulated in lane lo and the odd ones in lane hi computes every filter,
 // each bin being loaded once and broadcast to both lanes.  The live filters are cut into
-// contiguous SEGMENTS, one per sweep warp; a segment is a list of RUNS: `run_bins` bins to
+// contiguous SEGMENTS, one per warp; a segment is a list of RUNS: `run_bins` bins to
 // accumulate, then filter `run_emit` is complete (its sum leaves its lane, the lane restarts at 0).
 struct TirMelParams {
   int16_t seg_bin0[TIR_MAX_WARPS];  // first bin of the segment
   int16_t seg_run0[TIR_MAX_WARPS];  // first run
   int16_t seg_nruns[TIR_MAX_WARPS];
   int16_t seg_woff[TIR_MAX_WARPS];  // first weight record
-  int16_t run_bins[TIR_MAX_RUNS];
+  int16_t run_bins[TIR_MAX_RUNS];   // (every segment's list is followed by one unused sentinel entry)
   int8_t run_emit[TIR_MAX_RUNS];    // filter id completed by the run
   uint8_t dead[TIR_MAX_FILTERS];    // filter has no non-zero weight: its log-mel value is lg_dead
+  uint8_t live[TIR_MAX_FILTERS];    // ids of the n_live filters that have weights
+  uint8_t pad_[8];
   // (w_even[bin], w_odd[bin]) * 2^-33 : aubio weights of the even / odd filter active at a bin of the
   // segment (0 when none); 2^-33 undoes the scaled FFT (2x) and the scaled square root (2^32 x), exactly
   float2 w2[TIR_MAX_W2];
   float dct[TIR_MAX_COEFS][TIR_MAX_FILTERS];
   float log_clamp; // (float)2e-42 : aubio VERY_SMALL_NUMBER
   float lg_dead;   // log10f(log_clamp)
-  int n_filters, n_coefs, n_segs, pad_;
+  int n_filters, n_coefs, n_segs, n_live;
 };
 
 static_assert(sizeof(float4) == 16 && alignof(float4) == 16 && alignof(float2) == 8 && alignof(double2) == 16,
@@ -83,7 +85,7 @@ struct TirSmem {
   using C = TirCfg<WIN>;
   static constexpr int PCM_UNITS = (C::T + 1) * C::PCH;
   static constexpr int XCH_WORDS = 2 * C::N1 * 16 * 32; // [plane re/im][k1][n2][frame]
-  static_assert((C::M + 1 + 64) * 32 <= XCH_WORDS, "magnitudes (+ padded mel reads) alias the exchange buffer");
+  static_assert((C::M + 1 + 16) * 32 <= XCH_WORDS, "magnitudes (+ padded mel reads) alias the exchange buffer");
   uint2 pcm[2][PCM_UNITS];   // double buffered: tile N+1 streams in (cp.async) while tile N computes
   float xch[XCH_WORDS];
   float lg[2][TIR_MAX_FILTERS * 32]; // log-mel values of this and of the previous tile (P4 lags by one)
@@ -292,42 +294,49 @@ TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg,
 // ---- P3a: mel sweep -----------------------------------------------------------------------------
 // role = segment `seg` (warp-uniform), lane f = frame.  fmat_vecmul order: every filter's sum runs
 // over its bins in ascending order from 0.f; bins where a lane's weight is 0 add +0 (x is finite: a
-// magnitude).  Writes the raw sums to lg.
+// magnitude).  The parameters of the next run are fetched while the current one accumulates (the
+// constant-bank loads are dependent, ~100 cycles each).  Writes the raw sums to lg.
 TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, int seg, int f, TirP2 nz) {
+  const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
+  if (nr == 0) return;
   const float *m = norm + TIR_NORM_IDX(mp.seg_bin0[seg], f);
   const float2 *wp = mp.w2 + mp.seg_woff[seg];
-  const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
   TirP2 acc = tir_pbc(0.f);
+  int n = mp.run_bins[r0], fe = mp.run_emit[r0];
   for (int r = 0; r < nr; r++) {
-    const int n = mp.run_bins[r0 + r];
+    const int n_next = mp.run_bins[r0 + r + 1], fe_next = mp.run_emit[r0 + r + 1]; // the list ends with a sentinel
 #pragma unroll 4
     for (int b = 0; b < n; b++) {
       const float2 wv = wp[b];
       acc = tir_padd(acc, tir_pmulx(tir_pbc(m[32 * b]), tir_pmk(wv.x, wv.y), nz));
     }
     m += 32 * n, wp += n;
-    const int fe = mp.run_emit[r0 + r];
     if (fe & 1) lg[fe * 32 + f] = acc.hi, acc.hi = 0.f;
     else lg[fe * 32 + f] = acc.lo, acc.lo = 0.f;
+    n = n_next, fe = fe_next;
   }
 }
 
 // ---- P3b: clamp + log10f, in place ----------------------------------------------------------------
-// role w takes filters w, w + NW, ...: the same number of logarithms for every thread.
+// role w takes live filters w, w + NW, ...: the same number of logarithms for every thread, written
+// as straight-line code over all of them so that their (long, double precision) dependency chains
+// interleave.  Filters without weights keep the constant lg_dead written once at kernel start.
 template <int NW>
 TIR_DEV void tir_log_phase(float *lg, const double2 *logtab, const TirMelParams &mp, int w, int f) {
+  constexpr int Q = (TIR_MAX_FILTERS + NW - 1) / NW;
+  float v[Q];
+  int at[Q];
 #pragma unroll
-  for (int q = 0; q < (TIR_MAX_FILTERS + NW - 1) / NW; q++) {
+  for (int q = 0; q < Q; q++) {
     const int i = w + NW * q;
-    if (i < mp.n_filters) {
-      float *p = lg + i * 32 + f;
-      if (mp.dead[i]) {
-        *p = mp.lg_dead;
-      } else {
-        *p = tir_log10f_glibc(fmaxf(*p, mp.log_clamp), logtab); // sums are >= +0, never NaN
-      }
-    }
+    at[q] = i < mp.n_live ? mp.live[i] * 32 + f : -1;
+    v[q] = at[q] >= 0 ? lg[at[q]] : 1.f;
   }
+#pragma unroll
+  for (int q = 0; q < Q; q++) v[q] = tir_log10f_glibc(fmaxf(v[q], mp.log_clamp), logtab); // sums are >= +0, never NaN
+#pragma unroll
+  for (int q = 0; q < Q; q++)
+    if (at[q] >= 0) lg[at[q]] = v[q];
 }
 
 // ---- P4 ---------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
   const int64_t nframes = (nsamp + C::HOP - 1) / C::HOP;
   std::vector<TirPass2Regs> regs(C::NT);
   const TirP2 nz = tir_pbc(-0.0f);
+  for (int i = 0; i < 2 * TIR_MAX_FILTERS * 32; i++) // as the kernel prologue does
+    if ((i / 32) % TIR_MAX_FILTERS < tab.mel.n_filters && tab.mel.dead[(i / 32) % TIR_MAX_FILTERS]) (&sm->lg[0][0])[i] = tab.mel.lg_dead;
   int b = 0;
   for (int64_t f0 = 0; f0 < nframes; f0 += C::T, b ^= 1) {
     const int nvalid = (int)std::min<int64_t>(C::T, nframes - f0);
@@ -54,8 +56,8 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
         if (w == 0) tir_pass2_compute<WIN, true>(*sm, w, lane, regs[w * 32 + lane], nz);
         else tir_pass2_compute<WIN, false>(*sm, w, lane, regs[w * 32 + lane], nz);
       }
-    for (int w = tab.mel.n_coefs; w < C::NW; w++)
-      for (int lane = 0; lane < 32; lane++) tir_mel_sweep(sm->xch, sm->lg[b], tab.mel, w - tab.mel.n_coefs, lane, nz);
+    for (int w = 0; w < C::NW; w++)
+      for (int lane = 0; lane < 32; lane++) tir_mel_sweep(sm->xch, sm->lg[b], tab.mel, w, lane, nz);
     for (int w = 0; w < C::NW; w++)
       for (int lane = 0; lane < 32; lane++) tir_log_phase<C::NW>(sm->lg[b], sm->logtab, tab.mel, w, lane);
     for (int j = 0; j < 2; j++)
