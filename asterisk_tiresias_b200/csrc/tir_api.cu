@@ -126,7 +126,7 @@ void tir_close(tir_ctx *ctx) {
   if (ctx->db) tir_db_destroy(ctx->db);
   cudaFree(ctx->d_win4), cudaFree(ctx->d_twp4), cudaFree(ctx->d_twu4);
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
-  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y);
+  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y), free_dev(ctx->d_counter);
   if (ctx->h_meta.p) cudaFreeHost(ctx->h_meta.p);
   for (int w = 0; w < 2; w++)
     for (int e = 0; e < 2; e++)

@@ -35,7 +35,7 @@ struct tir_ctx {
   // device copies of the kernel-layout tables
   float4 *d_win4 = nullptr, *d_twp4 = nullptr, *d_twu4 = nullptr;
   // reusable device scratch
-  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y;
+  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y, d_counter;
   // pinned staging for small metadata
   DevBuf h_meta;
   TirDb *db = nullptr;
