@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   // the last quarter of its tiles alone on the SM.  Every CTA starts with tiles bid and bid + grid.
   __shared__ uint32_t s_claim;
   TirTile cur = tir_load_tile_desc(a.tiles + blockIdx.x); // grid <= n_tiles
-  tir_issue_tile_load<WIN>(sm.pcm[0], a.pcm, cur, base_aligned, tid);
+  tir_issue_tile_load<WIN>(sm.pcm, a.pcm, cur, base_aligned, tid);
   bool have_nxt = blockIdx.x + gridDim.x < a.n_tiles;
   TirTile nxt = cur, prev = cur;
   if (have_nxt) nxt = tir_load_tile_desc(a.tiles + blockIdx.x + gridDim.x);
@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   for (int i = tid; i < 16 * C::NW; i += C::NT) sm.win4[i] = a.win4[i], sm.twp4[i] = a.twp4[i];
   for (int i = tid; i < C::NW * 8; i += C::NT) sm.twu4[i] = a.twu4[i];
   if (tid < 16) sm.logtab[tid] = k_logf_tab[tid];
+  for (int i = tid; i < TIR_MAX_W2; i += C::NT) sm.w2[i] = mp.w2[i];
+  for (int i = tid; i < TIR_MAX_RUNS; i += C::NT) sm.run_bins[i] = mp.run_bins[i], sm.run_emit[i] = mp.run_emit[i];
   // bins 0 and M of the magnitude buffer are never written; keep the whole buffer finite
   for (int i = tid; i < TirSmem<WIN>::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
   // filters without weights: log10f(clamp) once, nothing overwrites it
@@ -182,18 +184,15 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   int b = 0;
   bool first = true;
   for (;;) {
-    // pcm[b] holds the current tile; pcm[b^1] was consumed by the previous tile's P1
     uint32_t claim = 0;
-    if (have_nxt) {
-      tir_issue_tile_load<WIN>(sm.pcm[b ^ 1], a.pcm, nxt, base_aligned, tid); // streams in under P1..P3a
-      if (tid == 0) claim = atomicAdd(a.tile_counter, 1u) + 2u * gridDim.x;     // the tile after nxt; lands under P1
-    }
-    tir_pass1<WIN>(sm, sm.pcm[b], warp, lane, nz);
+    if (have_nxt && tid == 0) claim = atomicAdd(a.tile_counter, 1u) + 2u * gridDim.x; // the tile after nxt; lands under P1
+    tir_pass1<WIN>(sm, sm.pcm, warp, lane, nz);
     if (tid == 0) s_claim = claim;
-    __syncthreads();
+    __syncthreads(); // P1 is done with the PCM buffer
     TirTile nn = nxt;
     bool have_nn = false;
     if (have_nxt) {
+      tir_issue_tile_load<WIN>(sm.pcm, a.pcm, nxt, base_aligned, tid); // streams in under P2..P3a
       const uint32_t t2 = s_claim;
       have_nn = t2 < a.n_tiles;
       if (have_nn) nn = tir_load_tile_desc(a.tiles + t2); // needed one tile from now
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
 #endif
 #ifndef TIR_ABLATE_P3
     if (warp < mp.n_coefs && !first) tir_emit_coefs(sm.lg[b ^ 1], mp, a, prev, warp, lane);
-    tir_mel_sweep(sm.xch, sm.lg[b], mp, warp, lane, nz);
+    tir_mel_sweep(sm.xch, sm.lg[b], mp, sm.w2, sm.run_bins, sm.run_emit, warp, lane, nz);
 #endif
 #ifdef TIR_TRACE
     long long tr1 = clock64();

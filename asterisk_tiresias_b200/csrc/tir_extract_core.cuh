@@ -31,7 +31,7 @@
 #define TIR_MAX_FILTERS 40
 #define TIR_MAX_COEFS 2
 #define TIR_MAX_RUNS 64
-#define TIR_MAX_W2 1536
+#define TIR_MAX_W2 1024
 #define TIR_MAX_WARPS 16
 #define TIR_TILE 32 // frames per tile == lanes per warp
 
@@ -86,13 +86,16 @@ struct TirSmem {
   static constexpr int PCM_UNITS = (C::T + 1) * C::PCH;
   static constexpr int XCH_WORDS = 2 * C::N1 * 16 * 32; // [plane re/im][k1][n2][frame]
   static_assert((C::M + 1 + 16) * 32 <= XCH_WORDS, "magnitudes (+ padded mel reads) alias the exchange buffer");
-  uint2 pcm[2][PCM_UNITS];   // double buffered: tile N+1 streams in (cp.async) while tile N computes
+  uint2 pcm[PCM_UNITS];      // P1 is its only reader: the next tile streams in (cp.async) under P2..P3a
   float xch[XCH_WORDS];
   float lg[2][TIR_MAX_FILTERS * 32]; // log-mel values of this and of the previous tile (P4 lags by one)
   float4 win4[16 * C::NW];   // window pairs of the two lanes, pre-scaled by 2^-15
   float4 twp4[16 * C::NW];   // pass-1 twiddles of the two lanes
   float4 twu4[C::NW * 8];    // untangle twiddles [role][slot pair]
   double2 logtab[16];
+  float2 w2[TIR_MAX_W2];     // mel sweep weights and run lists (copies of TirMelParams::w2 / run_*: a
+  int16_t run_bins[TIR_MAX_RUNS]; // broadcast LDS is much cheaper than an indexed constant-bank load
+  int16_t run_emit[TIR_MAX_RUNS]; // that misses the 2 KB constant cache)
 };
 
 #define TIR_XI(N1, plane, k1, n2, f) ((((plane) * (N1) + (k1)) * 16 + (n2)) * 32 + (f))
@@ -294,17 +297,18 @@ TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg,
 // ---- P3a: mel sweep -----------------------------------------------------------------------------
 // role = segment `seg` (warp-uniform), lane f = frame.  fmat_vecmul order: every filter's sum runs
 // over its bins in ascending order from 0.f; bins where a lane's weight is 0 add +0 (x is finite: a
-// magnitude).  The parameters of the next run are fetched while the current one accumulates (the
-// constant-bank loads are dependent, ~100 cycles each).  Writes the raw sums to lg.
-TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, int seg, int f, TirP2 nz) {
+// magnitude).  Weights and run lists are read from shared memory (w2, run_*); the parameters of the
+// next run are fetched while the current one accumulates.  Writes the raw sums to lg.
+TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, const float2 *w2, const int16_t *run_bins,
+                           const int16_t *run_emit, int seg, int f, TirP2 nz) {
   const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
   if (nr == 0) return;
   const float *m = norm + TIR_NORM_IDX(mp.seg_bin0[seg], f);
-  const float2 *wp = mp.w2 + mp.seg_woff[seg];
+  const float2 *wp = w2 + mp.seg_woff[seg];
   TirP2 acc = tir_pbc(0.f);
-  int n = mp.run_bins[r0], fe = mp.run_emit[r0];
+  int n = run_bins[r0], fe = run_emit[r0];
   for (int r = 0; r < nr; r++) {
-    const int n_next = mp.run_bins[r0 + r + 1], fe_next = mp.run_emit[r0 + r + 1]; // the list ends with a sentinel
+    const int n_next = run_bins[r0 + r + 1], fe_next = run_emit[r0 + r + 1]; // the list ends with a sentinel
 #pragma unroll 4
     for (int b = 0; b < n; b++) {
       const float2 wv = wp[b];

@@ -24,6 +24,8 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
   std::memcpy(sm->twu4, tab.twu4.data(), sizeof(sm->twu4));
   const double2 lt[16] = TIR_LOGF_TAB_INIT;
   std::memcpy(sm->logtab, lt, sizeof(lt));
+  std::memcpy(sm->w2, tab.mel.w2, sizeof(sm->w2));
+  for (int i = 0; i < TIR_MAX_RUNS; i++) sm->run_bins[i] = tab.mel.run_bins[i], sm->run_emit[i] = tab.mel.run_emit[i];
   const int64_t nsamp = (int64_t)n_samples;
   const int64_t nframes = (nsamp + C::HOP - 1) / C::HOP;
   std::vector<TirPass2Regs> regs(C::NT);
@@ -41,13 +43,13 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
           int64_t s = (f0 - 1 + chunk) * C::HOP + 4 * p + e;
           h[e] = (s >= 0 && s < nsamp) ? (uint16_t)pcm[s] : 0;
         }
-        sm->pcm[b][chunk * C::PCH + p].x = h[0] | (h[1] << 16);
-        sm->pcm[b][chunk * C::PCH + p].y = h[2] | (h[3] << 16);
+        sm->pcm[chunk * C::PCH + p].x = h[0] | (h[1] << 16);
+        sm->pcm[chunk * C::PCH + p].y = h[2] | (h[3] << 16);
       }
     for (int w = 0; w < C::NW; w++)
       for (int lane = 0; lane < 32; lane++) {
-        if constexpr (WIN == 512) tir_pass1_512(*sm, sm->pcm[b], w, lane, nz);
-        else tir_pass1_1024(*sm, sm->pcm[b], w, lane, nz);
+        if constexpr (WIN == 512) tir_pass1_512(*sm, sm->pcm, w, lane, nz);
+        else tir_pass1_1024(*sm, sm->pcm, w, lane, nz);
       }
     for (int w = 0; w < C::NW; w++)
       for (int lane = 0; lane < 32; lane++) tir_pass2_load<WIN>(*sm, w, lane, regs[w * 32 + lane]);
@@ -57,7 +59,7 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
         else tir_pass2_compute<WIN, false>(*sm, w, lane, regs[w * 32 + lane], nz);
       }
     for (int w = 0; w < C::NW; w++)
-      for (int lane = 0; lane < 32; lane++) tir_mel_sweep(sm->xch, sm->lg[b], tab.mel, w, lane, nz);
+      for (int lane = 0; lane < 32; lane++) tir_mel_sweep(sm->xch, sm->lg[b], tab.mel, sm->w2, sm->run_bins, sm->run_emit, w, lane, nz);
     for (int w = 0; w < C::NW; w++)
       for (int lane = 0; lane < 32; lane++) tir_log_phase<C::NW>(sm->lg[b], sm->logtab, tab.mel, w, lane);
     for (int j = 0; j < 2; j++)
