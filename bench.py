@@ -253,6 +253,7 @@ def match_bench(ctx, args, rank, world, device, dist):
     ms, kernel_ms, launches = timed(1, Q, max(args.steps, 5))
     hits = d_final.cpu().numpy().view(capi.HIT_DTYPE)
     search_e2e = search_bench(ctx, args, rank, world, device, dist, Q)
+    cpu_match = match_cpu_baseline(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     # verification on rank 0 / single GPU: brute-force restatement of the vote for a few queries
     verified = None
     if world == 1:
@@ -273,12 +274,36 @@ def match_bench(ctx, args, rank, world, device, dist):
            "per_query_path_coefs2": {"value": nq2 / (ms2 * 1e-3), "unit": "queries/s", "ms_per_batch": ms2, "queries_per_batch": nq2,
                                      "kernel_ms_rank0": k_ms2, "coefs": 2, "tolerance": 0.001},
            "self_matches_top": int((hits["match_count"][: Q // 10] > 0).sum()), "verified_queries": verified,
-           "search_e2e": search_e2e,
+           "search_e2e": search_e2e, "cpu_baseline": cpu_match,
            "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None,
                         "unit": "GB/s", "algorithmic_bytes_per_batch_this_rank": alg,
                         "note": "SURVEY 8d charge F_q*8 + sum_k(16 + 8*R_k) + 24 per QUERY; the shared-window path reads each distinct window once per BATCH (6 B per row in it) plus 4 B per uuid for the pattern sweep, so the charged figure can exceed the HBM peak"}}
     del uu, v1, v2
     return res
+
+
+def match_cpu_baseline(args):
+    """The reference's match path on the host: its SQL text on the real SQLite (oracle, kind "reference
+    SQL on libsqlite3"), one connection, one thread, on a BOUNDED database -- 5 000 fingerprints x 94
+    frames (470 k rows; SQLite ingests ~30 k rows/s through the reference's textual INSERTs, so the
+    10 M-fingerprint table of the GPU leg would take hours to build)."""
+    from oracle import pyoracle as po
+    from asterisk_tiresias_b200 import synth
+    rng = np.random.default_rng(77)
+    n_fp, F = 5000, 94
+    sq = po.SqliteDB()
+    t0 = time.time()
+    for i in range(n_fp):
+        y = np.stack([rng.uniform(15.5, 18.5, F), rng.uniform(-5.0, 20.0, F)], axis=1)
+        sq.add_audio(synth.uuid_for(3_000_000 + i), y)
+    ingest_s = time.time() - t0
+    qs = [np.stack([rng.uniform(15.5, 18.5, F), rng.uniform(-5.0, 20.0, F)], axis=1) for _ in range(20)]
+    t0 = time.time()
+    found = sum(1 for y in qs if sq.search(y, 1, 0.001) is not None)
+    dt = time.time() - t0
+    return {"value": len(qs) / dt, "unit": "queries/s", "cores": 1, "kind": "reference SQL on libsqlite3 " + po.SqliteDB.sqlite_version(),
+            "sample": f"{len(qs)} queries x {F} frames against {n_fp} fingerprints x {F} frames ({n_fp * F} rows), coefs 1, tolerance 0.001",
+            "ingest_rows_per_s": n_fp * F / ingest_s, "found": found}
 
 
 def search_bench(ctx, args, rank, world, device, dist, Q):
