@@ -52,6 +52,23 @@ int tir_reserve_host(tir_ctx *ctx, DevBuf &b, size_t bytes) {
   return TIR_OK;
 }
 
+int tir_stage_acquire(tir_ctx *ctx, size_t bytes, void **p, int *slot) {
+  const int k = ctx->h_stage_next;
+  ctx->h_stage_next = (k + 1) % tir_ctx::kStageSlots;
+  if (!ctx->h_stage_ev[k]) TIR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->h_stage_ev[k], cudaEventDisableTiming));
+  if (ctx->h_stage_used[k]) TIR_CUDA(ctx, cudaEventSynchronize(ctx->h_stage_ev[k])); // four calls ago: normally long done
+  int rc;
+  if ((rc = tir_reserve_host(ctx, ctx->h_stage[k], bytes))) return rc;
+  *p = ctx->h_stage[k].p, *slot = k;
+  return TIR_OK;
+}
+
+int tir_stage_release(tir_ctx *ctx, int slot) {
+  TIR_CUDA(ctx, cudaEventRecord(ctx->h_stage_ev[slot], ctx->stream));
+  ctx->h_stage_used[slot] = true;
+  return TIR_OK;
+}
+
 static void free_dev(DevBuf &b) {
   if (b.p) cudaFree(b.p);
   b.p = nullptr, b.cap = 0;
@@ -127,7 +144,10 @@ void tir_close(tir_ctx *ctx) {
   cudaFree(ctx->d_win4), cudaFree(ctx->d_twp4), cudaFree(ctx->d_twu4);
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
   free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y), free_dev(ctx->d_counter);
-  if (ctx->h_meta.p) cudaFreeHost(ctx->h_meta.p);
+  for (int k = 0; k < tir_ctx::kStageSlots; k++) {
+    if (ctx->h_stage[k].p) cudaFreeHost(ctx->h_stage[k].p);
+    if (ctx->h_stage_ev[k]) cudaEventDestroy(ctx->h_stage_ev[k]);
+  }
   for (int w = 0; w < 2; w++)
     for (int e = 0; e < 2; e++)
       if (ctx->ev[w][e]) cudaEventDestroy(ctx->ev[w][e]);

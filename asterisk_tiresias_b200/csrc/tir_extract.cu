@@ -266,16 +266,18 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
   const size_t off_clip = 0, off_frame = off_clip + nc1 * 8, off_tileoff = off_frame + nc1 * 8;
   const size_t meta_bytes = (off_tileoff + nc1 * 4 + 15) & ~(size_t)15;
   int rc;
-  if ((rc = tir_reserve_host(ctx, ctx->h_meta, meta_bytes))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_clipmeta, meta_bytes))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_tilemeta, (size_t)n_tiles * sizeof(TirTile)))) return rc;
-  unsigned char *h = (unsigned char *)ctx->h_meta.p;
-  TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the staging buffer may still be in flight
+  void *hp;
+  int slot;
+  if ((rc = tir_stage_acquire(ctx, meta_bytes, &hp, &slot))) return rc;
+  unsigned char *h = (unsigned char *)hp;
   std::memcpy(h + off_clip, clip_off, nc1 * 8);
   std::memcpy(h + off_frame, frame_off.data(), nc1 * 8);
   std::memcpy(h + off_tileoff, tile_off.data(), nc1 * 4);
   unsigned char *d = (unsigned char *)ctx->d_clipmeta.p;
   TIR_CUDA(ctx, cudaMemcpyAsync(d, h, meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = tir_stage_release(ctx, slot))) return rc;
   TirTile *d_tiles = (TirTile *)ctx->d_tilemeta.p;
   tir_build_tiles_kernel<C::T, C::HOP><<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(
       (const uint64_t *)(d + off_clip), (const uint64_t *)(d + off_frame), (const uint32_t *)(d + off_tileoff), n_clips,

@@ -36,8 +36,13 @@ struct tir_ctx {
   float4 *d_win4 = nullptr, *d_twp4 = nullptr, *d_twu4 = nullptr;
   // reusable device scratch
   DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y, d_counter;
-  // pinned staging for small metadata
-  DevBuf h_meta;
+  // pinned staging for small metadata: a ring, so that a call does not have to wait for the previous
+  // call's copy (each slot is guarded by an event recorded after the copy that reads it)
+  static constexpr int kStageSlots = 4;
+  DevBuf h_stage[kStageSlots];
+  cudaEvent_t h_stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool h_stage_used[kStageSlots] = {false, false, false, false};
+  int h_stage_next = 0;
   TirDb *db = nullptr;
   TirBatcher *batcher = nullptr;
   std::mutex batcher_mu; // guards `batcher` itself (never held across GPU work)
@@ -54,6 +59,10 @@ int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...);
 
 int tir_reserve(tir_ctx *ctx, DevBuf &b, size_t bytes);      // device scratch, grows only
 int tir_reserve_host(tir_ctx *ctx, DevBuf &b, size_t bytes); // pinned host scratch
+// next staging slot, at least `bytes` large and no longer read by the device; after enqueueing the
+// copy that reads it on ctx->stream call tir_stage_release(ctx, slot)
+int tir_stage_acquire(tir_ctx *ctx, size_t bytes, void **p, int *slot);
+int tir_stage_release(tir_ctx *ctx, int slot);
 
 // tir_extract.cu
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,

@@ -31,6 +31,25 @@
 
 #include "tir_internal.h"
 
+// Programmatic dependent launch: the query pipeline is seven small kernels whose launch gaps cost as
+// much as the kernels.  Each kernel of the chain lets its successor be scheduled at once
+// (griddepcontrol.launch_dependents) and waits for its predecessor's results
+// (griddepcontrol.wait = all of the predecessor's memory operations are visible) before touching them.
+#define TIR_PDL_PROLOGUE()                               \
+  asm volatile("griddepcontrol.launch_dependents;" ::);  \
+  asm volatile("griddepcontrol.wait;" ::: "memory")
+
+template <typename... KArgs, typename... Args>
+static cudaError_t tir_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = 0, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define TIR_BLOCK_UUIDS 16384 // uuids per index block: u16 local ids, 32 KB of u16 vote counters
 #define TIR_MATCH_THREADS 256
 
@@ -285,6 +304,7 @@ template <bool FROM_COEF>
 __global__ void tir_qprep_kernel(const double *__restrict__ y, const float *__restrict__ coef,
                                  const uint64_t *__restrict__ frame_off, const TirMatchParams mp,
                                  TirWindow *__restrict__ windows, uint32_t *__restrict__ n_windows) {
+  TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x;
   const uint64_t f0 = frame_off[q], f1 = frame_off[q + 1];
   TirWindow *wq = windows + f0;
@@ -386,6 +406,7 @@ struct TirBatch {
 __global__ void __launch_bounds__(1024)
     tir_batch_windows_kernel(TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
                              const uint64_t *__restrict__ frame_off, uint32_t n_queries, TirBatch *__restrict__ batch) {
+  TIR_PDL_PROLOGUE();
   __shared__ TirWindow s_w[TIR_MAX_SHARED];
   __shared__ uint32_t s_n, s_cand;
   const uint32_t tid = threadIdx.x;
@@ -431,6 +452,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_pattern_scan_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
                             const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
                             const TirBatch *__restrict__ batch, uint32_t *__restrict__ pattern) {
+  TIR_PDL_PROLOGUE();
   const uint32_t blk = blockIdx.x, k = blockIdx.y;
   if (batch->use_general || k >= batch->n_distinct) return;
   __shared__ uint64_t s_range[2];
@@ -462,6 +484,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
 __global__ void __launch_bounds__(256)
     tir_pattern_reduce_kernel(uint32_t *__restrict__ pattern, uint32_t n_audio, const TirBatch *__restrict__ batch,
                               uint32_t *__restrict__ max_rank1) {
+  TIR_PDL_PROLOGUE();
   if (batch->use_general || batch->n_distinct == 0) return;
   __shared__ uint32_t s_max[1 << TIR_MAX_SHARED];
   for (int i = threadIdx.x; i < (1 << TIR_MAX_SHARED); i += blockDim.x) s_max[i] = 0;
@@ -488,6 +511,7 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
                                            const uint64_t *__restrict__ frame_off, uint32_t n_queries,
                                            const TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
                                            unsigned long long *__restrict__ best) {
+  TIR_PDL_PROLOGUE();
   if (batch->use_general) return;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= n_queries) return;
@@ -523,6 +547,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
                      const TirBatch *__restrict__ batch) {
+  TIR_PDL_PROLOGUE();
   if (!batch->use_general) return;
   __shared__ uint32_t s_cnt[TIR_BLOCK_UUIDS / 2];  // u16 vote counters, two per word
   __shared__ uint32_t s_seen[TIR_BLOCK_UUIDS / 32]; // per-window "uuid already voted" bits
@@ -588,6 +613,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
 __global__ void tir_finalize_kernel(const unsigned long long *__restrict__ best, const uint32_t *__restrict__ order,
                                     const uint8_t *__restrict__ uuids, const uint64_t *__restrict__ frame_off,
                                     uint32_t n_queries, tir_hit *__restrict__ hits) {
+  TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_queries) return;
   const unsigned long long b = best[q];
@@ -651,11 +677,13 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   const size_t o_win = o_maxr + ((size_t)4 << TIR_MAX_SHARED);
   const size_t bytes = o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
   if ((rc = tir_reserve(ctx, ctx->d_qmeta, bytes))) return rc;
-  if ((rc = tir_reserve_host(ctx, ctx->h_meta, ((size_t)n_queries + 1) * 8))) return rc;
   unsigned char *d = (unsigned char *)ctx->d_qmeta.p;
-  TIR_CUDA(ctx, cudaStreamSynchronize(st));
-  std::memcpy(ctx->h_meta.p, frame_off, ((size_t)n_queries + 1) * 8);
-  TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, ctx->h_meta.p, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+  void *hp;
+  int slot;
+  if ((rc = tir_stage_acquire(ctx, ((size_t)n_queries + 1) * 8, &hp, &slot))) return rc;
+  std::memcpy(hp, frame_off, ((size_t)n_queries + 1) * 8);
+  TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, hp, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+  if ((rc = tir_stage_release(ctx, slot))) return rc;
   TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_win - o_best, st)); // best, batch, max_rank1
   TirMatchParams mp;
   mp.coefs = coefs;
@@ -670,9 +698,9 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   uint32_t *d_maxr = (uint32_t *)(d + o_maxr);
   TirWindow *d_win = (TirWindow *)(d + o_win);
   if (d_coef)
-    tir_qprep_kernel<true><<<n_queries, 128, 0, st>>>(nullptr, d_coef, d_foff, mp, d_win, d_nw);
+    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(128), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw));
   else
-    tir_qprep_kernel<false><<<n_queries, 128, 0, st>>>(d_y, nullptr, d_foff, mp, d_win, d_nw);
+    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(128), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw));
   ctx->launches++;
   if (db->n_blocks && db->n_indexed) {
     const int32_t *k1 = (const int32_t *)db->key1.p, *k2 = (const int32_t *)db->key2.p;
@@ -681,32 +709,32 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     uint32_t *pat = (uint32_t *)db->pattern.p;
     const uint32_t n_ranks = db->n_blocks * TIR_BLOCK_UUIDS;
     if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    tir_batch_windows_kernel<<<1, 1024, 0, st>>>(d_win, d_nw, d_foff, n_queries, d_batch);
+    TIR_CUDA(ctx, tir_launch_pdl(tir_batch_windows_kernel, dim3(1), dim3(1024), st, d_win, (const uint32_t *)d_nw, d_foff, n_queries, d_batch));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
     const dim3 pgrid(db->n_blocks, TIR_MAX_SHARED);
-    if (coefs >= 2) tir_pattern_scan_kernel<2><<<pgrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_batch, pat);
-    else tir_pattern_scan_kernel<1><<<pgrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_batch, pat);
+    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_scan_kernel<2>, pgrid, dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirBatch *)d_batch, pat));
+    else TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_scan_kernel<1>, pgrid, dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirBatch *)d_batch, pat));
     const uint32_t rgrid = std::min<uint32_t>((n_ranks / 4 + 255) / 256, (uint32_t)ctx->num_sms * 4);
-    tir_pattern_reduce_kernel<<<rgrid, 256, 0, st>>>(pat, n_ranks, d_batch, d_maxr);
-    tir_pattern_resolve_kernel<<<(n_queries * 32 + 255) / 256, 256, 0, st>>>(d_win, d_nw, d_foff, n_queries, d_batch, d_maxr,
-                                                                           d_best);
+    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_reduce_kernel, dim3(rgrid), dim3(256), st, pat, n_ranks, (const TirBatch *)d_batch, d_maxr));
+    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
+                                 (const uint32_t *)d_nw, d_foff, n_queries, (const TirBatch *)d_batch, (const uint32_t *)d_maxr, d_best));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 6);
     if (coefs >= 2)
-      tir_match_kernel<2><<<ggrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_win, d_nw, d_foff, d_best, db->n_blocks,
-                                                               n_queries, d_batch);
+      TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<2>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
+                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, (const TirBatch *)d_batch));
     else
-      tir_match_kernel<1><<<ggrid, TIR_MATCH_THREADS, 0, st>>>(k1, uid, k2, bst, d_win, d_nw, d_foff, d_best, db->n_blocks,
-                                                               n_queries, d_batch);
+      TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
+                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, (const TirBatch *)d_batch));
     ctx->launches += 5;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
       ctx->ev_valid[1] = true;
     }
   }
-  tir_finalize_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(d_best, (const uint32_t *)db->order.p,
-                                                               (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits);
+  TIR_CUDA(ctx, tir_launch_pdl(tir_finalize_kernel, dim3((n_queries + 127) / 128), dim3(128), st, (const unsigned long long *)d_best,
+                               (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits));
   ctx->launches++;
   TIR_CUDA(ctx, cudaGetLastError());
   return TIR_OK;

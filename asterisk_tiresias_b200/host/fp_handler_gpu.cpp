@@ -241,14 +241,29 @@ extern "C" {
 void fp_set_log(void (*fn)(int, const char *)) { g_log = fn; }
 void *fp_sqlite_handle(void) { return g.db; }
 
+static bool fp_init_locked(const char *backup_db, int device);
+
+static void reset_state() {
+  for (auto &kv : g.plans) tir_close(kv.second);
+  g.plans.clear(), g.main = nullptr;
+  if (g.db) tir_sqlite().close(g.db);
+  g.db = nullptr;
+}
+
 bool fp_init(const char *backup_db, int device) {
   std::lock_guard<std::mutex> lk(g.mu);
+  if (g.db) return true;
+  if (fp_init_locked(backup_db, device)) return true;
+  reset_state(); // a failed load leaves nothing behind: the module declines to load
+  return false;
+}
+
+static bool fp_init_locked(const char *backup_db, int device) {
   TirSqlite &s = tir_sqlite();
   if (!s.ok) {
     ast_log_(LOG_ERROR_, "Could not initiate database. err[libsqlite3 not found]\n");
     return false;
   }
-  if (g.db) return true;
   g.device = device, g.backup = backup_db ? backup_db : "";
   if (s.open(":memory:", &g.db) != kSqliteOk || !create_tables()) {
     ast_log_(LOG_ERROR_, "Could not initiate database.\n");
@@ -300,9 +315,7 @@ bool fp_term(void) {
     if (file) s.close(file);
     if (!ok) ast_log_(LOG_ERROR_, "Could not write database.\n");
   }
-  for (auto &kv : g.plans) tir_close(kv.second);
-  g.plans.clear(), g.main = nullptr;
-  s.close(g.db), g.db = nullptr;
+  reset_state();
   return ok;
 }
 

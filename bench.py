@@ -438,7 +438,11 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything that is timed: the library (a NULL handle would make it create
+    # its own stream), torch's events and NCCL's collectives all run on it
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = capi.Context(device=local_rank, win=WIN, hop=HOP, samplerate=SR, stream=stream.cuda_stream)
     ctx.set_profiling(True)
 

@@ -56,3 +56,32 @@ def test_no_gpu_means_loud_failure_not_fallback():
         pytest.skip("GPU present")
     with pytest.raises(capi.TirError):
         capi.Context(device=0)
+
+
+def test_host_mirror_exports_the_reference_interface_and_refuses_to_run_without_a_gpu():
+    """libtiresias_host.so carries every function of src/fp_handler.h:13-38 under the same name; with no
+    CUDA device fp_init() must fail (the module would decline to load) instead of falling back."""
+    import torch
+    from asterisk_tiresias_b200.host import fp_host
+    L = fp_host.lib()
+    for name in ["fp_init", "fp_term", "fp_create_context_list_info", "fp_delete_context_list_info", "fp_get_context_lists_all",
+                 "fp_get_context_list_info", "fp_get_audio_lists_all", "fp_get_audio_lists_by_contextname",
+                 "fp_craete_audio_list_info", "fp_delete_audio_list_info", "fp_search_fingerprint_info", "fp_generate_uuid",
+                 "fp_create_hash"]:
+        assert hasattr(L, name), name
+    u = fp_host.fp_generate_uuid()
+    assert len(u) == 36 and u[14] == "4"
+    if not torch.cuda.is_available():
+        assert fp_host.fp_init(None, 0) is False
+        assert fp_host.fp_init(None, 0) is False          # and a failed load leaves no half-open state behind
+        assert fp_host.fp_get_audio_lists_all() == []
+        assert fp_host.fp_search_fingerprint_info("ctx", "/nonexistent.wav") is None
+
+
+def test_batcher_and_stream_entry_points_reject_bad_arguments_without_a_gpu():
+    from asterisk_tiresias_b200 import capi
+    L = capi.lib()
+    assert L.tir_batcher_start(None, 16, 100) != 0
+    assert L.tir_search_one(None, None, 0, 1, 0.001, -1, -1, None) != 0
+    assert L.tir_stream_feed(None, None, 0) != 0
+    assert L.tir_db_load_sqlite(None, None, None, None, None) != 0
