@@ -56,6 +56,7 @@ def lib():
         L.tir_n_frames.restype = C.c_uint64
         L.tir_n_frames.argtypes = [C.c_uint64, C.c_int]
         L.tir_extract.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
+        L.tir_extract_ulaw.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_extract_dev.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_get_tables.argtypes = [vp, vp, vp, vp]
         L.tir_launch_count.restype = C.c_uint64
@@ -166,6 +167,20 @@ class Context:
         vq = np.empty((F, 2), np.int32)
         nf = C.c_uint64()
         self._chk(lib().tir_extract(self._h, _p(pcm), _p(clip_off), clip_off.size - 1, _p(coef), _p(vq), C.byref(nf)))
+        assert nf.value == F
+        return coef, vq
+
+    def extract_ulaw(self, ulaw, clip_off=None):
+        """G.711 mu-law bytes in (uint8), host buffers out."""
+        ulaw = np.ascontiguousarray(ulaw, dtype=np.uint8)
+        if clip_off is None:
+            clip_off = np.array([0, ulaw.size], np.uint64)
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        F = self.n_frames(clip_off)
+        coef = np.empty((F, 2), np.float32)
+        vq = np.empty((F, 2), np.int32)
+        nf = C.c_uint64()
+        self._chk(lib().tir_extract_ulaw(self._h, _p(ulaw), _p(clip_off), clip_off.size - 1, _p(coef), _p(vq), C.byref(nf)))
         assert nf.value == F
         return coef, vq
 

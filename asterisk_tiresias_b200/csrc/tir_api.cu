@@ -143,7 +143,7 @@ void tir_close(tir_ctx *ctx) {
   if (ctx->db) tir_db_destroy(ctx->db);
   cudaFree(ctx->d_win4), cudaFree(ctx->d_twp4), cudaFree(ctx->d_twu4);
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
-  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y), free_dev(ctx->d_counter);
+  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_hits), free_dev(ctx->d_y), free_dev(ctx->d_counter), free_dev(ctx->d_ulaw);
   for (int k = 0; k < tir_ctx::kStageSlots; k++) {
     if (ctx->h_stage[k].p) cudaFreeHost(ctx->h_stage[k].p);
     if (ctx->h_stage_ev[k]) cudaEventDestroy(ctx->h_stage_ev[k]);
@@ -191,9 +191,12 @@ int tir_extract_dev(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off
   return tir_extract_launch(ctx, d_pcm, clip_off[n_clips], clip_off, n_clips, d_coef, d_vq, n_frames);
 }
 
-int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, float *coef, int32_t *vq,
-                uint64_t *n_frames) {
-  if (!ctx || !clip_off || (!pcm && n_clips && clip_off[n_clips] > clip_off[0])) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+// host buffers in, host buffers out; `src` is PCM16 (ulaw == false) or G.711 mu-law bytes
+static int extract_host(tir_ctx *ctx, const void *src, bool ulaw, const uint64_t *clip_off, uint32_t n_clips, float *coef,
+                        int32_t *vq, uint64_t *n_frames) {
+  if (!ctx || !clip_off || (!src && n_clips && clip_off[n_clips] > clip_off[0])) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  const int16_t *pcm = ulaw ? nullptr : (const int16_t *)src;
+  const uint8_t *law = ulaw ? (const uint8_t *)src : nullptr;
   std::lock_guard<std::mutex> lk(ctx->mu);
   TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
   const uint64_t base = clip_off[0], total = clip_off[n_clips] - base;
@@ -208,6 +211,8 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
   if ((rc = tir_reserve(ctx, ctx->d_pcm, total * sizeof(int16_t) + 16))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_coef, F * TIR_N_COEFS * sizeof(float)))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_vq, F * TIR_N_COEFS * sizeof(int32_t)))) return rc;
+  if (ulaw && (rc = tir_reserve(ctx, ctx->d_ulaw, total + 16))) return rc;
+  uint8_t *d_law = (uint8_t *)ctx->d_ulaw.p;
   // The batch is cut into chunks of whole clips (~96 MB of PCM) that flow through three queues:
   // copy-in stream -> ctx's stream (kernel) -> copy-out stream, so the PCIe transfers of one chunk
   // overlap the kernel of another.
@@ -246,7 +251,8 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
   for (Chunk &k : chunks) {
     const uint64_t s0 = clip_off[k.c0] - base, s1 = clip_off[k.c1] - base;
     if (s1 > s0 && e == cudaSuccess)
-      e = cudaMemcpyAsync(d_pcm + s0, pcm + base + s0, (s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->s_in);
+      e = ulaw ? cudaMemcpyAsync(d_law + s0, law + base + s0, s1 - s0, cudaMemcpyHostToDevice, ctx->s_in)
+               : cudaMemcpyAsync(d_pcm + s0, pcm + base + s0, (s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->s_in);
     if (e == cudaSuccess) e = cudaEventRecord(k.in, ctx->s_in);
   }
   std::vector<uint64_t> rel;
@@ -254,6 +260,14 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
     if (e != cudaSuccess) break;
     e = cudaStreamWaitEvent(ctx->stream, k.in, 0);
     if (e != cudaSuccess) break;
+    if (ulaw) { // bytes -> PCM16 on the device: half the PCIe traffic of the PCM16 entry point
+      const uint64_t s0 = clip_off[k.c0] - base, s1 = clip_off[k.c1] - base;
+      if ((rc = tir_ulaw_decode_launch(ctx, d_law + s0, d_pcm + s0, s1 - s0))) {
+        cudaDeviceSynchronize();
+        cleanup();
+        return rc;
+      }
+    }
     // offsets stay relative to the whole staged batch: a clip keeps the alignment it has in the caller's buffer
     rel.assign((size_t)(k.c1 - k.c0) + 1, 0);
     for (uint32_t c = k.c0; c <= k.c1; c++) rel[c - k.c0] = clip_off[c] - base;
@@ -277,6 +291,16 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
   cleanup();
   if (e != cudaSuccess) return tir_fail(ctx, TIR_ERR_CUDA, "tir_extract: %s", cudaGetErrorString(e));
   return TIR_OK;
+}
+
+int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, float *coef, int32_t *vq,
+                uint64_t *n_frames) {
+  return extract_host(ctx, pcm, false, clip_off, n_clips, coef, vq, n_frames);
+}
+
+int tir_extract_ulaw(tir_ctx *ctx, const uint8_t *ulaw, const uint64_t *clip_off, uint32_t n_clips, float *coef, int32_t *vq,
+                     uint64_t *n_frames) {
+  return extract_host(ctx, ulaw, true, clip_off, n_clips, coef, vq, n_frames);
 }
 
 } // extern "C"

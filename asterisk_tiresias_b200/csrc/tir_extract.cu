@@ -238,6 +238,42 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   if (warp < mp.n_coefs) tir_emit_coefs(sm.lg[b], mp, a, cur, warp, lane);
 }
 
+// G.711 mu-law -> PCM16 (what a channel's native ulaw frames decode to; same table as Asterisk's
+// AST_MULAW).  16 samples per thread when the source is 16-byte aligned.
+__device__ __forceinline__ int16_t tir_ulaw1(uint32_t b) {
+  const uint32_t u = ~b & 0xffu;
+  const int32_t mag = (int32_t)((((u & 0x0fu) << 3) + 0x84u) << ((u >> 4) & 7u));
+  return (int16_t)((u & 0x80u) ? 0x84 - mag : mag - 0x84);
+}
+
+__global__ void tir_ulaw_decode_kernel(const uint8_t *__restrict__ in, int16_t *__restrict__ out, uint64_t n) {
+  const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 >= n) return;
+  if (i0 + 16 <= n && ((uintptr_t)(in + i0) & 15) == 0 && ((uintptr_t)(out + i0) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(in + i0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      o[2 * k] = (uint32_t)(uint16_t)tir_ulaw1(w[k] & 0xff) | ((uint32_t)(uint16_t)tir_ulaw1((w[k] >> 8) & 0xff) << 16);
+      o[2 * k + 1] = (uint32_t)(uint16_t)tir_ulaw1((w[k] >> 16) & 0xff) | ((uint32_t)(uint16_t)tir_ulaw1(w[k] >> 24) << 16);
+    }
+    reinterpret_cast<uint4 *>(out + i0)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4 *>(out + i0)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else {
+    for (uint64_t i = i0; i < n && i < i0 + 16; i++) out[i] = tir_ulaw1(in[i]);
+  }
+}
+
+int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, uint64_t n) {
+  if (n == 0) return TIR_OK;
+  const uint64_t threads = (n + 15) / 16;
+  tir_ulaw_decode_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_out, n);
+  TIR_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return TIR_OK;
+}
+
 size_t tir_extract_smem_bytes(int win) {
   return win == 512 ? sizeof(TirSmem<512>) : win == 1024 ? sizeof(TirSmem<1024>) : 0;
 }

@@ -35,7 +35,7 @@ struct tir_ctx {
   // device copies of the kernel-layout tables
   float4 *d_win4 = nullptr, *d_twp4 = nullptr, *d_twu4 = nullptr;
   // reusable device scratch
-  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y, d_counter;
+  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_hits, d_y, d_counter, d_ulaw;
   // pinned staging for small metadata: a ring, so that a call does not have to wait for the previous
   // call's copy (each slot is guarded by an event recorded after the copy that reads it)
   static constexpr int kStageSlots = 4;
@@ -68,6 +68,7 @@ int tir_stage_release(tir_ctx *ctx, int slot);
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
                        uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames);
 size_t tir_extract_smem_bytes(int win);
+int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, uint64_t n);
 
 // tir_match.cu
 void tir_db_destroy(TirDb *db);

@@ -548,6 +548,40 @@ def main():
         e2e = {"value": world * n_clips * SECONDS / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(d_pcm.numel() * 2 + (n_clips + 1) * 20), "d2h_bytes_per_step": int(F * 16),
                "api": "tir_extract (host PCM16 in pinned memory -> coefficients + hashes in host memory)", "matches_device_run": same}
+        # the same clips as the G.711 bytes they were decoded from (tir_extract_ulaw): half the H2D traffic
+        try:
+            sgn = d_pcm < 0
+            mag = torch.clamp(d_pcm.to(torch.int32).abs(), max=32635) + 0x84
+            ex_ = (torch.floor(torch.log2(mag.float())).to(torch.int32) - 7).clamp(0, 7)
+            code = (~(torch.where(sgn, 0x80, 0) | (ex_ << 4) | ((mag >> (ex_ + 3)) & 0x0F)) & 0xFF).to(torch.uint8)
+            h_law = torch.empty(code.shape, dtype=torch.uint8, pin_memory=True)
+            h_law.copy_(code)
+            del sgn, mag, ex_, code
+            torch.cuda.synchronize()
+
+            def ulaw_step():
+                rc = L.tir_extract_ulaw(ctx._h, C.c_void_p(h_law.data_ptr()), offc.ctypes.data_as(C.c_void_p), n_clips,
+                                        C.c_void_p(h_coef.data_ptr()), C.c_void_p(h_vq.data_ptr()), C.byref(nf))
+                if rc != 0:
+                    raise capi.TirError(rc, L.tir_last_error(ctx._h).decode())
+            for _ in range(2):
+                ulaw_step()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                ulaw_step()
+            e1.record()
+            barrier()
+            ms_u = e0.elapsed_time(e1) / args.steps
+            if world > 1:
+                tt = torch.tensor([ms_u], device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms_u = float(tt.item())
+            e2e["ulaw_input"] = {"value": world * n_clips * SECONDS / (ms_u * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_u,
+                                 "h2d_bytes_per_step": int(h_law.numel() + (n_clips + 1) * 20), "d2h_bytes_per_step": int(F * 16),
+                                 "api": "tir_extract_ulaw (the clips as the G.711 bytes they were decoded from; decoded on the device)",
+                                 "matches_device_run": bool((h_vq.view(-1)[: 2 * FRAMES_PER_CLIP] == d_vq.view(-1)[: 2 * FRAMES_PER_CLIP].cpu()).all())}
+            del h_law
+        except Exception as ex:  # noqa: BLE001
+            log("ulaw e2e leg failed:", ex)
         del h_pcm, h_coef, h_vq
     except Exception as ex:  # noqa: BLE001
         log("e2e leg failed:", ex)

