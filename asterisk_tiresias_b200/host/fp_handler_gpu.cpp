@@ -9,6 +9,7 @@
 // the SQL probe/tally of fp_search_fingerprint_info (:258-377) -> tir_match.
 #include "../../include/fp_handler_gpu.h"
 
+#include <dirent.h>
 #include <libgen.h>
 #include <openssl/evp.h>
 
@@ -513,6 +514,125 @@ bool fp_search_fingerprint_info(const char *context, const char *filename, const
   a.frame_count = hit.frame_count, a.match_count = hit.match_count; // :403-404
   if (out) *out = a;
   return true;
+}
+
+// init_audio() of the module shell (src/app_tiresias.c:324-551), which is where bulk fingerprinting
+// happens: for every context, audios whose file is gone are deleted (delete_removed_audio_info:
+// directory hashes vs audio_list.hash), files not yet listed are fingerprinted (create_new_audio_info
+// -> fp_craete_audio_list_info per file, scandir + alphasort, "." and ".." skipped).  Same outcome,
+// but the new files of a context go through ONE batched extraction launch per sample rate instead of
+// one aubio pass per file.  Returns the number of audios added, -1 on error.
+static int sync_context_locked(const fp_context_info &c) {
+  struct dirent **namelist = nullptr;
+  const int count = scandir(c.directory, &namelist, nullptr, alphasort);
+  if (count < 0) {
+    ast_log_(LOG_NOTICE_, "Could not get directory list info. context[%s]\n", c.name);
+    return -1;
+  }
+  std::vector<std::string> files, hashes;
+  for (int i = 0; i < count; i++) {
+    const std::string nm = namelist[i]->d_name;
+    free(namelist[i]);
+    if (nm == "." || nm == "..") continue; // file_select, :552-572
+    const std::string path = std::string(c.directory) + "/" + nm;
+    char *h = create_file_hash(path.c_str());
+    if (!h) continue;
+    files.push_back(path), hashes.push_back(h);
+    free(h);
+  }
+  free(namelist);
+  // delete_removed_audio_info(), :431-550
+  const std::string q = fmt("select * from audio_list where context = '%s';", c.name);
+  const int n_listed = query_audio(q, nullptr, 0);
+  std::vector<fp_audio_info> listed((size_t)std::max(n_listed, 0));
+  if (n_listed > 0) query_audio(q, listed.data(), n_listed);
+  for (const fp_audio_info &a : listed) {
+    bool found = false;
+    for (const std::string &h : hashes) found = found || h == a.hash;
+    if (!found && !delete_audio_locked(a.uuid)) ast_log_(LOG_DEBUG_, "Could not delete audio list info.\n");
+  }
+  // create_new_audio_info(), :364-424, batched: read every new file, one extraction per sample rate
+  struct NewAudio {
+    std::string path, hash, uuid;
+    std::vector<int16_t> pcm;
+    int rate;
+  };
+  std::vector<NewAudio> fresh;
+  for (size_t i = 0; i < files.size(); i++) {
+    bool known = false;
+    for (const fp_audio_info &a : listed) known = known || hashes[i] == a.hash;
+    for (const NewAudio &f : fresh) known = known || f.hash == hashes[i]; // the same bytes twice in one directory (P7)
+    if (known) continue;
+    NewAudio f;
+    f.path = files[i], f.hash = hashes[i];
+    char *u = fp_generate_uuid();
+    f.uuid = u;
+    free(u);
+    // the reference inserts the audio_list row before it tries to fingerprint, and leaves it there when
+    // fingerprinting fails (K2, src/fp_handler.c:186-195)
+    std::string tmp = f.path;
+    if (!exec(fmt("insert into audio_list(uuid, name, context, hash) values ('%s', '%s', '%s', '%s');", f.uuid.c_str(),
+                  basename(&tmp[0]), c.name, f.hash.c_str()).c_str()))
+      continue;
+    if (!read_wav_pcm16_mono(f.path.c_str(), f.pcm, f.rate)) continue;
+    fresh.push_back(std::move(f));
+  }
+  int added = 0;
+  std::map<int, std::vector<size_t>> by_rate;
+  for (size_t i = 0; i < fresh.size(); i++) by_rate[fresh[i].rate].push_back(i);
+  for (auto &kv : by_rate) {
+    tir_ctx *ctx = plan_for_rate(kv.first);
+    if (!ctx) continue;
+    std::vector<int16_t> pcm;
+    std::vector<uint64_t> off(1, 0);
+    for (size_t i : kv.second) {
+      pcm.insert(pcm.end(), fresh[i].pcm.begin(), fresh[i].pcm.end());
+      off.push_back(pcm.size());
+    }
+    uint64_t frames = 0;
+    for (size_t k = 0; k + 1 < off.size(); k++) frames += tir_n_frames(off[k + 1] - off[k], 256);
+    std::vector<int32_t> vq(frames * 2);
+    if (tir_extract(ctx, pcm.data(), off.data(), (uint32_t)kv.second.size(), nullptr, vq.data(), &frames) != TIR_OK) {
+      ast_log_(LOG_ERROR_, "Could not create fingerprint data. err[%s]\n", tir_last_error(ctx));
+      continue;
+    }
+    uint64_t f0 = 0;
+    for (size_t k = 0; k < kv.second.size(); k++) {
+      const NewAudio &f = fresh[kv.second[k]];
+      const uint32_t nf = (uint32_t)tir_n_frames(off[k + 1] - off[k], 256);
+      const int32_t *v = vq.data() + f0 * 2;
+      f0 += nf;
+      uint8_t u16[16];
+      if (!parse_uuid16(f.uuid.c_str(), u16)) continue;
+      if (tir_sqlite_insert_fingerprints(g.main, g.db, c.name, f.uuid.c_str(), v, nf) != TIR_OK) continue;
+      std::vector<int32_t> v1(nf), v2(nf);
+      for (uint32_t t = 0; t < nf; t++) v1[t] = v[2 * t], v2[t] = v[2 * t + 1];
+      if (tir_db_add(g.main, u16, v1.data(), v2.data(), nf) == TIR_OK) added++;
+    }
+  }
+  return added;
+}
+
+int fp_sync_directories(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.db) return -1;
+  TirSqlite &s = tir_sqlite();
+  std::vector<fp_context_info> ctxs;
+  void *st = nullptr;
+  if (s.prepare_v2(g.db, "select * from context_list;", -1, &st, nullptr) != kSqliteOk) return -1;
+  while (s.step(st) == kSqliteRow) {
+    fp_context_info c;
+    copy_field(c.name, sizeof c.name, s.column_text(st, 0));
+    copy_field(c.directory, sizeof c.directory, s.column_text(st, 1));
+    ctxs.push_back(c);
+  }
+  s.finalize(st);
+  int added = 0;
+  for (const fp_context_info &c : ctxs) {
+    const int n = sync_context_locked(c);
+    if (n > 0) added += n;
+  }
+  return added;
 }
 
 char *fp_generate_uuid(void) { // uuid_generate + uuid_unparse_lower, :1103-1115 (libuuid's header is not installed: RFC 4122 v4 from /dev/urandom)

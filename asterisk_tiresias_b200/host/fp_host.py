@@ -105,6 +105,10 @@ def fp_search_fingerprint_info(context, filename, coefs=1, tolerance=0.001, freq
     return out.as_dict() if ok else None
 
 
+def fp_sync_directories():
+    return int(lib().fp_sync_directories())
+
+
 def fp_create_hash(filename):
     p = lib().fp_create_hash(_enc(filename))
     if not p:

@@ -58,6 +58,11 @@ bool fp_delete_audio_list_info(const char *uuid);
 bool fp_search_fingerprint_info(const char *context, const char *filename, const int coefs, const double tolerance,
                                 const int freq_ignore_low, const int freq_ignore_high, fp_audio_info *out);
 
+/* init_audio() of the module shell (src/app_tiresias.c:324-551): for every context delete the audios
+ * whose file disappeared from its directory, fingerprint the files that are not listed yet -- the new
+ * files of a context in ONE batched extraction per sample rate.  Returns the audios added, -1 on error. */
+int fp_sync_directories(void);
+
 char *fp_generate_uuid(void);              /* malloc'ed, caller frees */
 char *fp_create_hash(const char *filename); /* malloc'ed md5 hex, caller frees */
 

@@ -88,6 +88,61 @@ def test_directory_fingerprint_search_delete_backup_restore(oracle, tmp_path):
         fp.fp_term()
 
 
+def test_directory_sync_batches_new_files_and_drops_removed_ones(oracle, tmp_path):
+    """init_audio() (src/app_tiresias.c:324-551): what module load does with the configured directories."""
+    plan = oracle.Plan()
+    d1, d2 = tmp_path / "prompts", tmp_path / "wide"
+    d1.mkdir(); d2.mkdir()
+    clips = {}
+    for i in range(40):
+        pcm = synth.make_clip(9100 + i, 1.0 + (i % 5) * 0.5)
+        fp.write_wav(str(d1 / f"p{i:02d}.wav"), pcm)
+        clips[f"p{i:02d}.wav"] = (pcm, 8000)
+    for i in range(6):                                          # a second context at 16 kHz: another plan, same table
+        pcm = synth.make_clip(9200 + i, 1.5, samplerate=16000)
+        fp.write_wav(str(d2 / f"w{i}.wav"), pcm, rate=16000)
+        clips[f"w{i}.wav"] = (pcm, 16000)
+    fp.write_wav(str(d1 / "copy-of-p00.wav"), clips["p00.wav"][0])   # same bytes, other name: one audio (P7);
+    clips["copy-of-p00.wav"] = clips["p00.wav"]                        # alphasort lists the copy first
+    assert fp.fp_init(None, 0)
+    try:
+        assert fp.fp_create_context_list_info("prompts", str(d1), False) and fp.fp_create_context_list_info("wide", str(d2), False)
+        assert fp.fp_sync_directories() == 46
+        assert fp.fp_sync_directories() == 0                      # idempotent
+        lst = fp.fp_get_audio_lists_all()
+        assert len(lst) == 46 and len(fp.fp_get_audio_lists_by_contextname("wide")) == 6
+        sq, by_uuid = oracle.SqliteDB(), {}
+        plans = {8000: plan, 16000: oracle.Plan(samplerate=16000)}
+        for a in lst:
+            pcm, sr = clips[a["name"]]
+            sq.add_audio(a["uuid"], plans[sr].extract(pcm)[1], context=a["context"], name=a["name"])
+            by_uuid[a["uuid"]] = a["name"]
+        for name in ("p07.wav", "p39.wav", "w3.wav"):
+            pcm, sr = clips[name]
+            for tol in (0.01, 0.2):
+                r = fp.fp_search_fingerprint_info("prompts", str((d2 if sr == 16000 else d1) / name), 1, tol)
+                assert got(r) == expect(sq, plans[sr], pcm, by_uuid, 1, tol), (name, tol)
+        # files removed from / added to the directory between two loads
+        os.remove(d1 / "p07.wav"); os.remove(d1 / "p08.wav")
+        extra = synth.make_clip(9300, 2.0)
+        fp.write_wav(str(d1 / "new.wav"), extra)
+        assert fp.fp_sync_directories() == 1
+        names = sorted(a["name"] for a in fp.fp_get_audio_lists_by_contextname("prompts"))
+        assert "p07.wav" not in names and "p08.wav" not in names and "new.wav" in names and len(names) == 39
+        now = {a["name"]: a["uuid"] for a in fp.fp_get_audio_lists_by_contextname("prompts")}
+        for a in lst:
+            if a["name"] in ("p07.wav", "p08.wav"):
+                sq.delete_audio(a["uuid"])
+        sq.add_audio(now["new.wav"], plan.extract(extra)[1], context="prompts", name="new.wav")
+        by_uuid[now["new.wav"]] = "new.wav"
+        for pcm in (extra, clips["p07.wav"][0], clips["p20.wav"][0]):
+            fp.write_wav(str(tmp_path / "q.wav"), pcm)
+            for tol in (0.001, 0.3):
+                assert got(fp.fp_search_fingerprint_info("prompts", str(tmp_path / "q.wav"), 1, tol)) == expect(sq, plan, pcm, by_uuid, 1, tol)
+    finally:
+        fp.fp_term()
+
+
 def test_non_mono_or_non_pcm16_files_are_refused(tmp_path):
     assert fp.fp_init(None, 0)
     try:
