@@ -56,6 +56,7 @@ def lib():
         L.tir_n_frames.restype = C.c_uint64
         L.tir_n_frames.argtypes = [C.c_uint64, C.c_int]
         L.tir_extract.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
+        L.tir_selftest.argtypes = [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.tir_extract_ulaw.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_extract_dev.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_get_tables.argtypes = [vp, vp, vp, vp]
@@ -169,6 +170,16 @@ class Context:
         self._chk(lib().tir_extract(self._h, _p(pcm), _p(clip_off), clip_off.size - 1, _p(coef), _p(vq), C.byref(nf)))
         assert nf.value == F
         return coef, vq
+
+    def selftest_sqrt(self):
+        bad = C.c_uint64(1 << 60)
+        self._chk(lib().tir_selftest(self._h, C.byref(bad), 0, 0, 0, None))
+        return int(bad.value)
+
+    def selftest_log10f(self, first_bits, step, count):
+        out = np.empty(count, np.float32)
+        self._chk(lib().tir_selftest(self._h, None, first_bits, step, count, _p(out)))
+        return out
 
     def extract_ulaw(self, ulaw, clip_off=None):
         """G.711 mu-law bytes in (uint8), host buffers out."""

@@ -175,6 +175,13 @@ float tir_last_kernel_ms(tir_ctx *ctx, int which) {
   return ms;
 }
 
+int tir_selftest(tir_ctx *ctx, uint64_t *sqrt_mismatches, uint32_t first_bits, uint32_t step, uint32_t count, float *log10f_out) {
+  if (!ctx) return TIR_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return tir_selftest_launch(ctx, sqrt_mismatches, first_bits, step, count, log10f_out);
+}
+
 int tir_get_tables(tir_ctx *ctx, float *window, float *filters, float *dct) {
   if (!ctx) return TIR_ERR_ARG;
   if (window) std::memcpy(window, ctx->tab.window.data(), ctx->tab.window.size() * sizeof(float));

@@ -274,6 +274,53 @@ int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, ui
   return TIR_OK;
 }
 
+// ---- self tests of the two float primitives the bit-exactness rests on ---------------------------
+// (a) tir_sqrt_scaled64 against the IEEE square root, for EVERY float in [2^-149, 2^60) and 0;
+// (b) the device build of tir_log10f_glibc over a strided range, returned for comparison with the
+//     host build of the same source (which the CPU tests pin to libm's log10f).
+__global__ void tir_selftest_sqrt_kernel(unsigned long long *__restrict__ bad) {
+  const uint32_t last = 0x5d800000u; // 2^60
+  unsigned long long n = 0;
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < last; u += (uint64_t)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((uint32_t)u);
+    const float a = tir_sqrt_scaled64(x), b = __fsqrt_rn(__fmul_rn(x, 18446744073709551616.0f));
+    n += __float_as_uint(a) != __float_as_uint(b);
+  }
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(bad, n);
+}
+
+__global__ void tir_selftest_log10f_kernel(uint32_t first, uint32_t step, uint32_t count, float *__restrict__ out) {
+  __shared__ double2 tab[16];
+  if (threadIdx.x < 16) tab[threadIdx.x] = k_logf_tab[threadIdx.x];
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = tir_log10f_glibc(__uint_as_float(first + i * step), tab);
+}
+
+int tir_selftest_launch(tir_ctx *ctx, uint64_t *sqrt_mismatches, uint32_t first, uint32_t step, uint32_t count, float *log10f_out) {
+  if (sqrt_mismatches) {
+    unsigned long long *d = nullptr;
+    TIR_CUDA(ctx, cudaMalloc(&d, 8));
+    TIR_CUDA(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+    tir_selftest_sqrt_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d);
+    unsigned long long h = 0;
+    TIR_CUDA(ctx, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    *sqrt_mismatches = h;
+  }
+  if (log10f_out && count) {
+    float *d = nullptr;
+    TIR_CUDA(ctx, cudaMalloc(&d, (size_t)count * 4));
+    tir_selftest_log10f_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(first, step, count, d);
+    TIR_CUDA(ctx, cudaMemcpyAsync(log10f_out, d, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+  }
+  return TIR_OK;
+}
+
 size_t tir_extract_smem_bytes(int win) {
   return win == 512 ? sizeof(TirSmem<512>) : win == 1024 ? sizeof(TirSmem<1024>) : 0;
 }

@@ -68,6 +68,7 @@ int tir_stage_release(tir_ctx *ctx, int slot);
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
                        uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames);
 size_t tir_extract_smem_bytes(int win);
+int tir_selftest_launch(tir_ctx *ctx, uint64_t *sqrt_mismatches, uint32_t first, uint32_t step, uint32_t count, float *log10f_out);
 int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, uint64_t n);
 
 // tir_match.cu

@@ -93,6 +93,14 @@ int tir_extract_ulaw(tir_ctx *ctx, const uint8_t *ulaw, const uint64_t *clip_off
 int tir_extract_dev(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,
                     float *d_coef, int32_t *d_vq, uint64_t *n_frames);
 
+/* Diagnostics of the two float primitives the bit-exactness of the extraction rests on.
+ *  sqrt_mismatches (may be NULL): the kernel's branch-free square root against the IEEE one for every
+ *    float in [2^-149, 2^60) -- must come back 0;
+ *  log10f_out (may be NULL): the DEVICE build of the glibc-exact log10f for the `count` floats with bit
+ *    patterns first_bits + i*step, for comparison with libm on the host. */
+int tir_selftest(tir_ctx *ctx, uint64_t *sqrt_mismatches, uint32_t first_bits, uint32_t step, uint32_t count,
+                 float *log10f_out);
+
 /* the plan's aubio-layout tables, for table-level parity tests (host copies) */
 int tir_get_tables(tir_ctx *ctx, float *window /*[win]*/, float *filters /*[n_filters][win/2+1]*/,
                    float *dct /*[2][n_filters]*/);

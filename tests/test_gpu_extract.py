@@ -181,6 +181,28 @@ def test_tables_match_oracle(gpu_ctx, oracle):
     assert np.array_equal(d.view(np.uint32), p.dct.view(np.uint32))
 
 
+def test_device_float_primitives(gpu_ctx):
+    """The two non-trivial float primitives, on the device itself: the branch-free square root is the
+    IEEE square root for every float in range (exhaustive, ~1.6e9 values), and the device build of the
+    glibc log10f equals libm's log10f (what aubio's fvec_log10 calls) on 12 M floats across all
+    binades, subnormals and the neighbourhood of 1 included."""
+    import ctypes as C
+    assert gpu_ctx.selftest_sqrt() == 0
+    libm = C.CDLL("libm.so.6")
+    libm.log10f.restype = C.c_float
+    libm.log10f.argtypes = [C.c_float]
+    for first, step, count in ((1, 997, 1_900_000), (1, 3, 4_000_000), (0x3f000000, 5, 3_400_000), (0x3f7fff00, 1, 1024),
+                               (0x00800000 - 2000, 1, 4000), (0x30000000, 389, 2_000_000)):
+        got = gpu_ctx.selftest_log10f(first, step, count)
+        x = (first + np.arange(count, dtype=np.uint64) * step).astype(np.uint32).view(np.float32)
+        idx = np.random.default_rng(first).integers(0, count, 20000)          # libm through ctypes is slow: sample it ...
+        want = np.array([libm.log10f(float(v)) for v in x[idx]], np.float32)
+        assert np.array_equal(got[idx].view(np.uint32), want.view(np.uint32))
+        ref = np.log10(x.astype(np.float64))                                    # ... and bound everything with float64
+        tol = 4.0 * np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64) + 4e-9    # glibc's own accuracy near x = 1
+        assert (np.abs(got.astype(np.float64) - ref) <= tol).all()
+
+
 def test_bad_arguments_are_errors_not_crashes():
     from asterisk_tiresias_b200 import capi
     with pytest.raises(capi.TirError):
