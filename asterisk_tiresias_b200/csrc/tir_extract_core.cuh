@@ -94,8 +94,8 @@ struct TirSmem {
   float4 twu4[C::NW * 8];    // untangle twiddles [role][slot pair]
   double2 logtab[16];
   float2 w2[TIR_MAX_W2];     // mel sweep weights and run lists (copies of TirMelParams::w2 / run_*: a
-  int16_t run_bins[TIR_MAX_RUNS]; // broadcast LDS is much cheaper than an indexed constant-bank load
-  int16_t run_emit[TIR_MAX_RUNS]; // that misses the 2 KB constant cache)
+  int run_bins[TIR_MAX_RUNS];     // broadcast LDS is much cheaper than an indexed constant-bank load
+  int run_emit[TIR_MAX_RUNS];     // that misses the 2 KB constant cache)
 };
 
 #define TIR_XI(N1, plane, k1, n2, f) ((((plane) * (N1) + (k1)) * 16 + (n2)) * 32 + (f))
@@ -299,8 +299,8 @@ TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg,
 // over its bins in ascending order from 0.f; bins where a lane's weight is 0 add +0 (x is finite: a
 // magnitude).  Weights and run lists are read from shared memory (w2, run_*); the parameters of the
 // next run are fetched while the current one accumulates.  Writes the raw sums to lg.
-TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, const float2 *w2, const int16_t *run_bins,
-                           const int16_t *run_emit, int seg, int f, TirP2 nz) {
+TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, const float2 *w2, const int *run_bins,
+                           const int *run_emit, int seg, int f, TirP2 nz) {
   const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
   if (nr == 0) return;
   const float *m = norm + TIR_NORM_IDX(mp.seg_bin0[seg], f);
