@@ -497,7 +497,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = F * BYTES_PER_FRAME / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 530.2 * F,   # ncu dram__bytes_read+write per launch, scaled from profiles/r1_extract_ncu_full_e.txt (530.2 B/frame)
+                "traffic": 530.2 * F,   # ncu dram__bytes_read+write per launch, scaled from profiles/r1_extract_ncu_full_g.txt (530.2 B/frame)
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "tir_extract_kernel<512>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": F * BYTES_PER_FRAME,
                 "note": "issue/latency-bound SIMT kernel on packed f32x2 instructions (float32 FFT reproduced operation for operation; FP32-pipe floor of the DAG = 24.7% of the HBM peak); see DESIGN.md 2.3 and profiles/"}
