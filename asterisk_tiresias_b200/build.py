@@ -74,7 +74,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("building tools/tir_concurrent_bench failed")
     with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
-        f.write("\n".join(log))
+        # registers / spills / shared memory per kernel; compile times would only make the file churn
+        f.write("\n".join(l for l in "\n".join(log).splitlines() if "Compile time" not in l) + "\n")
     if verbose:
         print("\n".join(log))
     return LIB

@@ -381,10 +381,9 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
   a.tile_counter = (uint32_t *)ctx->d_counter.p;
 
   const size_t smem = sizeof(TirSmem<WIN>);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->smem_attr_set) { // per context: the attribute belongs to the device the context is on
     TIR_CUDA(ctx, cudaFuncSetAttribute(tir_extract_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->smem_attr_set = true;
   }
   const uint32_t resident = (uint32_t)ctx->num_sms * (uint32_t)C::CTAS_PER_SM;
   const uint32_t grid = n_tiles < resident ? n_tiles : resident;

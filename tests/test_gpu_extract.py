@@ -142,11 +142,12 @@ def test_device_buffer_entry_point(gpu_ctx, oracle):
 
 
 def test_size_independent_properties_at_scale(gpu_ctx, oracle):
-    """2 000 x 30 s clips (BASELINE config-2 shape, a fifth of its size): the oracle cannot cover it
-    in seconds, so use properties: (i) a clip's frames do not depend on its neighbours or its
-    position in the batch, (ii) sampled clips equal the oracle, (iii) determinism."""
+    """10 000 x 30 s clips (BASELINE config[1] at its full size, 4.8 GB of PCM16): the oracle cannot
+    cover it in seconds, so use properties: (i) a clip's frames do not depend on its neighbours or
+    its position in the batch, (ii) every clip equals the oracle's result for the base clip it
+    repeats, (iii) determinism."""
     import torch
-    n_clips, n = 2000, 240000
+    n_clips, n = 10000, 240000
     base, _ = synth.make_corpus(8, 30.0, first_index=900)
     base = base.reshape(8, n)
     order = np.random.default_rng(0).integers(0, 8, n_clips)

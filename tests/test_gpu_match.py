@@ -210,3 +210,64 @@ def test_shard_merge_equals_unsharded(gpu_ctx, oracle):
         assert np.array_equal(got["match_count"], want["match_count"])
         assert np.array_equal(got["uuid"], want["uuid"])
         assert np.array_equal(got["frame_count"], want["frame_count"])
+
+
+def test_one_million_fingerprints_both_paths_and_brute_force(gpu_ctx):
+    """BASELINE config[2] at its full size (1 M fingerprints x 94 frames, generated on the device): the
+    SQLite oracle cannot ingest that in a test, so (i) the shared-window path (one batched call) and the
+    per-query path (a batch widened past 12 distinct windows by a decoy query) must agree on every
+    query, (ii) a brute-force restatement of the vote in torch confirms sampled queries, (iii) sharding
+    the same table four ways and merging gives the same winners."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n, F, Q = 1_000_000, 94, 64
+    g = torch.Generator(device=dev); g.manual_seed(123)
+    uu = torch.randint(0, 256, (n, 16), dtype=torch.uint8, device=dev, generator=g)
+    v1 = torch.randint(15_500_000, 18_500_000, (n * F,), dtype=torch.int32, device=dev, generator=g)
+    v2 = torch.randint(-5_000_000, 20_000_000, (n * F,), dtype=torch.int32, device=dev, generator=g)
+    off = torch.arange(n + 1, device=dev, dtype=torch.int64) * F
+    torch.cuda.synchronize()
+    gpu_ctx.db_load_dev(n, uu.data_ptr(), off.data_ptr(), v1.data_ptr(), v2.data_ptr(), n * F)
+    y = np.stack([np.random.default_rng(1).uniform(15.5, 18.5, (Q, F)), np.zeros((Q, F))], axis=2)
+    y[:8, :, 0] = (v1.view(n, F)[:8].cpu().numpy() * 1e-6)                     # stored entries as queries
+    foff = np.arange(Q + 1, dtype=np.uint64) * F
+    shared = gpu_ctx.match(y.reshape(-1, 2), foff, 1, 0.001)
+    decoy = np.stack([np.arange(40) - 20.0, np.zeros(40)], axis=1)              # 40 more distinct windows -> per-query path
+    foff2 = np.concatenate([foff, [foff[-1] + 40]]).astype(np.uint64)
+    general = gpu_ctx.match(np.concatenate([y.reshape(-1, 2), decoy]), foff2, 1, 0.001)[:Q]
+    assert np.array_equal(shared["match_count"], general["match_count"]) and np.array_equal(shared["uuid"], general["uuid"])
+    assert (shared["frame_count"] == F).all() and (shared["match_count"] > 0).all()
+    uub = uu.cpu().numpy()
+    order = np.lexsort(uub.T[::-1]); rank_of = np.empty(n, np.int64); rank_of[order] = np.arange(n)
+    rank_t = torch.from_numpy(rank_of).to(dev)
+    for q in (0, 7, 8, Q - 1):
+        ks, w = np.unique(np.trunc(y[q, :, 0]).astype(np.int64), return_counts=True)
+        votes = torch.zeros(n, dtype=torch.int64, device=dev)
+        for k, wk in zip(ks, w):
+            votes += ((v1 >= int(k) * 1_000_000 - 1000) & (v1 <= int(k) * 1_000_000 + 1000)).view(n, F).any(dim=1).to(torch.int64) * int(wk)
+        best = int(votes.max().item())
+        cand = torch.nonzero(votes == best).flatten()
+        win = int(cand[torch.argmax(rank_t[cand])].item())
+        assert shared["match_count"][q] == best and bytes(shared["uuid"][q].tolist()) == bytes(uub[win].tolist())
+    # four shards by uuid, merged
+    shard = np.array([capi.shard_of(u, 4) for u in uub[:200000]])                # (python loop: a 200 k prefix decides the split test)
+    sub_n = 200000
+    ctx_all = capi.Context(device=0)
+    ctx_all.db_load(uub[:sub_n], np.arange(sub_n + 1, dtype=np.uint64) * F, v1[: sub_n * F].cpu().numpy(), v2[: sub_n * F].cpu().numpy())
+    want = ctx_all.match(y.reshape(-1, 2), foff, 1, 0.001)
+    ctx_all.close()
+    gathered = []
+    for s_ in range(4):
+        idx = np.nonzero(shard == s_)[0]
+        rows = (idx[:, None] * F + np.arange(F)[None, :]).reshape(-1)
+        c = capi.Context(device=0)
+        c.db_load(uub[idx], np.arange(idx.size + 1, dtype=np.uint64) * F, v1.cpu().numpy()[rows], v2.cpu().numpy()[rows])
+        gathered.append(c.match(y.reshape(-1, 2), foff, 1, 0.001))
+        c.close()
+    gt = torch.from_numpy(np.concatenate(gathered).view(np.uint8)).cuda()
+    out = torch.zeros(Q * 24, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    gpu_ctx.merge_hits_dev(gt.data_ptr(), 4, Q, out.data_ptr())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(capi.HIT_DTYPE)
+    assert np.array_equal(got["match_count"], want["match_count"]) and np.array_equal(got["uuid"], want["uuid"])
