@@ -34,8 +34,34 @@ struct TirExtractArgs {
 };
 
 __device__ const double2 k_logf_tab[16] = TIR_LOGF_TAB_INIT;
+// Build with -DTIR_TRACE to get clock64 timestamps of the phases of one tile per warp, and the loop
+// cycles of every CTA, printed by the launcher (how the imbalances described in DESIGN.md 2.3 were
+// found; __syncthreads does not block at issue, so a phase's time includes the wait for the barrier
+// before it).  Not compiled into the product.
 #ifdef TIR_TRACE
-__device__ long long g_trace[64];
+__device__ long long g_trace[TIR_MAX_WARPS][8];
+__device__ long long g_trace_cta[2048][3];
+#define TIR_TRACE_DECL() long long tr_[6] = {0, 0, 0, 0, 0, 0}; int tr_iter = 0; const long long tr_loop0 = clock64()
+#define TIR_TRACE_MARK(i) tr_[i] = clock64()
+#define TIR_TRACE_TILE()                                                                     \
+  do {                                                                                       \
+    if (blockIdx.x == 7 && lane == 0 && tr_iter == 100)                                      \
+      for (int k_ = 0; k_ < 6; k_++) g_trace[warp][k_] = tr_[k_];                            \
+    tr_iter++;                                                                               \
+  } while (0)
+#define TIR_TRACE_END()                                                                      \
+  do {                                                                                       \
+    if (tid == 0 && blockIdx.x < 2048) {                                                     \
+      uint32_t smid_;                                                                        \
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                                     \
+      g_trace_cta[blockIdx.x][0] = clock64() - tr_loop0, g_trace_cta[blockIdx.x][1] = tr_iter, g_trace_cta[blockIdx.x][2] = smid_; \
+    }                                                                                        \
+  } while (0)
+#else
+#define TIR_TRACE_DECL() (void)0
+#define TIR_TRACE_MARK(i) (void)0
+#define TIR_TRACE_TILE() (void)0
+#define TIR_TRACE_END() (void)0
 #endif
 
 // tile descriptors from the per-clip prefix arrays (one thread per tile, binary search for its clip)
@@ -183,10 +209,13 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
 
   int b = 0;
   bool first = true;
+  TIR_TRACE_DECL();
   for (;;) {
     uint32_t claim = 0;
     if (have_nxt && tid == 0) claim = atomicAdd(a.tile_counter, 1u) + 2u * gridDim.x; // the tile after nxt; lands under P1
+    TIR_TRACE_MARK(0);
     tir_pass1<WIN>(sm, sm.pcm, warp, lane, nz);
+    TIR_TRACE_MARK(1);
     if (tid == 0) s_claim = claim;
     __syncthreads(); // P1 is done with the PCM buffer
     TirTile nn = nxt;
@@ -199,41 +228,24 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     }
     TirPass2Regs rg;
     tir_pass2_load<WIN>(sm, warp, lane, rg);
+    TIR_TRACE_MARK(2);
     __syncthreads(); // the magnitudes overwrite the exchange buffer
-#ifndef TIR_ABLATE_P2
     if (warp == 0) tir_pass2_compute<WIN, true>(sm, warp, lane, rg, nz);
     else tir_pass2_compute<WIN, false>(sm, warp, lane, rg, nz);
-#else
-    if (rg.X[lane & 15].r.lo == 1234.5f) sm.xch[tid] = rg.X[3].i.hi; // keep the loads alive
-#endif
     __syncthreads();
-#ifdef TIR_TRACE
-    long long tr0 = clock64();
-#endif
-#ifndef TIR_ABLATE_P3
+    TIR_TRACE_MARK(3);
     if (warp < mp.n_coefs && !first) tir_emit_coefs(sm.lg[b ^ 1], mp, a, prev, warp, lane);
     tir_mel_sweep(sm.xch, sm.lg[b], mp, sm.w2, sm.run_bins, sm.run_emit, warp, lane, nz);
-#endif
-#ifdef TIR_TRACE
-    long long tr1 = clock64();
-#endif
+    TIR_TRACE_MARK(4);
     cp_async_wait_all();
     __syncthreads(); // raw mel sums complete; the next tile's PCM has landed
-#ifdef TIR_TRACE
-    long long tr2 = clock64();
-#endif
-#ifndef TIR_ABLATE_P3B
     tir_log_phase<C::NW>(sm.lg[b], sm.logtab, mp, warp, lane);
-#endif
-#ifdef TIR_TRACE
-    if (blockIdx.x == 7 && lane == 0 && tile == blockIdx.x + 5 * gridDim.x) {
-      long long tr3 = clock64();
-      g_trace[warp * 4 + 0] = tr1 - tr0, g_trace[warp * 4 + 1] = tr2 - tr1, g_trace[warp * 4 + 2] = tr3 - tr2, g_trace[warp * 4 + 3] = tr0;
-    }
-#endif
+    TIR_TRACE_MARK(5);
+    TIR_TRACE_TILE();
     if (!have_nxt) break;
     prev = cur, cur = nxt, nxt = nn, have_nxt = have_nn, b ^= 1, first = false;
   }
+  TIR_TRACE_END();
   __syncthreads();
   if (warp < mp.n_coefs) tir_emit_coefs(sm.lg[b], mp, a, cur, warp, lane);
 }
@@ -397,11 +409,16 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
   ctx->launches++;
 #ifdef TIR_TRACE
   {
-    long long h[64];
+    static long long h[TIR_MAX_WARPS][8], hc[2048][3];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpyFromSymbol(h, g_trace, sizeof h);
+    cudaMemcpyFromSymbol(hc, g_trace_cta, sizeof hc);
+    long long mn = 1ll << 60, mx = 0, sum = 0;
+    for (uint32_t i = 0; i < grid && i < 2048; i++) mn = hc[i][0] < mn ? hc[i][0] : mn, mx = hc[i][0] > mx ? hc[i][0] : mx, sum += hc[i][0];
+    fprintf(stderr, "trace: CTA loop cycles min %lld mean %lld max %lld (CTA 7: %lld tiles on SM %lld)\n", mn, sum / (long long)grid, mx, hc[7][1], hc[7][2]);
     for (int w = 0; w < C::NW; w++)
-      fprintf(stderr, "trace warp %2d: P3a %6lld  wait-at-barrier %6lld  P3b %6lld  (start %lld)\n", w, h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3] - h[3]);
+      fprintf(stderr, "trace warp %2d: P1 %6lld | bar+P2load %6lld | bar+P2compute %6lld | bar+P3a %6lld | bar+P3b %6lld\n", w,
+              h[w][1] - h[w][0], h[w][2] - h[w][1], h[w][3] - h[w][2], h[w][4] - h[w][3], h[w][5] - h[w][4]);
   }
 #endif
   return TIR_OK;
