@@ -248,15 +248,11 @@ TIR_DEV void tir_pass2_load(const TirSmem<WIN> &sm, int t, int f, TirPass2Regs &
 // Two untangle slots at a time.  With Z[k] = U = (a, b), Z[M-k] = V = (c, d), k <= M/2:
 //   E2 = (a+c, b-d), O2 = (b+d, c-a), T = W_{2M}^k O2, 2X[k] = E2 + T, 2X[M-k] = conj(E2 - T)
 // -> mk = 2^32 |2X[k]|, mmk = 2^32 |2X[M-k]| (the 2^33 is folded, exactly, into the mel weights).
-// E2 / O2 mix the two rows (U of one lane meets V of the other row), so these eight additions are
-// scalar; everything after them runs on both slots at once.
-TIR_DEV void tir_untangle_mag2(float ulr, float uli, float vlr, float vli, float uhr, float uhi, float vhr, float vhi,
-                               float4 w, TirP2 nz, TirP2 &mk, TirP2 &mmk) {
+// U and V hold the two slots in their lanes.
+TIR_DEV void tir_untangle_mag2(TirC2 U, TirC2 V, float4 w, TirP2 nz, TirP2 &mk, TirP2 &mmk) {
   TirC2 E2, O2;
-  E2.r = tir_pmk(TIR_FADD(ulr, vlr), TIR_FADD(uhr, vhr));
-  E2.i = tir_pmk(TIR_FSUB(uli, vli), TIR_FSUB(uhi, vhi));
-  O2.r = tir_pmk(TIR_FADD(uli, vli), TIR_FADD(uhi, vhi));
-  O2.i = tir_pmk(TIR_FSUB(vlr, ulr), TIR_FSUB(vhr, uhr));
+  E2.r = tir_padd(U.r, V.r), E2.i = tir_psub(U.i, V.i);
+  O2.r = tir_padd(U.i, V.i), O2.i = tir_psub(V.r, U.r);
   const TirC2 Tt = tir_cmul(O2, tir_pmk(w.x, w.y), tir_pmk(w.z, w.w));
   const TirP2 pr = tir_padd(E2.r, Tt.r), pi = tir_padd(E2.i, Tt.i);
   const TirP2 qr = tir_psub(E2.r, Tt.r), qi = tir_psub(E2.i, Tt.i);
@@ -267,6 +263,8 @@ TIR_DEV void tir_untangle_mag2(float ulr, float uli, float vlr, float vli, float
 // T0 = (role == 0): warp-uniform, so the irregular pairing of rows 0 and N1/2 costs no selects.
 //   role t >= 1, slot pair s:  lane lo  k = t + N1 s         U = A[s]    V = B[15-s]
 //                              lane hi  k = (N1-t) + N1 s    U = B[s]    V = A[15-s]
+//     i.e. U = X[s] as it is and V = X[15-s] with its lanes SWAPPED -- a free operand form of the
+//     packed instructions (R.F32x2.LO_HI), so the row-mixing additions are packed too;
 //   role 0:                    lane lo  k = N1 (s+1)         U = A[s+1]  V = A[15-s]   (row 0)
 //                              lane hi  k = N1/2 + N1 s      U = B[s]    V = B[15-s]   (row N1/2)
 //   (role 0, s = 7, lane lo is k = M/2 paired with itself; bins 0 and M are never produced: no mel
@@ -280,12 +278,16 @@ TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg,
 #pragma unroll
   for (int s = 0; s < 8; s++) {
     const TirC2 &Xs = rg.X[s], &Xr = rg.X[15 - s], &Xn = rg.X[s + 1];
+    TirC2 U, V;
+    if (T0) {
+      U.r = tir_pmk(Xn.r.lo, Xs.r.hi), U.i = tir_pmk(Xn.i.lo, Xs.i.hi);
+      V = Xr;
+    } else {
+      U = Xs;
+      V.r = tir_pmk(Xr.r.hi, Xr.r.lo), V.i = tir_pmk(Xr.i.hi, Xr.i.lo);
+    }
     TirP2 mk, mmk;
-    const float4 w = sm.twu4[t * 8 + s];
-    if (T0)
-      tir_untangle_mag2(Xn.r.lo, Xn.i.lo, Xr.r.lo, Xr.i.lo, Xs.r.hi, Xs.i.hi, Xr.r.hi, Xr.i.hi, w, nz, mk, mmk);
-    else
-      tir_untangle_mag2(Xs.r.lo, Xs.i.lo, Xr.r.hi, Xr.i.hi, Xs.r.hi, Xs.i.hi, Xr.r.lo, Xr.i.lo, w, nz, mk, mmk);
+    tir_untangle_mag2(U, V, sm.twu4[t * 8 + s], nz, mk, mmk);
     const int klo = klo0 + C::N1 * s, khi = khi0 + C::N1 * s;
     mags[klo * 32] = mk.lo;
     if (!(T0 && s == 7)) mags[(C::M - klo) * 32] = mmk.lo;
