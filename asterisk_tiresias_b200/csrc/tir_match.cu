@@ -300,19 +300,24 @@ __device__ __forceinline__ bool tir_frame_window(double y1, double y2, const Tir
 // One CTA per query: windows of all frames, identical windows folded into one with a weight
 // (a uuid gets one vote per frame, so frames with the same window vote identically).
 // FROM_COEF: y is recomputed from the float mfcc coefficients as the reference does (:651).
+#define TIR_QPREP_THREADS 128
+#define TIR_QPREP_SMEM_FRAMES 1024 // queries up to this many frames are folded in shared memory
+
 template <bool FROM_COEF>
-__global__ void tir_qprep_kernel(const double *__restrict__ y, const float *__restrict__ coef,
-                                 const uint64_t *__restrict__ frame_off, const TirMatchParams mp,
-                                 TirWindow *__restrict__ windows, uint32_t *__restrict__ n_windows) {
+__global__ void __launch_bounds__(TIR_QPREP_THREADS)
+    tir_qprep_kernel(const double *__restrict__ y, const float *__restrict__ coef, const uint64_t *__restrict__ frame_off,
+                     const TirMatchParams mp, TirWindow *__restrict__ windows, uint32_t *__restrict__ n_windows) {
   TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x;
   const uint64_t f0 = frame_off[q], f1 = frame_off[q + 1];
+  const uint32_t nf = (uint32_t)(f1 - f0);
   TirWindow *wq = windows + f0;
-  __shared__ uint32_t s_count;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  // pass 1: every frame writes its own window (weight 0 = skipped) in place
-  for (uint64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+  __shared__ TirWindow s_w[TIR_QPREP_SMEM_FRAMES];
+  __shared__ uint32_t s_warp[TIR_QPREP_THREADS / 32], s_base;
+  TirWindow *ws = nf <= TIR_QPREP_SMEM_FRAMES ? s_w : wq; // long queries work in place in global memory
+  // pass 1: every frame computes its own window (weight 0 = skipped)
+  for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
+    const uint64_t f = f0 + i;
     double y1, y2;
     if (FROM_COEF) {
       y1 = tir_coef_to_y(coef[f * 2]), y2 = tir_coef_to_y(coef[f * 2 + 1]);
@@ -321,38 +326,55 @@ __global__ void tir_qprep_kernel(const double *__restrict__ y, const float *__re
     }
     TirWindow w;
     if (!tir_frame_window(y1, y2, mp, w)) w.lo1 = 0, w.hi1 = -1, w.lo2 = 0, w.hi2 = -1, w.weight = 0, w.pad = 0;
-    wq[f - f0] = w;
+    ws[i] = w;
   }
+  if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
-  // pass 2: a frame is a leader if no earlier frame has the same window; weight = multiplicity
-  const uint32_t nf = (uint32_t)(f1 - f0);
+  // pass 2: a frame is a leader if no earlier frame has the same window; its weight = the multiplicity
+  // of the window in the query (stashed in .pad, 0 = not a leader)
   for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
-    const TirWindow w = wq[i];
+    const TirWindow w = ws[i];
     uint32_t mult = 0;
     bool leader = w.weight != 0;
-    if (leader) {
-      for (uint32_t j = 0; j < nf; j++) {
-        const TirWindow o = wq[j];
-        const bool same = o.weight != 0 && o.lo1 == w.lo1 && o.hi1 == w.hi1 && o.lo2 == w.lo2 && o.hi2 == w.hi2;
-        if (same && j < i) { leader = false; break; }
-        mult += same;
-      }
+    for (uint32_t j = 0; leader && j < nf; j++) {
+      const TirWindow o = ws[j];
+      const bool same = o.weight != 0 && o.lo1 == w.lo1 && o.hi1 == w.hi1 && o.lo2 == w.lo2 && o.hi2 == w.hi2;
+      if (same && j < i) leader = false;
+      mult += same;
     }
-    wq[i].pad = leader ? mult : 0; // stash, compacted below
+    ws[i].pad = leader ? mult : 0;
   }
   __syncthreads();
-  // pass 3: compact leaders to the front (serial per query; the list is tiny for coefs == 1)
-  if (threadIdx.x == 0) {
-    uint32_t k = 0;
-    for (uint32_t i = 0; i < nf; i++) {
-      TirWindow w = wq[i];
-      if (w.pad) {
-        w.weight = w.pad, w.pad = 0;
-        wq[k++] = w; // k <= i: never overwrites an unread entry
-      }
+  // pass 3: leaders to the front of the query's slice, in frame order (ballot prefix per chunk of
+  // blockDim frames).  In the in-place case a chunk's writes land at indices <= its first frame, which
+  // were consumed by earlier chunks; its own entries are read before the barrier.
+  for (uint32_t c0 = 0; c0 < nf; c0 += blockDim.x) {
+    const uint32_t i = c0 + threadIdx.x;
+    TirWindow w;
+    bool leader = false;
+    if (i < nf) {
+      w = ws[i];
+      leader = w.pad != 0;
     }
-    n_windows[q] = k;
+    const uint32_t bal = __ballot_sync(0xffffffffu, leader);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t pos = s_base + __popc(bal & ((1u << lane) - 1u));
+    for (int k = 0; k < wid; k++) pos += s_warp[k];
+    if (leader) {
+      w.weight = w.pad, w.pad = 0;
+      wq[pos] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = s_base;
+      for (int k = 0; k < TIR_QPREP_THREADS / 32; k++) t += s_warp[k];
+      s_base = t;
+    }
+    __syncthreads();
   }
+  if (threadIdx.x == 0) n_windows[q] = s_base;
 }
 
 // ================================================================================ match kernel
@@ -698,9 +720,9 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   uint32_t *d_maxr = (uint32_t *)(d + o_maxr);
   TirWindow *d_win = (TirWindow *)(d + o_win);
   if (d_coef)
-    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(128), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw));
+    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw));
   else
-    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(128), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw));
+    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw));
   ctx->launches++;
   if (db->n_blocks && db->n_indexed) {
     const int32_t *k1 = (const int32_t *)db->key1.p, *k2 = (const int32_t *)db->key2.p;

@@ -102,6 +102,24 @@ def test_shared_window_and_per_query_paths_agree(gpu_ctx, oracle):
         assert gpu_result(h) == sql_result(sq.search(y, 1, 0.3)), n_int
 
 
+def test_long_queries_fold_in_place(gpu_ctx, oracle):
+    """Queries longer than the 1 024 frames qprep folds in shared memory (a 30 s recording is 938 frames,
+    a minute is 1 875) take the in-place path; short and long queries mixed in one batch."""
+    rng = np.random.default_rng(12)
+    db = synth_db.make_db(500, 10, 40, seed=5)
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    ys = [synth_db.random_y(rng, 1875, near_int_frac=0.5), db[3][1], synth_db.random_y(rng, 1025, null_frac=0.05),
+          synth_db.random_y(rng, 1024), synth_db.random_y(rng, 4000, lo=10.0, hi=30.0)]
+    foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    for coefs, tol in ((1, 0.01), (2, 1.0)):
+        hits = gpu_ctx.match(np.concatenate(ys), foff, coefs, tol)
+        for y, h in zip(ys, hits):
+            assert gpu_result(h) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, y.shape)
+
+
 def test_ties_resolve_to_greatest_uuid(gpu_ctx, oracle):
     # many audios with identical rows, spread over several index blocks (> 16384 uuids)
     n = 40000
