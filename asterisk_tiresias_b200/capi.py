@@ -80,6 +80,18 @@ def lib():
             L.tir_db_load_sqlite.argtypes = [vp, vp, u64p, u64p, u64p]
             L.tir_db_load_sqlite_file.argtypes = [vp, C.c_char_p, u64p, u64p, u64p]
             L.tir_sqlite_insert_fingerprints.argtypes = [vp, vp, C.c_char_p, C.c_char_p, vp, C.c_uint32]
+            L.tir_group_open.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+            L.tir_group_close.argtypes = [vp]
+            L.tir_group_last_error.restype = C.c_char_p
+            L.tir_group_last_error.argtypes = [vp]
+            L.tir_group_size.argtypes = [vp]
+            L.tir_group_ctx.restype = vp
+            L.tir_group_ctx.argtypes = [vp, C.c_int]
+            L.tir_group_db_load.argtypes = [vp, C.c_uint32, vp, u64p, vp, vp]
+            L.tir_group_db_add.argtypes = [vp, vp, vp, vp, C.c_uint32]
+            L.tir_group_db_remove.argtypes = [vp, vp]
+            L.tir_group_db_stats.argtypes = [vp, u64p, u64p]
+            L.tir_group_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
             L.tir_batcher_start.argtypes = [vp, C.c_uint32, C.c_uint32]
             L.tir_batcher_stop.argtypes = [vp]
             L.tir_search_one.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int, vp]
@@ -309,6 +321,67 @@ class Context:
 def shard_of(uuid16, n_shards: int) -> int:
     u = np.ascontiguousarray(uuid16, dtype=np.uint8)
     return int(lib().tir_shard_of(_p(u), n_shards))
+
+
+class Group:
+    """tir_group wrapper: one context per device in this process, table sharded by uuid."""
+
+    def __init__(self, devices, win=512, hop=256, n_filters=40, samplerate=8000):
+        L = lib()
+        cfg = Cfg()
+        L.tir_cfg_default(C.byref(cfg))
+        cfg.win, cfg.hop, cfg.n_filters, cfg.samplerate = win, hop, n_filters, samplerate
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self._g = C.c_void_p()
+        rc = L.tir_group_open(C.byref(cfg), _p(dev), dev.size, C.byref(self._g))
+        if rc != OK:
+            msg = L.tir_group_last_error(self._g).decode() if self._g else "tir_group_open failed"
+            if self._g:
+                L.tir_group_close(self._g)
+            self._g = None
+            raise TirError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_g", None) and _lib is not None:
+            _lib.tir_group_close(self._g)
+        self._g = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise TirError(rc, lib().tir_group_last_error(self._g).decode())
+
+    def db_load(self, uuids, row_off, v1, v2):
+        uuids = np.ascontiguousarray(uuids, dtype=np.uint8).reshape(-1, 16)
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+        v1 = np.ascontiguousarray(v1, dtype=np.int32); v2 = np.ascontiguousarray(v2, dtype=np.int32)
+        self._chk(lib().tir_group_db_load(self._g, uuids.shape[0], _p(uuids), _p(row_off), _p(v1), _p(v2)))
+
+    def db_add(self, uuid, v1, v2):
+        uuid = np.ascontiguousarray(uuid, dtype=np.uint8)
+        v1 = np.ascontiguousarray(v1, dtype=np.int32); v2 = np.ascontiguousarray(v2, dtype=np.int32)
+        self._chk(lib().tir_group_db_add(self._g, _p(uuid), _p(v1), _p(v2), v1.size))
+
+    def db_remove(self, uuid):
+        uuid = np.ascontiguousarray(uuid, dtype=np.uint8)
+        self._chk(lib().tir_group_db_remove(self._g, _p(uuid)))
+
+    def db_stats(self):
+        a, r = C.c_uint64(), C.c_uint64()
+        self._chk(lib().tir_group_db_stats(self._g, C.byref(a), C.byref(r)))
+        return int(a.value), int(r.value)
+
+    def search(self, pcm, clip_off=None, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if clip_off is None:
+            clip_off = np.array([0, pcm.size], np.uint64)
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        nq = clip_off.size - 1
+        hits = np.zeros(nq, HIT_DTYPE)
+        self._chk(lib().tir_group_search(self._g, _p(pcm), _p(clip_off), nq, coefs, float(tolerance), int(freq_ignore_low),
+                                         int(freq_ignore_high), _p(hits)))
+        return hits
 
 
 def sqlite_insert_fingerprints(sqlite3_handle, context, uuid_text, vq):

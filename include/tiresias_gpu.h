@@ -200,6 +200,25 @@ void tir_stream_close(tir_stream *s);
 int tir_merge_hits_dev(tir_ctx *ctx, const tir_hit *d_gathered, uint32_t n_shards, uint32_t n_queries,
                        tir_hit *d_out);
 
+/* The same inside ONE process (an Asterisk module cannot be launched one process per GPU): a group
+ * owns one context per device, shards the table by uuid over them, and a search extracts on the
+ * first device, hands the coefficients to the others over NVLink (cudaMemcpyPeerAsync), matches on
+ * all devices concurrently and folds the per-shard winners -- only 24 bytes per query and shard cross
+ * the links.  Results equal those of one context holding the whole table. */
+typedef struct tir_group tir_group;
+int tir_group_open(const tir_cfg *cfg, const int *devices, int n_devices, tir_group **out); /* cfg->device/stream ignored */
+void tir_group_close(tir_group *g);
+const char *tir_group_last_error(tir_group *g);
+int tir_group_size(tir_group *g);
+tir_ctx *tir_group_ctx(tir_group *g, int i); /* borrowed: e.g. tir_extract on a particular device */
+int tir_group_db_load(tir_group *g, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off,
+                      const int32_t *v1, const int32_t *v2);
+int tir_group_db_add(tir_group *g, const uint8_t uuid[16], const int32_t *v1, const int32_t *v2, uint32_t n_rows);
+int tir_group_db_remove(tir_group *g, const uint8_t uuid[16]);
+int tir_group_db_stats(tir_group *g, uint64_t *n_audio, uint64_t *n_rows);
+int tir_group_search(tir_group *g, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
+                     double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits);
+
 /* which shard (0..n_shards-1) owns a uuid */
 uint32_t tir_shard_of(const uint8_t uuid[16], uint32_t n_shards);
 
