@@ -512,8 +512,16 @@ def main():
         oc, _, ov = plan.extract_batch(h.reshape(-1), np.arange(len(idx) + 1, dtype=np.uint64) * N_SAMP, n_threads=3)
         gc = torch.stack([d_coef.view(n_clips, FRAMES_PER_CLIP, 2)[i] for i in idx]).cpu().numpy().reshape(-1, 2)
         gv = torch.stack([d_vq.view(n_clips, FRAMES_PER_CLIP, 2)[i] for i in idx]).cpu().numpy().reshape(-1, 2)
-        parity = {"clips_checked": len(idx), "coef_bit_identical": float((gc.view(np.uint32) == oc.view(np.uint32)).mean()),
-                  "hash_identical": float((gv == ov).mean())}
+        # the three identity rates SURVEY.md H2 asks for: the exact micro-unit hash, the query side's
+        # trunc(max1), and window membership at the default tolerance (|v1 - k*1e6| <= 1000)
+        k_g, k_o = np.trunc(gv[:, 0] / 1e6), np.trunc(ov[:, 0] / 1e6)
+        in_g = np.abs(gv[:, 0] - np.rint(gv[:, 0] / 1e6) * 1e6) <= 1000
+        in_o = np.abs(ov[:, 0] - np.rint(ov[:, 0] / 1e6) * 1e6) <= 1000
+        relerr = np.abs(gc.astype(np.float64) - oc) / np.maximum(np.abs(oc), 1e-3 * np.abs(oc).max())
+        parity = {"clips_checked": len(idx), "frames_checked": int(gc.shape[0]),
+                  "coef_bit_identical": float((gc.view(np.uint32) == oc.view(np.uint32)).mean()),
+                  "mfcc_max_rel_err": float(relerr.max()), "hash_identical": float((gv == ov).mean()),
+                  "trunc_max1_identical": float((k_g == k_o).mean()), "window_membership_identical": float((in_g == in_o).mean())}
 
     # ---- end to end: host buffers through tir_extract ---------------------------------------
     e2e = None
