@@ -1,6 +1,6 @@
 """Quick GPU probe: extraction parity vs the oracle on a small corpus + a rough kernel timing."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from asterisk_tiresias_b200 import capi, synth

@@ -1,6 +1,6 @@
 """Quick GPU probe: match parity vs the SQLite oracle on random DBs."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from asterisk_tiresias_b200 import capi, synth_db
 from oracle import pyoracle as po
