@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     TIR_TRACE_MARK(4);
     cp_async_wait_all();
     __syncthreads(); // raw mel sums complete; the next tile's PCM has landed
-    tir_log_phase<C::NW>(sm.lg[b], sm.logtab, mp, warp, lane);
+    if (mp.live_prefix) tir_log_phase_prefix<C::NW>(sm.lg[b], sm.logtab, mp.log_clamp, mp.n_live, warp, lane);
+    else tir_log_phase<C::NW>(sm.lg[b], sm.logtab, mp, warp, lane);
     TIR_TRACE_MARK(5);
     TIR_TRACE_TILE();
     if (!have_nxt) break;

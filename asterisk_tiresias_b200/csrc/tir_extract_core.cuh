@@ -54,7 +54,8 @@ struct TirMelParams {
   int8_t run_emit[TIR_MAX_RUNS];    // filter id completed by the run
   uint8_t dead[TIR_MAX_FILTERS];    // filter has no non-zero weight: its log-mel value is lg_dead
   uint8_t live[TIR_MAX_FILTERS];    // ids of the n_live filters that have weights
-  uint8_t pad_[8];
+  uint8_t live_prefix;              // live[i] == i: P3b needs no index table (dead filters lie above Nyquist)
+  uint8_t pad_[7];
   // (w_even[bin], w_odd[bin]) * 2^-33 : aubio weights of the even / odd filter active at a bin of the
   // segment (0 when none); 2^-33 undoes the scaled FFT (2x) and the scaled square root (2^32 x), exactly
   float2 w2[TIR_MAX_W2];
@@ -343,6 +344,26 @@ TIR_DEV void tir_log_phase(float *lg, const double2 *logtab, const TirMelParams 
 #pragma unroll
   for (int q = 0; q < Q; q++)
     if (at[q] >= 0) lg[at[q]] = v[q];
+}
+
+// the same when the live filters are 0..n_live-1 (every plan of the reference: only filters above
+// Nyquist are empty): the addresses are lane + immediate, no constant-bank index loads
+template <int NW>
+TIR_DEV void tir_log_phase_prefix(float *lg, const double2 *logtab, float log_clamp, int n_live, int w, int f) {
+  constexpr int Q = (TIR_MAX_FILTERS + NW - 1) / NW;
+  float *p = lg + w * 32 + f;
+  float v[Q];
+  bool on[Q];
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    on[q] = w + NW * q < n_live;
+    v[q] = on[q] ? p[q * NW * 32] : 1.f;
+  }
+#pragma unroll
+  for (int q = 0; q < Q; q++) v[q] = tir_log10f_glibc(fmaxf(v[q], log_clamp), logtab);
+#pragma unroll
+  for (int q = 0; q < Q; q++)
+    if (on[q]) p[q * NW * 32] = v[q];
 }
 
 // ---- P4 ---------------------------------------------------------------------------------------

@@ -179,7 +179,8 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
     for (size_t j = i + 1; j < live.size(); j++)
       if (((live[i] ^ live[j]) & 1) == 0 && first[live[j]] <= last[live[i]]) return false;
   mp.n_live = (int)live.size();
-  for (size_t i = 0; i < live.size(); i++) mp.live[i] = (uint8_t)live[i];
+  mp.live_prefix = 1;
+  for (size_t i = 0; i < live.size(); i++) mp.live[i] = (uint8_t)live[i], mp.live_prefix &= live[i] == (int)i;
   // contiguous segments of live filters, one per warp, balanced on issue slots (measured with ncu:
   // 5.25 per bin, 26 per filter, 20 per segment); the n_coefs coefficient warps first run the DCT
   // of the previous tile (clock64 trace: worth about 270 slots), so their segments are smaller

@@ -12,6 +12,9 @@
 #include "../../asterisk_tiresias_b200/csrc/tir_extract_core.cuh"
 #include "../../asterisk_tiresias_b200/csrc/tir_tables.h"
 
+static bool force_indexed_logs = false; // exercise the table-indexed P3b on plans that would take the prefix path
+extern "C" void emul_force_indexed_logs(int on) { force_indexed_logs = on != 0; }
+
 template <int WIN>
 static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate, float *coef, int32_t *vq) {
   using C = TirCfg<WIN>;
@@ -61,7 +64,11 @@ static int emul_extract_t(const int16_t *pcm, uint64_t n_samples, int samplerate
     for (int w = 0; w < C::NW; w++)
       for (int lane = 0; lane < 32; lane++) tir_mel_sweep(sm->xch, sm->lg[b], tab.mel, sm->w2, sm->run_bins, sm->run_emit, w, lane, nz);
     for (int w = 0; w < C::NW; w++)
-      for (int lane = 0; lane < 32; lane++) tir_log_phase<C::NW>(sm->lg[b], sm->logtab, tab.mel, w, lane);
+      for (int lane = 0; lane < 32; lane++) {
+        if (tab.mel.live_prefix && !force_indexed_logs)
+          tir_log_phase_prefix<C::NW>(sm->lg[b], sm->logtab, tab.mel.log_clamp, tab.mel.n_live, w, lane);
+        else tir_log_phase<C::NW>(sm->lg[b], sm->logtab, tab.mel, w, lane);
+      }
     for (int j = 0; j < 2; j++)
       for (int lane = 0; lane < nvalid; lane++) {
         float c;

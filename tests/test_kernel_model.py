@@ -54,6 +54,23 @@ def test_kernel_phases_other_plans(oracle, emul, win, sr, idx, kind, sec):
     assert np.array_equal(vq, v2)
 
 
+def test_both_log_phase_variants_match_oracle(oracle, emul):
+    """P3b has two address schemes (live filters 0..n-1: immediates; otherwise an index table); every
+    plan of the reference takes the first, so the second is forced here."""
+    p = oracle.Plan()
+    pcm = synth.make_clip(3, 2.0, kind="composite")
+    co, y, vq = p.extract(pcm)
+    F = co.shape[0]
+    try:
+        for forced in (1, 0):
+            emul.emul_force_indexed_logs(forced)
+            c2 = np.zeros((F, 2), np.float32); v2 = np.zeros((F, 2), np.int32)
+            assert emul.emul_extract(pcm.ctypes.data, pcm.size, 8000, c2.ctypes.data, v2.ctypes.data) == 0
+            assert np.array_equal(co.view(np.uint32), c2.view(np.uint32)) and np.array_equal(vq, v2)
+    finally:
+        emul.emul_force_indexed_logs(0)
+
+
 def test_log10f_model_equals_libm(emul):
     # strided sweep over every binade of the positive floats incl. subnormals (the exhaustive
     # 2^31 sweep was run once: 0 mismatches, see DESIGN.md)
