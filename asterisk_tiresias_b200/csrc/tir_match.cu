@@ -413,14 +413,24 @@ __device__ __forceinline__ uint64_t tir_warp_bound(const int32_t *__restrict__ k
 // pattern", and each query then only weighs the patterns:
 //     match_count(q, uuid) = sum_k weight(q, k) * [bit k of pattern(uuid)]
 // -- the same votes, the same winner and tie rule as the per-query path, for a cost that is
-// independent of the number of queries.  Batches with more than TIR_MAX_SHARED distinct windows
-// (coefs == 2: the max2 bounds are real numbers) take the per-query kernel below; the choice is
-// made on the device (TirBatch::use_general), nothing is read back.
-#define TIR_MAX_SHARED 12
+// independent of the number of queries.  "Greatest rank per pattern" lives in a direct table for up
+// to TIR_SHARED_DIRECT windows (2^12 patterns; synthetic audio and most telephone speech: max1 is
+// 10*log10|c0|, a handful of integers) and in a hash table for up to TIR_MAX_SHARED windows (a batch
+// of recordings of very different loudness): the patterns that OCCUR are few, whatever their width.
+// Batches with more distinct windows (coefs == 2: the max2 bounds are real numbers), or more
+// occurring patterns than the hash table holds, take the per-query kernel below; the choice is made
+// on the device (TirBatch::use_general), nothing is read back.
+#define TIR_SHARED_DIRECT 12
+#define TIR_MAX_SHARED 32
+#define TIR_PAT_HASH_CTA 2048     // slots of a CTA's table (16 KB, the size of the direct table)
+#define TIR_PAT_HASH_GLOBAL 16384 // slots of the batch's table
 struct TirBatch {
   uint32_t n_distinct, use_general;
+  uint32_t n_patterns; // hashed mode: occupied slots of the batch's table (listed in pat_list)
+  uint32_t overflow;   // hashed mode: a pattern table filled up -> per-query path (set by the reduce kernel)
   TirWindow distinct[TIR_MAX_SHARED];
 };
+__device__ __forceinline__ uint32_t tir_pat_hash(uint32_t p) { return (p * 0x9e3779b1u) >> 7; }
 
 // one CTA: distinct windows of the whole batch; every folded window learns its bit (TirWindow::pad).
 // Rounds: every thread walks its queries' windows while they are in the list; the lowest thread
@@ -468,19 +478,22 @@ __global__ void __launch_bounds__(1024)
   if (tid == 0) batch->n_distinct = over ? 0 : n, batch->use_general = over ? 1u : 0u;
 }
 
-// grid (n_blocks, TIR_MAX_SHARED): rows of distinct window k in index block blk -> pattern bits
+// grid (n_blocks, TIR_SHARED_DIRECT): rows of distinct window k (k += gridDim.y) in index block blk -> pattern bits
 template <int COEFS>
 __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_pattern_scan_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
                             const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
                             const TirBatch *__restrict__ batch, uint32_t *__restrict__ pattern) {
   TIR_PDL_PROLOGUE();
-  const uint32_t blk = blockIdx.x, k = blockIdx.y;
-  if (batch->use_general || k >= batch->n_distinct) return;
+  const uint32_t blk = blockIdx.x;
+  if (batch->use_general || blockIdx.y >= batch->n_distinct) return;
   __shared__ uint64_t s_range[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t bs = block_start[blk], be = block_start[blk + 1];
   if (bs == be) return;
+  const uint32_t K = batch->n_distinct;
+  for (uint32_t k = blockIdx.y; k < K; k += gridDim.y) {
+  if (k != blockIdx.y) __syncthreads(); // s_range of the previous window has been read
   const TirWindow w = batch->distinct[k];
   if (warp == 0) {
     const uint64_t r = tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
@@ -499,45 +512,99 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     }
     atomicOr(pat + __ldg(uid + r), 1u << k); // group by audio_uuid: a bit, not a count
   }
+  } // k
 }
 
 // greatest rank (+1) per pattern; clears the patterns for the next batch.  Warp-aggregated through
-// a shared-memory table, one global atomicMax per CTA and occupied pattern.
+// a shared-memory table, one global atomicMax per CTA and occupied pattern.  Up to TIR_SHARED_DIRECT
+// windows the pattern is the table index; beyond, both tables are open-addressing hash tables keyed
+// by the pattern (0 = empty: the zero pattern is never inserted), and a pattern new to the batch's
+// table is appended to pat_list.  A table that fills up sends the batch to the per-query path.
+__device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, uint32_t mask, uint32_t p, uint32_t rank1,
+                                               uint32_t *slot_out, bool *is_new) {
+  uint32_t h = tir_pat_hash(p) & mask;
+  for (uint32_t probe = 0; probe <= mask; probe++, h = (h + 1) & mask) {
+    uint32_t cur = keys[h];
+    if (cur == 0) cur = atomicCAS(&keys[h], 0u, p);
+    if (cur == 0 || cur == p) {
+      atomicMax(&vals[h], rank1);
+      if (slot_out) *slot_out = h;
+      if (is_new) *is_new = cur == 0;
+      return true;
+    }
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(256)
-    tir_pattern_reduce_kernel(uint32_t *__restrict__ pattern, uint32_t n_audio, const TirBatch *__restrict__ batch,
-                              uint32_t *__restrict__ max_rank1) {
+    tir_pattern_reduce_kernel(uint32_t *__restrict__ pattern, uint32_t n_audio, TirBatch *__restrict__ batch,
+                              uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys, uint32_t *__restrict__ g_vals,
+                              uint32_t *__restrict__ pat_list) {
   TIR_PDL_PROLOGUE();
   if (batch->use_general || batch->n_distinct == 0) return;
-  __shared__ uint32_t s_max[1 << TIR_MAX_SHARED];
-  for (int i = threadIdx.x; i < (1 << TIR_MAX_SHARED); i += blockDim.x) s_max[i] = 0;
+  const bool hashed = batch->n_distinct > TIR_SHARED_DIRECT;
+  __shared__ uint32_t s_tab[1 << TIR_SHARED_DIRECT]; // direct: max rank by pattern; hashed: keys | values
+  __shared__ uint32_t s_full;
+  static_assert(2 * TIR_PAT_HASH_CTA == (1 << TIR_SHARED_DIRECT), "the two uses share one table");
+  uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
+  for (int i = threadIdx.x; i < (1 << TIR_SHARED_DIRECT); i += blockDim.x) s_tab[i] = 0;
+  if (threadIdx.x == 0) s_full = 0;
   __syncthreads();
   const uint32_t n4 = (n_audio + 3) / 4; // the buffer is padded to whole uint4
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     uint4 p = reinterpret_cast<uint4 *>(pattern)[i];
     if (p.x | p.y | p.z | p.w) {
-      if (p.x) atomicMax(&s_max[p.x], 4 * i + 1);
-      if (p.y) atomicMax(&s_max[p.y], 4 * i + 2);
-      if (p.z) atomicMax(&s_max[p.z], 4 * i + 3);
-      if (p.w) atomicMax(&s_max[p.w], 4 * i + 4);
-      reinterpret_cast<uint4 *>(pattern)[i] = make_uint4(0, 0, 0, 0);
+      if (!hashed) {
+        if (p.x) atomicMax(&s_tab[p.x], 4 * i + 1);
+        if (p.y) atomicMax(&s_tab[p.y], 4 * i + 2);
+        if (p.z) atomicMax(&s_tab[p.z], 4 * i + 3);
+        if (p.w) atomicMax(&s_tab[p.w], 4 * i + 4);
+      } else {
+        bool ok = true;
+        if (p.x) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.x, 4 * i + 1, nullptr, nullptr);
+        if (p.y) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.y, 4 * i + 2, nullptr, nullptr);
+        if (p.z) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.z, 4 * i + 3, nullptr, nullptr);
+        if (p.w) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.w, 4 * i + 4, nullptr, nullptr);
+        if (!ok) s_full = 1;
+      }
+      reinterpret_cast<uint4 *>(pattern)[i] = make_uint4(0, 0, 0, 0); // (also when a table is full: the next batch starts clean)
     }
   }
   __syncthreads();
-  const uint32_t np = 1u << batch->n_distinct;
-  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
-    if (s_max[i]) atomicMax(max_rank1 + i, s_max[i]);
+  if (!hashed) {
+    const uint32_t np = 1u << batch->n_distinct;
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
+      if (s_tab[i]) atomicMax(max_rank1 + i, s_tab[i]);
+    return;
+  }
+  bool full = s_full != 0;
+  for (uint32_t i = threadIdx.x; i < TIR_PAT_HASH_CTA && !full; i += blockDim.x) {
+    const uint32_t p = s_keys[i];
+    if (!p) continue;
+    uint32_t slot;
+    bool is_new;
+    if (!tir_pat_insert(g_keys, g_vals, TIR_PAT_HASH_GLOBAL - 1, p, s_vals[i], &slot, &is_new)) full = true;
+    else if (is_new) {
+      const uint32_t at = atomicAdd(&batch->n_patterns, 1u);
+      if (at < TIR_PAT_HASH_GLOBAL / 2) pat_list[at] = slot;
+      else full = true; // keep the table at most half full
+    }
+  }
+  if (full) atomicExch(&batch->overflow, 1u); // the per-query kernel (launched after the resolve) takes the batch
 }
 
-// one warp per query: weigh the occupied patterns
+// one warp per query: weigh the occupied patterns (direct: every table index; hashed: pat_list)
 __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
                                            const uint64_t *__restrict__ frame_off, uint32_t n_queries,
                                            const TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
-                                           unsigned long long *__restrict__ best) {
+                                           const uint32_t *__restrict__ g_keys, const uint32_t *__restrict__ g_vals,
+                                           const uint32_t *__restrict__ pat_list, unsigned long long *__restrict__ best) {
   TIR_PDL_PROLOGUE();
-  if (batch->use_general) return;
+  if (batch->use_general || batch->overflow) return;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= n_queries) return;
   const uint32_t K = batch->n_distinct, nw = n_windows[q];
+  const bool hashed = K > TIR_SHARED_DIRECT;
   const TirWindow *wq = windows + frame_off[q];
   uint32_t wk = 0; // lane k holds weight(q, k)
   for (uint32_t i = 0; i < nw; i++) {
@@ -545,10 +612,18 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
     if (w.pad == lane) wk += w.weight;
   }
   unsigned long long bestv = 0;
-  const uint32_t np = K ? (1u << K) : 0;
+  const uint32_t np = hashed ? batch->n_patterns : (K ? (1u << K) : 0);
   for (uint32_t p0 = 0; p0 < np; p0 += 32) {
-    const uint32_t p = p0 + lane;
-    const uint32_t r1 = p < np ? __ldg(max_rank1 + p) : 0;
+    const uint32_t i = p0 + lane;
+    uint32_t p = i, r1 = 0;
+    if (i < np) {
+      if (hashed) {
+        const uint32_t slot = __ldg(pat_list + i);
+        p = g_keys[slot], r1 = g_vals[slot];
+      } else {
+        r1 = __ldg(max_rank1 + i);
+      }
+    }
     uint32_t score = 0;
     for (uint32_t k = 0; k < K; k++) {
       const uint32_t w = __shfl_sync(0xffffffffu, wk, k);
@@ -570,7 +645,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
                      const TirBatch *__restrict__ batch) {
   TIR_PDL_PROLOGUE();
-  if (!batch->use_general) return;
+  if (!(batch->use_general || batch->overflow)) return;
   __shared__ uint32_t s_cnt[TIR_BLOCK_UUIDS / 2];  // u16 vote counters, two per word
   __shared__ uint32_t s_seen[TIR_BLOCK_UUIDS / 32]; // per-window "uuid already voted" bits
   __shared__ uint64_t s_range[2];
@@ -692,11 +767,13 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   for (uint32_t q = 0; q < n_queries; q++)
     if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 65535)
       return tir_fail(ctx, TIR_ERR_ARG, "a query may have at most 65535 frames (u16 vote counters)");
-  // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | windows
+  // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | pattern hash keys | values | pattern list | windows
   const size_t o_foff = 0, o_nw = o_foff + ((size_t)n_queries + 1) * 8, o_best = (o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
   const size_t o_batch = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
   const size_t o_maxr = (o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
-  const size_t o_win = o_maxr + ((size_t)4 << TIR_MAX_SHARED);
+  const size_t o_gkeys = o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), o_gvals = o_gkeys + (size_t)4 * TIR_PAT_HASH_GLOBAL;
+  const size_t o_plist = o_gvals + (size_t)4 * TIR_PAT_HASH_GLOBAL; // (first bytes that need no clearing)
+  const size_t o_win = o_plist + (size_t)4 * TIR_PAT_HASH_GLOBAL;
   const size_t bytes = o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
   if ((rc = tir_reserve(ctx, ctx->d_qmeta, bytes))) return rc;
   unsigned char *d = (unsigned char *)ctx->d_qmeta.p;
@@ -706,7 +783,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   std::memcpy(hp, frame_off, ((size_t)n_queries + 1) * 8);
   TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, hp, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
   if ((rc = tir_stage_release(ctx, slot))) return rc;
-  TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_win - o_best, st)); // best, batch, max_rank1
+  TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_plist - o_best, st)); // best, batch, max_rank1, pattern hash table
   TirMatchParams mp;
   mp.coefs = coefs;
   mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
@@ -717,7 +794,8 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
   unsigned long long *d_best = (unsigned long long *)(d + o_best);
   TirBatch *d_batch = (TirBatch *)(d + o_batch);
-  uint32_t *d_maxr = (uint32_t *)(d + o_maxr);
+  uint32_t *d_maxr = (uint32_t *)(d + o_maxr), *d_gkeys = (uint32_t *)(d + o_gkeys), *d_gvals = (uint32_t *)(d + o_gvals);
+  uint32_t *d_plist = (uint32_t *)(d + o_plist);
   TirWindow *d_win = (TirWindow *)(d + o_win);
   if (d_coef)
     TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw));
@@ -733,13 +811,14 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     TIR_CUDA(ctx, tir_launch_pdl(tir_batch_windows_kernel, dim3(1), dim3(1024), st, d_win, (const uint32_t *)d_nw, d_foff, n_queries, d_batch));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
-    const dim3 pgrid(db->n_blocks, TIR_MAX_SHARED);
+    const dim3 pgrid(db->n_blocks, TIR_SHARED_DIRECT);
     if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_scan_kernel<2>, pgrid, dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirBatch *)d_batch, pat));
     else TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_scan_kernel<1>, pgrid, dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirBatch *)d_batch, pat));
     const uint32_t rgrid = std::min<uint32_t>((n_ranks / 4 + 255) / 256, (uint32_t)ctx->num_sms * 4);
-    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_reduce_kernel, dim3(rgrid), dim3(256), st, pat, n_ranks, (const TirBatch *)d_batch, d_maxr));
+    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_reduce_kernel, dim3(rgrid), dim3(256), st, pat, n_ranks, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
     TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
-                                 (const uint32_t *)d_nw, d_foff, n_queries, (const TirBatch *)d_batch, (const uint32_t *)d_maxr, d_best));
+                                 (const uint32_t *)d_nw, d_foff, n_queries, (const TirBatch *)d_batch, (const uint32_t *)d_maxr,
+                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, d_best));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 6);

@@ -95,11 +95,57 @@ def test_shared_window_and_per_query_paths_agree(gpu_ctx, oracle):
             assert gpu_result(single) == gpu_result(batch[qi]), (coefs, tol, qi)
             if qi % 3 == 0 and y.shape[0]:
                 assert gpu_result(batch[qi]) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, qi)
-    # exactly TIR_MAX_SHARED (12) and 13 distinct windows in one batch
-    for n_int in (12, 13):
-        y = np.stack([np.arange(n_int) + 10.2, np.zeros(n_int)], axis=1)
+    # the table boundaries: 12 distinct windows (direct pattern table), 13 and 32 (hashed), 33 (per-query)
+    for n_int in (12, 13, 32, 33):
+        y = np.stack([np.arange(n_int) - 5 + 0.2, np.zeros(n_int)], axis=1)
         h = gpu_ctx.match(y, None, 1, 0.3)[0]
         assert gpu_result(h) == sql_result(sq.search(y, 1, 0.3)), n_int
+
+
+def test_hashed_pattern_tables(gpu_ctx, oracle):
+    """13..32 distinct windows in a batch (recordings of very different loudness): the shared-window
+    path keeps 'greatest rank per pattern' in hash tables.  (a) a batch of 24 windows against singles
+    and SQLite; (b) wide windows over a DB whose audios carry ~20 000 different bit patterns: the
+    batch's table (8 192 patterns) fills up and the batch is handed to the per-query kernel on the
+    device -- same answers."""
+    rng = np.random.default_rng(77)
+    db = synth_db.make_db(6000, 4, 24, seed=91, lo=-6.0, hi=26.0, near_int_frac=0.7)
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    ys = []
+    for qi in range(48):
+        base = -4 + (qi * 5) % 22  # all queries together: integers -4 .. 19 -> 24 windows
+        ys.append(synth_db.random_y(rng, int(rng.integers(2, 60)), lo=base, hi=base + 1.99, near_int_frac=0.7))
+    ys.append(db[123][1].copy())
+    foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    ints = {int(v) for y in ys for v in np.trunc(y[:, 0])}
+    assert 13 <= len(ints) <= 32, len(ints)
+    for tol in (0.001, 0.05):
+        batch = gpu_ctx.match(np.concatenate(ys), foff, 1, tol)
+        for qi, y in enumerate(ys):
+            assert gpu_result(gpu_ctx.match(y, None, 1, tol)[0]) == gpu_result(batch[qi]), (tol, qi)
+            if qi % 4 == 0:
+                assert gpu_result(batch[qi]) == sql_result(sq.search(y, 1, tol, has_y=np.isfinite(y))), (tol, qi)
+    # (b) every row lies in some window (tol 0.5 around every integer the DB uses): patterns are dense
+    db2 = synth_db.make_db(20000, 6, 14, seed=92, lo=0.0, hi=19.99)
+    sq2 = oracle.SqliteDB()
+    for u, y in db2[:3000]:
+        sq2.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db2))
+    y_all = np.stack([np.arange(20) + 0.5, np.zeros(20)], axis=1)             # 20 windows, all occupied
+    qs = [y_all, y_all[:14], db2[5][1].copy(), np.concatenate([y_all, y_all[3:9]])]
+    foff = np.zeros(len(qs) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in qs])
+    batch = gpu_ctx.match(np.concatenate(qs), foff, 1, 0.5)
+    for qi, y in enumerate(qs):
+        single = gpu_ctx.match(y, None, 1, 0.5)[0]
+        assert gpu_result(single) == gpu_result(batch[qi]), qi
+    # and against SQLite on the first 3 000 audios
+    gpu_ctx.db_load(*synth_db.db_arrays(db2[:3000]))
+    batch = gpu_ctx.match(np.concatenate(qs), foff, 1, 0.5)
+    for qi, y in enumerate(qs):
+        assert gpu_result(batch[qi]) == sql_result(sq2.search(y, 1, 0.5)), qi
 
 
 def test_long_queries_fold_in_place(gpu_ctx, oracle):
