@@ -40,14 +40,19 @@
   asm volatile("griddepcontrol.wait;" ::: "memory")
 
 template <typename... KArgs, typename... Args>
-static cudaError_t tir_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+static cudaError_t tir_launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = 0, cfg.stream = st;
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t tir_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  return tir_launch_pdl_smem(kernel, grid, block, 0, st, args...);
 }
 
 #define TIR_BLOCK_UUIDS 16384 // uuids per index block: u16 local ids, 32 KB of u16 vote counters
@@ -87,13 +92,12 @@ struct TirDb {
   uint32_t n_blocks = 0;
   uint64_t n_indexed = 0;
   DevBuf order, key1, uid, key2, block_start;
-  DevBuf pattern; // u32 per uuid rank: windows of the current batch that hold a row of it (all zero between batches)
 };
 
 void tir_db_destroy(TirDb *db) {
   if (!db) return;
   for (DevBuf *b : {&db->uuids, &db->row_off, &db->v1, &db->v2, &db->alive, &db->order, &db->key1, &db->uid, &db->key2,
-                    &db->block_start, &db->pattern})
+                    &db->block_start})
     if (b->p) cudaFree(b->p);
   delete db;
 }
@@ -193,9 +197,6 @@ static int db_build_index(tir_ctx *ctx, TirDb *db) {
   int rc;
   if ((rc = tir_reserve(ctx, db->order, (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
   if ((rc = tir_reserve(ctx, db->block_start, ((size_t)db->n_blocks + 1) * 8))) return rc;
-  const size_t pat_bytes = ((size_t)db->n_blocks * TIR_BLOCK_UUIDS + 16) * 4; // whole blocks, whole uint4
-  if ((rc = tir_reserve(ctx, db->pattern, pat_bytes))) return rc;
-  TIR_CUDA(ctx, cudaMemsetAsync(db->pattern.p, 0, pat_bytes, st));
   if (n == 0 || rows == 0) {
     TIR_CUDA(ctx, cudaMemsetAsync(db->block_start.p, 0, ((size_t)db->n_blocks + 1) * 8, st));
     db->dirty = false;
@@ -297,6 +298,75 @@ __device__ __forceinline__ bool tir_frame_window(double y1, double y2, const Tir
   return true;
 }
 
+// ---- shared-window path -------------------------------------------------------------------------
+// The query side truncates max1 to an integer (src/fp_handler.c:290), so with coefs == 1 all the
+// frames of all the queries of a batch probe a handful of DISTINCT windows (one per integer value of
+// max1 that occurs).  "uuid has a row in window k" does not depend on the query, so the batch scans
+// every distinct window ONCE, leaves a bit pattern per uuid, reduces "greatest uuid rank per
+// pattern", and each query then only weighs the patterns:
+//     match_count(q, uuid) = sum_k weight(q, k) * [bit k of pattern(uuid)]
+// -- the same votes, the same winner and tie rule as the per-query path, for a cost that is
+// independent of the number of queries.  "Greatest rank per pattern" lives in a direct table for up
+// to TIR_SHARED_DIRECT windows (2^11 patterns; synthetic audio and most telephone speech: max1 is
+// 10*log10|c0|, a handful of integers) and in a hash table for up to TIR_MAX_SHARED windows (a batch
+// of recordings of very different loudness): the patterns that OCCUR are few, whatever their width.
+// Batches with more distinct windows (coefs == 2: the max2 bounds are real numbers), or more
+// occurring patterns than the hash table holds, take the per-query kernel below; the choice is made
+// on the device (TirBatch::use_general), nothing is read back.
+#define TIR_SHARED_DIRECT 11
+#define TIR_MAX_SHARED 32
+#define TIR_PAT_HASH_CTA 1024     // slots of a CTA's table (8 KB, the size of the direct table)
+#define TIR_PAT_HASH_GLOBAL 16384 // slots of the batch's table
+#define TIR_WSET_SLOTS 64 // window set of the batch (open addressing; > TIR_MAX_SHARED so that probes stay short)
+struct TirBatch {
+  uint32_t n_distinct, use_general; // published by the last qprep CTA (use_general also by an inserter that finds the set full)
+  uint32_t n_patterns; // hashed mode: occupied slots of the batch's table (listed in pat_list)
+  uint32_t overflow;   // a pattern table filled up, or two windows shared a 64-bit key -> per-query path
+  uint32_t done, pad_[3];                  // qprep CTAs that have finished
+  unsigned long long wkey[TIR_WSET_SLOTS]; // 0 = free, else the 64-bit key of the window that claimed the slot
+  TirWindow wfull[TIR_WSET_SLOTS];         // ... and the window itself (written by the claimer)
+  uint32_t wbit[TIR_WSET_SLOTS];           // slot -> bit of the window in the patterns
+  TirWindow distinct[TIR_MAX_SHARED];      // bit -> window
+};
+
+// The distinct windows of a batch are collected while the queries are prepared: every leader window
+// of every query is inserted into TirBatch::wkey (atomicCAS on a 64-bit key of its four bounds) and
+// remembers its slot; the LAST qprep CTA to finish numbers the occupied slots (= pattern bits) and
+// publishes the compact list.  No extra kernel, no read-back.  Two different windows with the same
+// 64-bit key would share a slot: the resolve kernel compares every window with the one its bit
+// stands for and sends the batch to the per-query path if they differ (never observed; it keeps
+// the result exact regardless of the hash).
+__device__ __forceinline__ unsigned long long tir_window_key(const TirWindow &w) {
+  unsigned long long k = ((unsigned long long)(uint32_t)w.lo1 << 32) | (uint32_t)w.hi1;
+  unsigned long long m = ((unsigned long long)(uint32_t)w.lo2 << 32) | (uint32_t)w.hi2;
+  m ^= 0x800000007fffffffull; // "no predicate on max2" (INT32_MIN, INT32_MAX) -> 0: coefs == 1 keys are exact
+  k ^= m * 0x9e3779b97f4a7c15ull;
+  k ^= (m >> 29);
+  return k ? k : 1ull;
+}
+__device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w) {
+  const unsigned long long key = tir_window_key(w);
+  uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 58); // 6 bits
+  for (int probe = 0; probe < TIR_WSET_SLOTS; probe++, h = (h + 1) & (TIR_WSET_SLOTS - 1)) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&batch->wkey[h]);
+    if (cur == 0) {
+      cur = atomicCAS(&batch->wkey[h], 0ull, key);
+      if (cur == 0) { // claimed: publish the window (read after this grid has completed, or by its last CTA)
+        TirWindow f = w;
+        f.weight = 1, f.pad = 0;
+        batch->wfull[h] = f;
+        return h;
+      }
+    }
+    if (cur == key) return h;
+  }
+  atomicExch(&batch->use_general, 1u); // more than TIR_WSET_SLOTS distinct windows
+  return 0;
+}
+
+__device__ __forceinline__ uint32_t tir_pat_hash(uint32_t p) { return (p * 0x9e3779b1u) >> 7; }
+
+
 // One CTA per query: windows of all frames, identical windows folded into one with a weight
 // (a uuid gets one vote per frame, so frames with the same window vote identically).
 // FROM_COEF: y is recomputed from the float mfcc coefficients as the reference does (:651).
@@ -306,14 +376,15 @@ __device__ __forceinline__ bool tir_frame_window(double y1, double y2, const Tir
 template <bool FROM_COEF>
 __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     tir_qprep_kernel(const double *__restrict__ y, const float *__restrict__ coef, const uint64_t *__restrict__ frame_off,
-                     const TirMatchParams mp, TirWindow *__restrict__ windows, uint32_t *__restrict__ n_windows) {
+                     const TirMatchParams mp, TirWindow *__restrict__ windows, uint32_t *__restrict__ n_windows,
+                     TirBatch *__restrict__ batch) {
   TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x;
   const uint64_t f0 = frame_off[q], f1 = frame_off[q + 1];
   const uint32_t nf = (uint32_t)(f1 - f0);
   TirWindow *wq = windows + f0;
   __shared__ TirWindow s_w[TIR_QPREP_SMEM_FRAMES];
-  __shared__ uint32_t s_warp[TIR_QPREP_THREADS / 32], s_base;
+  __shared__ uint32_t s_warp[TIR_QPREP_THREADS / 32], s_base, s_last;
   TirWindow *ws = nf <= TIR_QPREP_SMEM_FRAMES ? s_w : wq; // long queries work in place in global memory
   // pass 1: every frame computes its own window (weight 0 = skipped)
   for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
@@ -363,7 +434,8 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     uint32_t pos = s_base + __popc(bal & ((1u << lane) - 1u));
     for (int k = 0; k < wid; k++) pos += s_warp[k];
     if (leader) {
-      w.weight = w.pad, w.pad = 0;
+      w.weight = w.pad;
+      w.pad = tir_wset_insert(batch, w); // slot in the batch's window set
       wq[pos] = w;
     }
     __syncthreads();
@@ -375,6 +447,35 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     __syncthreads();
   }
   if (threadIdx.x == 0) n_windows[q] = s_base;
+  // the last CTA to finish numbers the occupied slots of the window set
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&batch->done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < TIR_WSET_SLOTS) { // two warps
+    const int slot = threadIdx.x, lane = slot & 31;
+    const bool occ = *reinterpret_cast<volatile unsigned long long *>(&batch->wkey[slot]) != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) s_warp[slot >> 5] = __popc(m);
+    asm volatile("bar.sync 1, 64;"); // the two warps only
+    const uint32_t bit = (slot >= 32 ? s_warp[0] : 0) + __popc(m & ((1u << lane) - 1u));
+    const uint32_t K = s_warp[0] + s_warp[1];
+    if (occ) {
+      batch->wbit[slot] = bit;
+      if (bit < TIR_MAX_SHARED) {
+        const volatile TirWindow *f = &batch->wfull[slot];
+        TirWindow d;
+        d.lo1 = f->lo1, d.hi1 = f->hi1, d.lo2 = f->lo2, d.hi2 = f->hi2, d.weight = 1, d.pad = 0;
+        batch->distinct[bit] = d;
+      }
+    }
+    if (slot == 0) {
+      batch->n_distinct = K > TIR_MAX_SHARED ? 0 : K;
+      if (K > TIR_MAX_SHARED) batch->use_general = 1u; // too many distinct windows: per-query path
+    }
+  }
 }
 
 // ================================================================================ match kernel
@@ -405,121 +506,9 @@ __device__ __forceinline__ uint64_t tir_warp_bound(const int32_t *__restrict__ k
   return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
-// ---- shared-window path -------------------------------------------------------------------------
-// The query side truncates max1 to an integer (src/fp_handler.c:290), so with coefs == 1 all the
-// frames of all the queries of a batch probe a handful of DISTINCT windows (one per integer value of
-// max1 that occurs).  "uuid has a row in window k" does not depend on the query, so the batch scans
-// every distinct window ONCE, leaves a bit pattern per uuid, reduces "greatest uuid rank per
-// pattern", and each query then only weighs the patterns:
-//     match_count(q, uuid) = sum_k weight(q, k) * [bit k of pattern(uuid)]
-// -- the same votes, the same winner and tie rule as the per-query path, for a cost that is
-// independent of the number of queries.  "Greatest rank per pattern" lives in a direct table for up
-// to TIR_SHARED_DIRECT windows (2^12 patterns; synthetic audio and most telephone speech: max1 is
-// 10*log10|c0|, a handful of integers) and in a hash table for up to TIR_MAX_SHARED windows (a batch
-// of recordings of very different loudness): the patterns that OCCUR are few, whatever their width.
-// Batches with more distinct windows (coefs == 2: the max2 bounds are real numbers), or more
-// occurring patterns than the hash table holds, take the per-query kernel below; the choice is made
-// on the device (TirBatch::use_general), nothing is read back.
-#define TIR_SHARED_DIRECT 12
-#define TIR_MAX_SHARED 32
-#define TIR_PAT_HASH_CTA 2048     // slots of a CTA's table (16 KB, the size of the direct table)
-#define TIR_PAT_HASH_GLOBAL 16384 // slots of the batch's table
-struct TirBatch {
-  uint32_t n_distinct, use_general;
-  uint32_t n_patterns; // hashed mode: occupied slots of the batch's table (listed in pat_list)
-  uint32_t overflow;   // hashed mode: a pattern table filled up -> per-query path (set by the reduce kernel)
-  TirWindow distinct[TIR_MAX_SHARED];
-};
-__device__ __forceinline__ uint32_t tir_pat_hash(uint32_t p) { return (p * 0x9e3779b1u) >> 7; }
-
-// one CTA: distinct windows of the whole batch; every folded window learns its bit (TirWindow::pad).
-// Rounds: every thread walks its queries' windows while they are in the list; the lowest thread
-// that is stuck on an unknown window appends it; at most TIR_MAX_SHARED + 1 rounds.
-__global__ void __launch_bounds__(1024)
-    tir_batch_windows_kernel(TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
-                             const uint64_t *__restrict__ frame_off, uint32_t n_queries, TirBatch *__restrict__ batch) {
-  TIR_PDL_PROLOGUE();
-  __shared__ TirWindow s_w[TIR_MAX_SHARED];
-  __shared__ uint32_t s_n, s_cand;
-  const uint32_t tid = threadIdx.x;
-  if (tid == 0) s_n = 0;
-  __syncthreads();
-  uint32_t q = tid, i = 0;
-  bool over = false;
-  for (;;) {
-    const uint32_t n = s_n;
-    TirWindow w;
-    bool stuck = false;
-    while (q < n_queries) { // advance while the current window is known
-      if (i >= n_windows[q]) { q += blockDim.x, i = 0; continue; }
-      TirWindow *wp = windows + frame_off[q] + i;
-      w = *wp;
-      uint32_t bit = 0xffffffffu;
-      for (uint32_t k = 0; k < n; k++)
-        if (s_w[k].lo1 == w.lo1 && s_w[k].hi1 == w.hi1 && s_w[k].lo2 == w.lo2 && s_w[k].hi2 == w.hi2) { bit = k; break; }
-      if (bit == 0xffffffffu) { stuck = true; break; }
-      wp->pad = bit, i++;
-    }
-    __syncthreads();
-    if (tid == 0) s_cand = 0xffffffffu;
-    __syncthreads();
-    if (stuck) atomicMin(&s_cand, tid);
-    __syncthreads();
-    const uint32_t cand = s_cand;
-    if (cand == 0xffffffffu) break;                 // every window has its bit
-    if (n >= TIR_MAX_SHARED) { over = true; break; } // too many distinct windows: per-query path
-    if (tid == cand) s_w[n] = w;
-    __syncthreads();
-    if (tid == 0) s_n = n + 1;
-    __syncthreads();
-  }
-  const uint32_t n = s_n;
-  if (tid < TIR_MAX_SHARED && tid < n) batch->distinct[tid] = s_w[tid];
-  if (tid == 0) batch->n_distinct = over ? 0 : n, batch->use_general = over ? 1u : 0u;
-}
-
-// grid (n_blocks, TIR_SHARED_DIRECT): rows of distinct window k (k += gridDim.y) in index block blk -> pattern bits
-template <int COEFS>
-__global__ void __launch_bounds__(TIR_MATCH_THREADS)
-    tir_pattern_scan_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
-                            const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
-                            const TirBatch *__restrict__ batch, uint32_t *__restrict__ pattern) {
-  TIR_PDL_PROLOGUE();
-  const uint32_t blk = blockIdx.x;
-  if (batch->use_general || blockIdx.y >= batch->n_distinct) return;
-  __shared__ uint64_t s_range[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
-  if (bs == be) return;
-  const uint32_t K = batch->n_distinct;
-  for (uint32_t k = blockIdx.y; k < K; k += gridDim.y) {
-  if (k != blockIdx.y) __syncthreads(); // s_range of the previous window has been read
-  const TirWindow w = batch->distinct[k];
-  if (warp == 0) {
-    const uint64_t r = tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
-    if (lane == 0) s_range[0] = r;
-  } else if (warp == 1) {
-    const uint64_t r = tir_warp_bound<true>(key1, bs, be, w.hi1, lane);
-    if (lane == 0) s_range[1] = r;
-  }
-  __syncthreads();
-  const uint64_t r0 = s_range[0], r1 = s_range[1];
-  uint32_t *pat = pattern + (size_t)blk * TIR_BLOCK_UUIDS;
-  for (uint64_t r = r0 + tid; r < r1; r += TIR_MATCH_THREADS) {
-    if (COEFS >= 2) {
-      const int32_t k2 = __ldg(key2 + r);
-      if (k2 < w.lo2 || k2 > w.hi2) continue;
-    }
-    atomicOr(pat + __ldg(uid + r), 1u << k); // group by audio_uuid: a bit, not a count
-  }
-  } // k
-}
-
-// greatest rank (+1) per pattern; clears the patterns for the next batch.  Warp-aggregated through
-// a shared-memory table, one global atomicMax per CTA and occupied pattern.  Up to TIR_SHARED_DIRECT
-// windows the pattern is the table index; beyond, both tables are open-addressing hash tables keyed
-// by the pattern (0 = empty: the zero pattern is never inserted), and a pattern new to the batch's
-// table is appended to pat_list.  A table that fills up sends the batch to the per-query path.
+// ---- shared-window path: kernels (TirBatch and the window set are defined above tir_qprep_kernel) ----
+// A pattern new to a hash table claims a slot with atomicCAS (0 = empty: the zero pattern is never
+// inserted); the value is the greatest rank + 1 seen with that pattern.
 __device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, uint32_t mask, uint32_t p, uint32_t rank1,
                                                uint32_t *slot_out, bool *is_new) {
   uint32_t h = tir_pat_hash(p) & mask;
@@ -536,49 +525,105 @@ __device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, u
   return false;
 }
 
-__global__ void __launch_bounds__(256)
-    tir_pattern_reduce_kernel(uint32_t *__restrict__ pattern, uint32_t n_audio, TirBatch *__restrict__ batch,
-                              uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys, uint32_t *__restrict__ g_vals,
-                              uint32_t *__restrict__ pat_list) {
+// One CTA per index block, everything in shared memory: (1) the 2K bound searches of the K distinct
+// windows (dependent global loads: the latency of this kernel) run concurrently, one warp each;
+// (2) the rows of every window OR bit k into the block's 16 384 patterns (64 KB) -- GROUP BY
+// audio_uuid is a bit, not a count; (3) the patterns are swept into "greatest rank (+1) per pattern"
+// -- a direct table up to TIR_SHARED_DIRECT windows, an open-addressing hash table beyond (same 16 KB);
+// (4) one global atomicMax per occupied pattern (hashed: insertion into the batch's table; a pattern
+// new to it is appended to pat_list).  No per-uuid state in HBM, no global atomics per row.
+// A hash table that fills up raises TirBatch::overflow: the per-query kernel takes the batch.
+// PW = the pattern word: uint16_t serves batches of up to 16 windows with 40 KB of shared memory --
+// five CTAs per SM, so that the 611 blocks of a 10 M-fingerprint table are ONE wave of a kernel whose
+// duration is a chain of latencies; uint32_t (72 KB) serves 17..32 windows.  Both are launched, the
+// one whose range does not hold the batch returns at once.
+template <typename PW> struct TirPBlock {
+  static constexpr int kSmem = TIR_BLOCK_UUIDS * (int)sizeof(PW) + (4 << TIR_SHARED_DIRECT);
+  static constexpr uint32_t kMinK = sizeof(PW) == 2 ? 1 : 17, kMaxK = sizeof(PW) == 2 ? 16 : TIR_MAX_SHARED;
+};
+template <int COEFS, typename PW>
+__global__ void __launch_bounds__(TIR_MATCH_THREADS)
+    tir_pattern_block_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
+                             const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
+                             TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys,
+                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list) {
   TIR_PDL_PROLOGUE();
-  if (batch->use_general || batch->n_distinct == 0) return;
-  const bool hashed = batch->n_distinct > TIR_SHARED_DIRECT;
-  __shared__ uint32_t s_tab[1 << TIR_SHARED_DIRECT]; // direct: max rank by pattern; hashed: keys | values
-  __shared__ uint32_t s_full;
-  static_assert(2 * TIR_PAT_HASH_CTA == (1 << TIR_SHARED_DIRECT), "the two uses share one table");
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: keys | values
+  uint32_t *s_pat = s_dyn + (1 << TIR_SHARED_DIRECT); // PW patterns, updated with 32-bit atomics on the holding word
   uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
-  for (int i = threadIdx.x; i < (1 << TIR_SHARED_DIRECT); i += blockDim.x) s_tab[i] = 0;
-  if (threadIdx.x == 0) s_full = 0;
+  static_assert(2 * TIR_PAT_HASH_CTA == (1 << TIR_SHARED_DIRECT), "the two uses share one table");
+  __shared__ uint64_t s_range[TIR_MAX_SHARED][2];
+  __shared__ uint32_t s_full;
+  const uint32_t blk = blockIdx.x;
+  const uint32_t K = batch->n_distinct;
+  if (batch->use_general || K < TirPBlock<PW>::kMinK || K > TirPBlock<PW>::kMaxK) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
+  if (bs == be) return;
+  const bool hashed = K > TIR_SHARED_DIRECT;
+  for (int i = tid; i < TirPBlock<PW>::kSmem / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_dyn)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) s_full = 0;
+  for (uint32_t j = warp; j < 2 * K; j += TIR_MATCH_THREADS / 32) {
+    const TirWindow w = batch->distinct[j >> 1];
+    const uint64_t r = (j & 1) ? tir_warp_bound<true>(key1, bs, be, w.hi1, lane) : tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
+    if (lane == 0) s_range[j >> 1][j & 1] = r;
+  }
   __syncthreads();
-  const uint32_t n4 = (n_audio + 3) / 4; // the buffer is padded to whole uint4
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-    uint4 p = reinterpret_cast<uint4 *>(pattern)[i];
-    if (p.x | p.y | p.z | p.w) {
-      if (!hashed) {
-        if (p.x) atomicMax(&s_tab[p.x], 4 * i + 1);
-        if (p.y) atomicMax(&s_tab[p.y], 4 * i + 2);
-        if (p.z) atomicMax(&s_tab[p.z], 4 * i + 3);
-        if (p.w) atomicMax(&s_tab[p.w], 4 * i + 4);
-      } else {
-        bool ok = true;
-        if (p.x) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.x, 4 * i + 1, nullptr, nullptr);
-        if (p.y) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.y, 4 * i + 2, nullptr, nullptr);
-        if (p.z) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.z, 4 * i + 3, nullptr, nullptr);
-        if (p.w) ok &= tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, p.w, 4 * i + 4, nullptr, nullptr);
-        if (!ok) s_full = 1;
+  bool any = false;
+  for (uint32_t k = 0; k < K; k++) {
+    const uint64_t r0 = s_range[k][0], r1 = s_range[k][1];
+    any |= r1 > r0;
+    int32_t lo2 = 0, hi2 = 0;
+    if (COEFS >= 2) lo2 = batch->distinct[k].lo2, hi2 = batch->distinct[k].hi2;
+    // four independent row loads in flight per thread (a window holds ~4 rows per thread: without the
+    // unrolling their latencies add up)
+    for (uint64_t r = r0 + tid; r < r1; r += 4 * TIR_MATCH_THREADS) {
+      uint32_t u[4];
+      bool ok[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const uint64_t re = r + (uint64_t)e * TIR_MATCH_THREADS;
+        ok[e] = re < r1;
+        u[e] = ok[e] ? __ldg(uid + re) : 0u;
+        if (COEFS >= 2 && ok[e]) {
+          const int32_t k2 = __ldg(key2 + re);
+          ok[e] = k2 >= lo2 && k2 <= hi2;
+        }
       }
-      reinterpret_cast<uint4 *>(pattern)[i] = make_uint4(0, 0, 0, 0); // (also when a table is full: the next batch starts clean)
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (ok[e]) {
+          if (sizeof(PW) == 2) atomicOr(&s_pat[u[e] >> 1], (1u << k) << ((u[e] & 1) * 16));
+          else atomicOr(&s_pat[u[e]], 1u << k);
+        }
+    }
+  }
+  if (!any) return; // (CTA-uniform) no row of this block lies in any window
+  __syncthreads();
+  const uint32_t rank0 = blk * TIR_BLOCK_UUIDS + 1;
+  constexpr int PER16 = 16 / (int)sizeof(PW); // patterns per 16-byte load
+  for (int i = tid; i < TIR_BLOCK_UUIDS / PER16; i += TIR_MATCH_THREADS) {
+    const uint4 p = reinterpret_cast<const uint4 *>(s_pat)[i];
+    if (!(p.x | p.y | p.z | p.w)) continue;
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int e = 0; e < PER16; e++) {
+      const uint32_t pv = sizeof(PW) == 2 ? (pw[e >> 1] >> ((e & 1) * 16)) & 0xffffu : pw[e & 3];
+      if (!pv) continue;
+      if (!hashed) atomicMax(&s_tab[pv], rank0 + PER16 * i + e);
+      else if (!tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, pv, rank0 + PER16 * i + e, nullptr, nullptr)) s_full = 1;
     }
   }
   __syncthreads();
   if (!hashed) {
-    const uint32_t np = 1u << batch->n_distinct;
-    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
+    const uint32_t np = 1u << K;
+    for (uint32_t i = tid; i < np; i += TIR_MATCH_THREADS)
       if (s_tab[i]) atomicMax(max_rank1 + i, s_tab[i]);
     return;
   }
   bool full = s_full != 0;
-  for (uint32_t i = threadIdx.x; i < TIR_PAT_HASH_CTA && !full; i += blockDim.x) {
+  for (uint32_t i = tid; i < TIR_PAT_HASH_CTA && !full; i += TIR_MATCH_THREADS) {
     const uint32_t p = s_keys[i];
     if (!p) continue;
     uint32_t slot;
@@ -596,9 +641,9 @@ __global__ void __launch_bounds__(256)
 // one warp per query: weigh the occupied patterns (direct: every table index; hashed: pat_list)
 __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
                                            const uint64_t *__restrict__ frame_off, uint32_t n_queries,
-                                           const TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
+                                           TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
                                            const uint32_t *__restrict__ g_keys, const uint32_t *__restrict__ g_vals,
-                                           const uint32_t *__restrict__ pat_list, unsigned long long *__restrict__ best) {
+                                           const uint32_t *__restrict__ pat_list, unsigned long long *__restrict__ best_shared) {
   TIR_PDL_PROLOGUE();
   if (batch->use_general || batch->overflow) return;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -609,7 +654,11 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
   uint32_t wk = 0; // lane k holds weight(q, k)
   for (uint32_t i = 0; i < nw; i++) {
     const TirWindow w = wq[i];
-    if (w.pad == lane) wk += w.weight;
+    const uint32_t bit = batch->wbit[w.pad]; // .pad: slot in the batch's window set
+    const TirWindow d = batch->distinct[bit];
+    if (lane == 0 && (d.lo1 != w.lo1 || d.hi1 != w.hi1 || d.lo2 != w.lo2 || d.hi2 != w.hi2))
+      atomicExch(&batch->overflow, 1u); // two windows behind one 64-bit key
+    if (bit == lane) wk += w.weight;
   }
   unsigned long long bestv = 0;
   const uint32_t np = hashed ? batch->n_patterns : (K ? (1u << K) : 0);
@@ -632,7 +681,7 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
     if (r1 && score) bestv = max(bestv, ((unsigned long long)score << 32) | (unsigned long long)(r1 - 1));
   }
   for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
-  if (lane == 0) best[q] = bestv;
+  if (lane == 0) best_shared[q] = bestv;
 }
 
 // ---- per-query path -------------------------------------------------------------------------------
@@ -707,13 +756,16 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   } // items
 }
 
-__global__ void tir_finalize_kernel(const unsigned long long *__restrict__ best, const uint32_t *__restrict__ order,
+// best: winners of the per-query kernel; best_shared: of the shared-window path (which of the two ran
+// is known only on the device)
+__global__ void tir_finalize_kernel(const unsigned long long *__restrict__ best, const unsigned long long *__restrict__ best_shared,
+                                    const TirBatch *__restrict__ batch, const uint32_t *__restrict__ order,
                                     const uint8_t *__restrict__ uuids, const uint64_t *__restrict__ frame_off,
                                     uint32_t n_queries, tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_queries) return;
-  const unsigned long long b = best[q];
+  const unsigned long long b = (batch->use_general || batch->overflow) ? best[q] : best_shared[q];
   tir_hit h;
   h.match_count = (int32_t)(b >> 32);
   h.frame_count = (int32_t)(frame_off[q + 1] - frame_off[q]); // all frames, :286,403
@@ -767,9 +819,10 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   for (uint32_t q = 0; q < n_queries; q++)
     if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 65535)
       return tir_fail(ctx, TIR_ERR_ARG, "a query may have at most 65535 frames (u16 vote counters)");
-  // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | pattern hash keys | values | pattern list | windows
+  // scratch: frame_off (device) | n_windows | best | best_shared | batch | max_rank1 | pattern hash keys | values | pattern list | windows
   const size_t o_foff = 0, o_nw = o_foff + ((size_t)n_queries + 1) * 8, o_best = (o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
-  const size_t o_batch = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  const size_t o_best2 = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  const size_t o_batch = (o_best2 + (size_t)n_queries * 8 + 15) & ~(size_t)15;
   const size_t o_maxr = (o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
   const size_t o_gkeys = o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), o_gvals = o_gkeys + (size_t)4 * TIR_PAT_HASH_GLOBAL;
   const size_t o_plist = o_gvals + (size_t)4 * TIR_PAT_HASH_GLOBAL; // (first bytes that need no clearing)
@@ -792,33 +845,38 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   mp.thr_hi = mp.use_hi ? 10 * log10((double)ign_hi) : 0.0;
   const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
-  unsigned long long *d_best = (unsigned long long *)(d + o_best);
+  unsigned long long *d_best = (unsigned long long *)(d + o_best), *d_best2 = (unsigned long long *)(d + o_best2);
   TirBatch *d_batch = (TirBatch *)(d + o_batch);
   uint32_t *d_maxr = (uint32_t *)(d + o_maxr), *d_gkeys = (uint32_t *)(d + o_gkeys), *d_gvals = (uint32_t *)(d + o_gvals);
   uint32_t *d_plist = (uint32_t *)(d + o_plist);
   TirWindow *d_win = (TirWindow *)(d + o_win);
   if (d_coef)
-    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw));
+    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw, d_batch));
   else
-    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw));
+    TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw, d_batch));
   ctx->launches++;
   if (db->n_blocks && db->n_indexed) {
     const int32_t *k1 = (const int32_t *)db->key1.p, *k2 = (const int32_t *)db->key2.p;
     const uint16_t *uid = (const uint16_t *)db->uid.p;
     const uint64_t *bst = (const uint64_t *)db->block_start.p;
-    uint32_t *pat = (uint32_t *)db->pattern.p;
-    const uint32_t n_ranks = db->n_blocks * TIR_BLOCK_UUIDS;
     if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    TIR_CUDA(ctx, tir_launch_pdl(tir_batch_windows_kernel, dim3(1), dim3(1024), st, d_win, (const uint32_t *)d_nw, d_foff, n_queries, d_batch));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
-    const dim3 pgrid(db->n_blocks, TIR_SHARED_DIRECT);
-    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_scan_kernel<2>, pgrid, dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirBatch *)d_batch, pat));
-    else TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_scan_kernel<1>, pgrid, dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirBatch *)d_batch, pat));
-    const uint32_t rgrid = std::min<uint32_t>((n_ranks / 4 + 255) / 256, (uint32_t)ctx->num_sms * 4);
-    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_reduce_kernel, dim3(rgrid), dim3(256), st, pat, n_ranks, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+    if (!ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_pattern_block_kernel<1, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TirPBlock<uint32_t>::kSmem));
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_pattern_block_kernel<2, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TirPBlock<uint32_t>::kSmem));
+      ctx->match_smem_attr_set = true;
+    }
+    const dim3 pgrid(db->n_blocks), pthr(TIR_MATCH_THREADS);
+    if (coefs >= 2) {
+      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2, uint16_t>, pgrid, pthr, TirPBlock<uint16_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2, uint32_t>, pgrid, pthr, TirPBlock<uint32_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+    } else {
+      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1, uint16_t>, pgrid, pthr, TirPBlock<uint16_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1, uint32_t>, pgrid, pthr, TirPBlock<uint32_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+    }
     TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
-                                 (const uint32_t *)d_nw, d_foff, n_queries, (const TirBatch *)d_batch, (const uint32_t *)d_maxr,
-                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, d_best));
+                                 (const uint32_t *)d_nw, d_foff, n_queries, d_batch, (const uint32_t *)d_maxr,
+                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, d_best2));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 6);
@@ -828,14 +886,14 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     else
       TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
                                    (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, (const TirBatch *)d_batch));
-    ctx->launches += 5;
+    ctx->launches += 4;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
       ctx->ev_valid[1] = true;
     }
   }
   TIR_CUDA(ctx, tir_launch_pdl(tir_finalize_kernel, dim3((n_queries + 127) / 128), dim3(128), st, (const unsigned long long *)d_best,
-                               (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits));
+                               (const unsigned long long *)d_best2, (const TirBatch *)d_batch, (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits));
   ctx->launches++;
   TIR_CUDA(ctx, cudaGetLastError());
   return TIR_OK;

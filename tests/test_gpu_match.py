@@ -95,8 +95,9 @@ def test_shared_window_and_per_query_paths_agree(gpu_ctx, oracle):
             assert gpu_result(single) == gpu_result(batch[qi]), (coefs, tol, qi)
             if qi % 3 == 0 and y.shape[0]:
                 assert gpu_result(batch[qi]) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, qi)
-    # the table boundaries: 12 distinct windows (direct pattern table), 13 and 32 (hashed), 33 (per-query)
-    for n_int in (12, 13, 32, 33):
+    # the table boundaries: 11 distinct windows (direct pattern table), 12..16 (hashed, 16-bit patterns),
+    # 17..32 (hashed, 32-bit patterns), 33 (per-query)
+    for n_int in (11, 12, 16, 17, 32, 33):
         y = np.stack([np.arange(n_int) - 5 + 0.2, np.zeros(n_int)], axis=1)
         h = gpu_ctx.match(y, None, 1, 0.3)[0]
         assert gpu_result(h) == sql_result(sq.search(y, 1, 0.3)), n_int
