@@ -344,7 +344,7 @@ __device__ __forceinline__ unsigned long long tir_window_key(const TirWindow &w)
   k ^= (m >> 29);
   return k ? k : 1ull;
 }
-__device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w) {
+__device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w, bool &claimed) {
   const unsigned long long key = tir_window_key(w);
   uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 58); // 6 bits
   for (int probe = 0; probe < TIR_WSET_SLOTS; probe++, h = (h + 1) & (TIR_WSET_SLOTS - 1)) {
@@ -355,6 +355,7 @@ __device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWi
         TirWindow f = w;
         f.weight = 1, f.pad = 0;
         batch->wfull[h] = f;
+        claimed = true;
         return h;
       }
     }
@@ -401,24 +402,23 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
   }
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
-  // pass 2: a frame is a leader if no earlier frame has the same window; its weight = the multiplicity
-  // of the window in the query (stashed in .pad, 0 = not a leader)
+  // pass 2: every frame looks for the first frame with its window (itself: a leader) and adds one to
+  // that frame's multiplicity (kept in .pad; 0 = not a leader, or a skipped frame)
   for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
     const TirWindow w = ws[i];
-    uint32_t mult = 0;
-    bool leader = w.weight != 0;
-    for (uint32_t j = 0; leader && j < nf; j++) {
+    if (w.weight == 0) continue;
+    uint32_t j = 0;
+    for (; j < i; j++) {
       const TirWindow o = ws[j];
-      const bool same = o.weight != 0 && o.lo1 == w.lo1 && o.hi1 == w.hi1 && o.lo2 == w.lo2 && o.hi2 == w.hi2;
-      if (same && j < i) leader = false;
-      mult += same;
+      if (o.weight != 0 && o.lo1 == w.lo1 && o.hi1 == w.hi1 && o.lo2 == w.lo2 && o.hi2 == w.hi2) break;
     }
-    ws[i].pad = leader ? mult : 0;
+    atomicAdd(&ws[j].pad, 1u);
   }
   __syncthreads();
   // pass 3: leaders to the front of the query's slice, in frame order (ballot prefix per chunk of
   // blockDim frames).  In the in-place case a chunk's writes land at indices <= its first frame, which
   // were consumed by earlier chunks; its own entries are read before the barrier.
+  bool claimed = false;
   for (uint32_t c0 = 0; c0 < nf; c0 += blockDim.x) {
     const uint32_t i = c0 + threadIdx.x;
     TirWindow w;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     for (int k = 0; k < wid; k++) pos += s_warp[k];
     if (leader) {
       w.weight = w.pad;
-      w.pad = tir_wset_insert(batch, w); // slot in the batch's window set
+      w.pad = tir_wset_insert(batch, w, claimed); // slot in the batch's window set
       wq[pos] = w;
     }
     __syncthreads();
@@ -447,8 +447,9 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     __syncthreads();
   }
   if (threadIdx.x == 0) n_windows[q] = s_base;
-  // the last CTA to finish numbers the occupied slots of the window set
-  __threadfence();
+  // the last CTA to finish numbers the occupied slots of the window set (a CTA that claimed a slot
+  // makes the window it stored there visible before it counts itself done)
+  if (claimed) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&batch->done, 1u) == gridDim.x - 1;
   __syncthreads();
@@ -651,14 +652,24 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
   const uint32_t K = batch->n_distinct, nw = n_windows[q];
   const bool hashed = K > TIR_SHARED_DIRECT;
   const TirWindow *wq = windows + frame_off[q];
+  // lane i takes window i (32 at a time): window -> slot -> bit -> the window that bit stands for are
+  // three dependent loads, paid once per 32 windows instead of once per window
   uint32_t wk = 0; // lane k holds weight(q, k)
-  for (uint32_t i = 0; i < nw; i++) {
-    const TirWindow w = wq[i];
-    const uint32_t bit = batch->wbit[w.pad]; // .pad: slot in the batch's window set
-    const TirWindow d = batch->distinct[bit];
-    if (lane == 0 && (d.lo1 != w.lo1 || d.hi1 != w.hi1 || d.lo2 != w.lo2 || d.hi2 != w.hi2))
-      atomicExch(&batch->overflow, 1u); // two windows behind one 64-bit key
-    if (bit == lane) wk += w.weight;
+  for (uint32_t i0 = 0; i0 < nw; i0 += 32) {
+    uint32_t bit = 0xffffffffu, weight = 0;
+    if (i0 + lane < nw) {
+      const TirWindow w = wq[i0 + lane];
+      bit = batch->wbit[w.pad]; // .pad: slot in the batch's window set
+      weight = w.weight;
+      const TirWindow d = batch->distinct[bit];
+      if (d.lo1 != w.lo1 || d.hi1 != w.hi1 || d.lo2 != w.lo2 || d.hi2 != w.hi2)
+        atomicExch(&batch->overflow, 1u); // two windows behind one 64-bit key
+    }
+    const uint32_t n = min(32u, nw - i0);
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t b = __shfl_sync(0xffffffffu, bit, i), wg = __shfl_sync(0xffffffffu, weight, i);
+      if (b == lane) wk += wg;
+    }
   }
   unsigned long long bestv = 0;
   const uint32_t np = hashed ? batch->n_patterns : (K ? (1u << K) : 0);

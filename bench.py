@@ -277,7 +277,7 @@ def match_bench(ctx, args, rank, world, device, dist):
            "search_e2e": search_e2e, "cpu_baseline": cpu_match,
            "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None,
                         "unit": "GB/s", "algorithmic_bytes_per_batch_this_rank": alg,
-                        "note": "SURVEY 8d charge F_q*8 + sum_k(16 + 8*R_k) + 24 per QUERY; the shared-window path reads each distinct window once per BATCH (6 B per row in it) plus 4 B per uuid for the pattern sweep, so the charged figure can exceed the HBM peak"}}
+                        "note": "SURVEY 8d charge F_q*8 + sum_k(16 + 8*R_k) + 24 per QUERY; the shared-window path reads each distinct window once per BATCH (6 B per row in it; the per-uuid patterns live in shared memory), so the charged figure can exceed the HBM peak"}}
     del uu, v1, v2
     return res
 
