@@ -322,7 +322,7 @@ struct TirBatch {
   uint32_t n_distinct, use_general; // published by the last qprep CTA (use_general also by an inserter that finds the set full)
   uint32_t n_patterns; // hashed mode: occupied slots of the batch's table (listed in pat_list)
   uint32_t overflow;   // a pattern table filled up, or two windows shared a 64-bit key -> per-query path
-  uint32_t done, pad_[3];                  // qprep CTAs that have finished
+  uint32_t done, done_general, pad_[2];    // qprep CTAs / per-query CTAs that have finished
   unsigned long long wkey[TIR_WSET_SLOTS]; // 0 = free, else the 64-bit key of the window that claimed the slot
   TirWindow wfull[TIR_WSET_SLOTS];         // ... and the window itself (written by the claimer)
   uint32_t wbit[TIR_WSET_SLOTS];           // slot -> bit of the window in the patterns
@@ -526,6 +526,24 @@ __device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, u
   return false;
 }
 
+// rank -> uuid bytes, tir_hit{uuid, match_count, frame_count}; b = (count << 32 | rank), 0 = no row matched
+__device__ __forceinline__ void tir_write_hit(unsigned long long b, const uint32_t *__restrict__ order,
+                                              const uint8_t *__restrict__ uuids, const uint64_t *__restrict__ frame_off,
+                                              uint32_t q, tir_hit *__restrict__ hits) {
+  tir_hit h;
+  h.match_count = (int32_t)(b >> 32);
+  h.frame_count = (int32_t)(frame_off[q + 1] - frame_off[q]); // all frames, :286,403
+  if (b) {
+    const uint8_t *u = uuids + (size_t)order[(uint32_t)b] * 16;
+#pragma unroll
+    for (int i = 0; i < 16; i++) h.uuid[i] = u[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) h.uuid[i] = 0;
+  }
+  hits[q] = h;
+}
+
 // One CTA per index block, everything in shared memory: (1) the 2K bound searches of the K distinct
 // windows (dependent global loads: the latency of this kernel) run concurrently, one warp each;
 // (2) the rows of every window OR bit k into the block's 16 384 patterns (64 KB) -- GROUP BY
@@ -534,47 +552,23 @@ __device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, u
 // (4) one global atomicMax per occupied pattern (hashed: insertion into the batch's table; a pattern
 // new to it is appended to pat_list).  No per-uuid state in HBM, no global atomics per row.
 // A hash table that fills up raises TirBatch::overflow: the per-query kernel takes the batch.
-// PW = the pattern word: uint16_t serves batches of up to 16 windows with 40 KB of shared memory --
-// five CTAs per SM, so that the 611 blocks of a 10 M-fingerprint table are ONE wave of a kernel whose
-// duration is a chain of latencies; uint32_t (72 KB) serves 17..32 windows.  Both are launched, the
-// one whose range does not hold the batch returns at once.
-template <typename PW> struct TirPBlock {
-  static constexpr int kSmem = TIR_BLOCK_UUIDS * (int)sizeof(PW) + (4 << TIR_SHARED_DIRECT);
-  static constexpr uint32_t kMinK = sizeof(PW) == 2 ? 1 : 17, kMaxK = sizeof(PW) == 2 ? 16 : TIR_MAX_SHARED;
-};
+// The pattern array is 32 KB: 16 384 patterns of 16 bits for batches of up to 16 windows, or -- for
+// 17..32 windows -- 8 192 patterns of 32 bits, the block's uuids taken in two halves (the few rows
+// are read twice).  With the 8 KB table that is 40 KB per CTA: five CTAs per SM, so that the 611
+// blocks of a 10 M-fingerprint table are ONE wave of a kernel whose duration is a chain of latencies.
+#define TIR_PBLOCK_SMEM (TIR_BLOCK_UUIDS * 2 + (4 << TIR_SHARED_DIRECT))
+
+// rows of the K windows -> patterns of uuids [uid0, uid0 + n_uuid) -> table.  PW: pattern word.
 template <int COEFS, typename PW>
-__global__ void __launch_bounds__(TIR_MATCH_THREADS)
-    tir_pattern_block_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
-                             const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
-                             TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys,
-                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list) {
-  TIR_PDL_PROLOGUE();
-  extern __shared__ __align__(16) uint32_t s_dyn[];
-  uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: keys | values
-  uint32_t *s_pat = s_dyn + (1 << TIR_SHARED_DIRECT); // PW patterns, updated with 32-bit atomics on the holding word
+__device__ __forceinline__ void tir_pblock_pass(const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
+                                                const TirBatch *__restrict__ batch, const uint64_t (*s_range)[2], uint32_t K,
+                                                uint32_t *s_pat, uint32_t *s_tab, uint32_t *s_full, bool hashed, uint32_t uid0,
+                                                uint32_t n_uuid, uint32_t rank0, int tid) {
   uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
-  static_assert(2 * TIR_PAT_HASH_CTA == (1 << TIR_SHARED_DIRECT), "the two uses share one table");
-  __shared__ uint64_t s_range[TIR_MAX_SHARED][2];
-  __shared__ uint32_t s_full;
-  const uint32_t blk = blockIdx.x;
-  const uint32_t K = batch->n_distinct;
-  if (batch->use_general || K < TirPBlock<PW>::kMinK || K > TirPBlock<PW>::kMaxK) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
-  if (bs == be) return;
-  const bool hashed = K > TIR_SHARED_DIRECT;
-  for (int i = tid; i < TirPBlock<PW>::kSmem / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_dyn)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) s_full = 0;
-  for (uint32_t j = warp; j < 2 * K; j += TIR_MATCH_THREADS / 32) {
-    const TirWindow w = batch->distinct[j >> 1];
-    const uint64_t r = (j & 1) ? tir_warp_bound<true>(key1, bs, be, w.hi1, lane) : tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
-    if (lane == 0) s_range[j >> 1][j & 1] = r;
-  }
+  for (uint32_t i = tid; i < n_uuid * sizeof(PW) / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_pat)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  bool any = false;
   for (uint32_t k = 0; k < K; k++) {
     const uint64_t r0 = s_range[k][0], r1 = s_range[k][1];
-    any |= r1 > r0;
     int32_t lo2 = 0, hi2 = 0;
     if (COEFS >= 2) lo2 = batch->distinct[k].lo2, hi2 = batch->distinct[k].hi2;
     // four independent row loads in flight per thread (a window holds ~4 rows per thread: without the
@@ -586,7 +580,8 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
       for (int e = 0; e < 4; e++) {
         const uint64_t re = r + (uint64_t)e * TIR_MATCH_THREADS;
         ok[e] = re < r1;
-        u[e] = ok[e] ? __ldg(uid + re) : 0u;
+        u[e] = ok[e] ? (uint32_t)__ldg(uid + re) - uid0 : 0xffffffffu;
+        ok[e] = u[e] < n_uuid;
         if (COEFS >= 2 && ok[e]) {
           const int32_t k2 = __ldg(key2 + re);
           ok[e] = k2 >= lo2 && k2 <= hi2;
@@ -595,28 +590,68 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
 #pragma unroll
       for (int e = 0; e < 4; e++)
         if (ok[e]) {
-          if (sizeof(PW) == 2) atomicOr(&s_pat[u[e] >> 1], (1u << k) << ((u[e] & 1) * 16));
+          if (sizeof(PW) == 2) atomicOr(&s_pat[u[e] >> 1], (1u << k) << ((u[e] & 1) * 16)); // 32-bit atomics on the holding word
           else atomicOr(&s_pat[u[e]], 1u << k);
         }
     }
   }
-  if (!any) return; // (CTA-uniform) no row of this block lies in any window
   __syncthreads();
-  const uint32_t rank0 = blk * TIR_BLOCK_UUIDS + 1;
-  constexpr int PER16 = 16 / (int)sizeof(PW); // patterns per 16-byte load
-  for (int i = tid; i < TIR_BLOCK_UUIDS / PER16; i += TIR_MATCH_THREADS) {
+  constexpr uint32_t PER16 = 16 / (uint32_t)sizeof(PW); // patterns per 16-byte load
+  for (uint32_t i = tid; i < n_uuid / PER16; i += TIR_MATCH_THREADS) {
     const uint4 p = reinterpret_cast<const uint4 *>(s_pat)[i];
     if (!(p.x | p.y | p.z | p.w)) continue;
     const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-    for (int e = 0; e < PER16; e++) {
+    for (uint32_t e = 0; e < PER16; e++) {
       const uint32_t pv = sizeof(PW) == 2 ? (pw[e >> 1] >> ((e & 1) * 16)) & 0xffffu : pw[e & 3];
       if (!pv) continue;
-      if (!hashed) atomicMax(&s_tab[pv], rank0 + PER16 * i + e);
-      else if (!tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, pv, rank0 + PER16 * i + e, nullptr, nullptr)) s_full = 1;
+      const uint32_t r1v = rank0 + uid0 + PER16 * i + e;
+      if (!hashed) atomicMax(&s_tab[pv], r1v);
+      else if (!tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, pv, r1v, nullptr, nullptr)) *s_full = 1;
     }
   }
   __syncthreads();
+}
+
+template <int COEFS>
+__global__ void __launch_bounds__(TIR_MATCH_THREADS)
+    tir_pattern_block_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
+                             const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
+                             TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys,
+                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list) {
+  TIR_PDL_PROLOGUE();
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: keys | values
+  uint32_t *s_pat = s_dyn + (1 << TIR_SHARED_DIRECT);
+  uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
+  static_assert(2 * TIR_PAT_HASH_CTA == (1 << TIR_SHARED_DIRECT), "the two uses share one table");
+  __shared__ uint64_t s_range[TIR_MAX_SHARED][2];
+  __shared__ uint32_t s_full;
+  const uint32_t blk = blockIdx.x;
+  const uint32_t K = batch->n_distinct;
+  if (batch->use_general || K == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
+  if (bs == be) return;
+  const bool hashed = K > TIR_SHARED_DIRECT;
+  for (int i = tid; i < (4 << TIR_SHARED_DIRECT) / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_tab)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) s_full = 0;
+  for (uint32_t j = warp; j < 2 * K; j += TIR_MATCH_THREADS / 32) {
+    const TirWindow w = batch->distinct[j >> 1];
+    const uint64_t r = (j & 1) ? tir_warp_bound<true>(key1, bs, be, w.hi1, lane) : tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
+    if (lane == 0) s_range[j >> 1][j & 1] = r;
+  }
+  __syncthreads();
+  bool any = false;
+  for (uint32_t k = 0; k < K; k++) any |= s_range[k][1] > s_range[k][0];
+  if (!any) return; // (CTA-uniform) no row of this block lies in any window
+  const uint32_t rank0 = blk * TIR_BLOCK_UUIDS + 1;
+  if (K <= 16) {
+    tir_pblock_pass<COEFS, uint16_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid);
+  } else {
+    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS / 2, rank0, tid);
+    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, TIR_BLOCK_UUIDS / 2, TIR_BLOCK_UUIDS / 2, rank0, tid);
+  }
   if (!hashed) {
     const uint32_t np = 1u << K;
     for (uint32_t i = tid; i < np; i += TIR_MATCH_THREADS)
@@ -644,7 +679,8 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
                                            const uint64_t *__restrict__ frame_off, uint32_t n_queries,
                                            TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
                                            const uint32_t *__restrict__ g_keys, const uint32_t *__restrict__ g_vals,
-                                           const uint32_t *__restrict__ pat_list, unsigned long long *__restrict__ best_shared) {
+                                           const uint32_t *__restrict__ pat_list, const uint32_t *__restrict__ order,
+                                           const uint8_t *__restrict__ uuids, tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
   if (batch->use_general || batch->overflow) return;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -692,7 +728,7 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
     if (r1 && score) bestv = max(bestv, ((unsigned long long)score << 32) | (unsigned long long)(r1 - 1));
   }
   for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
-  if (lane == 0) best_shared[q] = bestv;
+  if (lane == 0) tir_write_hit(bestv, order, uuids, frame_off, q, hits); // (the per-query kernel rewrites it if it runs)
 }
 
 // ---- per-query path -------------------------------------------------------------------------------
@@ -703,9 +739,11 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      const uint64_t *__restrict__ block_start, const TirWindow *__restrict__ windows,
                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
-                     const TirBatch *__restrict__ batch) {
+                     TirBatch *__restrict__ batch, const uint32_t *__restrict__ order, const uint8_t *__restrict__ uuids,
+                     tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
   if (!(batch->use_general || batch->overflow)) return;
+  __shared__ uint32_t s_last;
   __shared__ uint32_t s_cnt[TIR_BLOCK_UUIDS / 2];  // u16 vote counters, two per word
   __shared__ uint32_t s_seen[TIR_BLOCK_UUIDS / 32]; // per-window "uuid already voted" bits
   __shared__ uint64_t s_range[2];
@@ -765,30 +803,22 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   }
   (void)any;
   } // items
+  // the last CTA to finish turns the winners into hits
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&batch->done_general, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (uint32_t q = tid; q < n_queries; q += TIR_MATCH_THREADS)
+    tir_write_hit(*reinterpret_cast<volatile unsigned long long *>(best + q), order, uuids, frame_off, q, hits);
 }
 
-// best: winners of the per-query kernel; best_shared: of the shared-window path (which of the two ran
-// is known only on the device)
-__global__ void tir_finalize_kernel(const unsigned long long *__restrict__ best, const unsigned long long *__restrict__ best_shared,
-                                    const TirBatch *__restrict__ batch, const uint32_t *__restrict__ order,
-                                    const uint8_t *__restrict__ uuids, const uint64_t *__restrict__ frame_off,
-                                    uint32_t n_queries, tir_hit *__restrict__ hits) {
+// empty table: every query gets {no uuid, 0, frame_count}
+__global__ void tir_no_hits_kernel(const uint64_t *__restrict__ frame_off, uint32_t n_queries, tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_queries) return;
-  const unsigned long long b = (batch->use_general || batch->overflow) ? best[q] : best_shared[q];
-  tir_hit h;
-  h.match_count = (int32_t)(b >> 32);
-  h.frame_count = (int32_t)(frame_off[q + 1] - frame_off[q]); // all frames, :286,403
-  if (b) {
-    const uint8_t *u = uuids + (size_t)order[(uint32_t)b] * 16;
-#pragma unroll
-    for (int i = 0; i < 16; i++) h.uuid[i] = u[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; i++) h.uuid[i] = 0;
-  }
-  hits[q] = h;
+  if (q < n_queries) tir_write_hit(0ull, nullptr, nullptr, frame_off, q, hits);
 }
 
 __global__ void tir_merge_hits_kernel(const tir_hit *__restrict__ gathered, uint32_t n_shards, uint32_t n_queries,
@@ -830,10 +860,9 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   for (uint32_t q = 0; q < n_queries; q++)
     if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 65535)
       return tir_fail(ctx, TIR_ERR_ARG, "a query may have at most 65535 frames (u16 vote counters)");
-  // scratch: frame_off (device) | n_windows | best | best_shared | batch | max_rank1 | pattern hash keys | values | pattern list | windows
+  // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | pattern hash keys | values | pattern list | windows
   const size_t o_foff = 0, o_nw = o_foff + ((size_t)n_queries + 1) * 8, o_best = (o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
-  const size_t o_best2 = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
-  const size_t o_batch = (o_best2 + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  const size_t o_batch = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
   const size_t o_maxr = (o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
   const size_t o_gkeys = o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), o_gvals = o_gkeys + (size_t)4 * TIR_PAT_HASH_GLOBAL;
   const size_t o_plist = o_gvals + (size_t)4 * TIR_PAT_HASH_GLOBAL; // (first bytes that need no clearing)
@@ -856,7 +885,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   mp.thr_hi = mp.use_hi ? 10 * log10((double)ign_hi) : 0.0;
   const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
-  unsigned long long *d_best = (unsigned long long *)(d + o_best), *d_best2 = (unsigned long long *)(d + o_best2);
+  unsigned long long *d_best = (unsigned long long *)(d + o_best);
   TirBatch *d_batch = (TirBatch *)(d + o_batch);
   uint32_t *d_maxr = (uint32_t *)(d + o_maxr), *d_gkeys = (uint32_t *)(d + o_gkeys), *d_gvals = (uint32_t *)(d + o_gvals);
   uint32_t *d_plist = (uint32_t *)(d + o_plist);
@@ -872,40 +901,33 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     const uint64_t *bst = (const uint64_t *)db->block_start.p;
     if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
-    if (!ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_pattern_block_kernel<1, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TirPBlock<uint32_t>::kSmem));
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_pattern_block_kernel<2, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, TirPBlock<uint32_t>::kSmem));
-      ctx->match_smem_attr_set = true;
-    }
     const dim3 pgrid(db->n_blocks), pthr(TIR_MATCH_THREADS);
-    if (coefs >= 2) {
-      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2, uint16_t>, pgrid, pthr, TirPBlock<uint16_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
-      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2, uint32_t>, pgrid, pthr, TirPBlock<uint32_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
-    } else {
-      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1, uint16_t>, pgrid, pthr, TirPBlock<uint16_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
-      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1, uint32_t>, pgrid, pthr, TirPBlock<uint32_t>::kSmem, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
-    }
+    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+    else TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
     TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
                                  (const uint32_t *)d_nw, d_foff, n_queries, d_batch, (const uint32_t *)d_maxr,
-                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, d_best2));
+                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist,
+                                 (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 6);
     if (coefs >= 2)
       TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<2>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
-                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, (const TirBatch *)d_batch));
+                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
+                                   (const uint8_t *)db->uuids.p, d_hits));
     else
       TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
-                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, (const TirBatch *)d_batch));
-    ctx->launches += 4;
+                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
+                                   (const uint8_t *)db->uuids.p, d_hits));
+    ctx->launches += 3;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
       ctx->ev_valid[1] = true;
     }
+  } else {
+    TIR_CUDA(ctx, tir_launch_pdl(tir_no_hits_kernel, dim3((n_queries + 127) / 128), dim3(128), st, d_foff, n_queries, d_hits));
+    ctx->launches++;
   }
-  TIR_CUDA(ctx, tir_launch_pdl(tir_finalize_kernel, dim3((n_queries + 127) / 128), dim3(128), st, (const unsigned long long *)d_best,
-                               (const unsigned long long *)d_best2, (const TirBatch *)d_batch, (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_foff, n_queries, d_hits));
-  ctx->launches++;
   TIR_CUDA(ctx, cudaGetLastError());
   return TIR_OK;
 }
