@@ -30,6 +30,7 @@ struct tir_ctx {
   uint64_t launches = 0;
   bool profiling = false;
   bool smem_attr_set = false;
+  bool match_smem_attr_set = false;
   cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; // [which][begin/end]
   bool ev_valid[2] = {false, false};
   TirHostTables tab;

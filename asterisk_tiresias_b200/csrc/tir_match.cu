@@ -732,7 +732,26 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
 }
 
 // ---- per-query path -------------------------------------------------------------------------------
-// persistent grid over (index block, query) items.  Votes of one query into the uuids of one block.
+// persistent grid over (index block, query) items: the votes of one query into the uuids of one block.
+// Shared memory: u16 vote counters for the block's 16 384 uuids (32 KB) and, per warp, a bitmap
+// "uuid has voted in the window this warp is on" (8 x 2 KB): one vote per frame per uuid (GROUP BY
+// audio_uuid) without a barrier between windows.  Per chunk of 128 windows: (A) the 256 bounds are
+// found by 256 independent per-thread binary searches -- dependent loads, but all in flight together
+// and sharing their top levels in L1/L2; (B) one warp per window walks its row range with four loads
+// in flight per lane (uid, 2 B/row; key2 too for coefs == 2); a warp clears its bitmap only after a
+// window that voted.
+#define TIR_GEN_CHUNK 128
+#define TIR_GEN_SMEM (TIR_BLOCK_UUIDS * 2 + (TIR_MATCH_THREADS / 32) * (TIR_BLOCK_UUIDS / 8))
+template <bool UPPER>
+__device__ __forceinline__ uint64_t tir_thread_bound(const int32_t *__restrict__ key, uint64_t lo, uint64_t hi, int32_t target) {
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    const int32_t k = __ldg(key + mid);
+    if (UPPER ? (k <= target) : (k < target)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 template <int COEFS>
 __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_match_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
@@ -743,65 +762,79 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
   if (!(batch->use_general || batch->overflow)) return;
-  __shared__ uint32_t s_last;
-  __shared__ uint32_t s_cnt[TIR_BLOCK_UUIDS / 2];  // u16 vote counters, two per word
-  __shared__ uint32_t s_seen[TIR_BLOCK_UUIDS / 32]; // per-window "uuid already voted" bits
-  __shared__ uint64_t s_range[2];
+  extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word; then the warps' bitmaps
+  uint32_t *s_seen = s_cnt + TIR_BLOCK_UUIDS / 2 + (threadIdx.x >> 5) * (TIR_BLOCK_UUIDS / 32);
+  __shared__ uint64_t s_range[TIR_GEN_CHUNK][2];
   __shared__ unsigned long long s_best[TIR_MATCH_THREADS / 32];
+  __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t n_items = (uint64_t)n_blocks * n_queries;
   for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-  const uint32_t blk = (uint32_t)(item % n_blocks), q = (uint32_t)(item / n_blocks);
-  __syncthreads(); // the previous item is done with the shared arrays
-  const uint64_t bs = block_start[blk], be = block_start[blk + 1];
-  const uint32_t nw = n_windows[q];
-  if (bs == be || nw == 0) continue;
-  const TirWindow *wq = windows + frame_off[q];
-  uint16_t *cnt16 = reinterpret_cast<uint16_t *>(s_cnt);
-  for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) s_cnt[i] = 0;
-  bool any = false;
-  for (uint32_t wi = 0; wi < nw; wi++) {
-    const TirWindow w = wq[wi];
-    for (int i = tid; i < TIR_BLOCK_UUIDS / 32; i += TIR_MATCH_THREADS) s_seen[i] = 0;
-    if (warp == 0) {
-      const uint64_t r = tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
-      if (lane == 0) s_range[0] = r;
-    } else if (warp == 1) {
-      const uint64_t r = tir_warp_bound<true>(key1, bs, be, w.hi1, lane);
-      if (lane == 0) s_range[1] = r;
-    }
-    __syncthreads();
-    const uint64_t r0 = s_range[0], r1 = s_range[1];
-    for (uint64_t r = r0 + tid; r < r1; r += TIR_MATCH_THREADS) {
-      if (COEFS >= 2) {
-        const int32_t k2 = __ldg(key2 + r);
-        if (k2 < w.lo2 || k2 > w.hi2) continue;
+    const uint32_t blk = (uint32_t)(item % n_blocks), q = (uint32_t)(item / n_blocks);
+    const uint64_t bs = block_start[blk], be = block_start[blk + 1];
+    const uint32_t nw = n_windows[q];
+    if (bs == be || nw == 0) continue;
+    const TirWindow *wq = windows + frame_off[q];
+    __syncthreads(); // the previous item is done with the shared arrays
+    for (int i = tid; i < TIR_GEN_SMEM / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t c0 = 0; c0 < nw; c0 += TIR_GEN_CHUNK) {
+      const uint32_t nc = min((uint32_t)TIR_GEN_CHUNK, nw - c0);
+      __syncthreads(); // zeroing done / the previous chunk's ranges consumed
+      if ((uint32_t)tid < 2 * nc) {
+        const TirWindow &w = wq[c0 + (tid >> 1)];
+        s_range[tid >> 1][tid & 1] = (tid & 1) ? tir_thread_bound<true>(key1, bs, be, w.hi1) : tir_thread_bound<false>(key1, bs, be, w.lo1);
       }
-      const uint32_t u = __ldg(uid + r);
-      const uint32_t bit = 1u << (u & 31);
-      const uint32_t old = atomicOr(&s_seen[u >> 5], bit); // group by audio_uuid: one vote per frame
-      if (!(old & bit)) cnt16[u] = (uint16_t)(cnt16[u] + w.weight);
+      __syncthreads();
+      for (uint32_t wl = warp; wl < nc; wl += TIR_MATCH_THREADS / 32) {
+        const TirWindow w = wq[c0 + wl];
+        const uint64_t r0 = s_range[wl][0], r1 = s_range[wl][1];
+        bool voted = false;
+        for (uint64_t r = r0 + lane; r < r1; r += 4 * 32) {
+          uint32_t u[4];
+          bool ok[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const uint64_t re = r + (uint64_t)e * 32;
+            ok[e] = re < r1;
+            if (COEFS >= 2 && ok[e]) {
+              const int32_t k2 = __ldg(key2 + re);
+              ok[e] = k2 >= w.lo2 && k2 <= w.hi2;
+            }
+            u[e] = ok[e] ? (uint32_t)__ldg(uid + re) : 0u;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if (!ok[e]) continue;
+            const uint32_t bit = 1u << (u[e] & 31);
+            const uint32_t old = atomicOr(&s_seen[u[e] >> 5], bit); // group by audio_uuid: one vote per frame
+            if (!(old & bit)) atomicAdd(&s_cnt[u[e] >> 1], w.weight << ((u[e] & 1) * 16)); // total <= 65535: no carry
+            voted = true;
+          }
+        }
+        if (__any_sync(0xffffffffu, voted)) { // next window of this warp: a clean bitmap
+          __syncwarp();
+          for (int i = lane; i < TIR_BLOCK_UUIDS / 32 / 4; i += 32) reinterpret_cast<uint4 *>(s_seen)[i] = make_uint4(0, 0, 0, 0);
+          __syncwarp();
+        }
+      }
     }
-    any |= (r1 > r0);
     __syncthreads();
-  }
-  // winner of this block: greatest count, ties -> greatest rank (== greatest uuid)
-  unsigned long long bestv = 0;
-  for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) {
-    const uint32_t pair = s_cnt[i];
-    const uint32_t c0 = pair & 0xffffu, c1 = pair >> 16;
-    const uint64_t rank0 = (uint64_t)blk * TIR_BLOCK_UUIDS + 2 * i;
-    if (c0) bestv = max(bestv, ((unsigned long long)c0 << 32) | rank0);
-    if (c1) bestv = max(bestv, ((unsigned long long)c1 << 32) | (rank0 + 1));
-  }
-  for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
-  if (lane == 0) s_best[warp] = bestv;
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 1; i < TIR_MATCH_THREADS / 32; i++) bestv = max(bestv, s_best[i]);
-    if (bestv) atomicMax(best + q, bestv);
-  }
-  (void)any;
+    // winner of this block: greatest count, ties -> greatest rank (== greatest uuid)
+    unsigned long long bestv = 0;
+    for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) {
+      const uint32_t pair = s_cnt[i];
+      const uint32_t c0v = pair & 0xffffu, c1v = pair >> 16;
+      const uint64_t rank0 = (uint64_t)blk * TIR_BLOCK_UUIDS + 2 * i;
+      if (c0v) bestv = max(bestv, ((unsigned long long)c0v << 32) | rank0);
+      if (c1v) bestv = max(bestv, ((unsigned long long)c1v << 32) | (rank0 + 1));
+    }
+    for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
+    if (lane == 0) s_best[warp] = bestv;
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < TIR_MATCH_THREADS / 32; i++) bestv = max(bestv, s_best[i]);
+      if (bestv) atomicMax(best + q, bestv);
+    }
   } // items
   // the last CTA to finish turns the winners into hits
   __threadfence();
@@ -910,13 +943,18 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
                                  (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
-    const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 6);
+    const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);
+    if (!ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM));
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM));
+      ctx->match_smem_attr_set = true;
+    }
     if (coefs >= 2)
-      TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<2>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
+      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_match_kernel<2>, dim3(ggrid), dim3(TIR_MATCH_THREADS), TIR_GEN_SMEM, st, k1, uid, k2, bst, (const TirWindow *)d_win,
                                    (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
                                    (const uint8_t *)db->uuids.p, d_hits));
     else
-      TIR_CUDA(ctx, tir_launch_pdl(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), st, k1, uid, k2, bst, (const TirWindow *)d_win,
+      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), TIR_GEN_SMEM, st, k1, uid, k2, bst, (const TirWindow *)d_win,
                                    (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
                                    (const uint8_t *)db->uuids.p, d_hits));
     ctx->launches += 3;
