@@ -222,8 +222,7 @@ def match_bench(ctx, args, rank, world, device, dist):
         if world > 1:
             dist.all_gather_into_tensor(d_gather[: world * nq * 24], d_hits[: nq * 24])   # nq x 24 B per rank: the only cross-GPU traffic
             ctx.merge_hits_dev(d_gather.data_ptr(), world, nq, d_final.data_ptr())
-        else:
-            d_final[: nq * 24].copy_(d_hits[: nq * 24])
+        # (one GPU: the shard's winners are the answer, nothing to merge)
 
     def timed(coefs, nq, steps):
         for _ in range(3):
@@ -251,7 +250,7 @@ def match_bench(ctx, args, rank, world, device, dist):
     ms2, k_ms2, _ = timed(2, nq2, max(1, min(args.steps, 3)))
     # headline: coefs = 1, what the dialplan application passes (src/application_handler.c:180)
     ms, kernel_ms, launches = timed(1, Q, max(args.steps, 5))
-    hits = d_final.cpu().numpy().view(capi.HIT_DTYPE)
+    hits = (d_final if world > 1 else d_hits).cpu().numpy().view(capi.HIT_DTYPE)
     search_e2e = search_bench(ctx, args, rank, world, device, dist, Q)
     cpu_match = match_cpu_baseline(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     # verification on rank 0 / single GPU: brute-force restatement of the vote for a few queries
