@@ -92,6 +92,14 @@ def lib():
             L.tir_group_db_remove.argtypes = [vp, vp]
             L.tir_group_db_stats.argtypes = [vp, u64p, u64p]
             L.tir_group_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_p2p_create.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(vp)]
+            L.tir_p2p_handle.argtypes = [vp, vp]
+            L.tir_p2p_connect.argtypes = [vp, vp]
+            L.tir_p2p_connect_local.argtypes = [vp, vp]
+            L.tir_p2p_match_dev.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_p2p_error.argtypes = [vp, vp]
+            L.tir_p2p_destroy.argtypes = [vp]
+            L.tir_p2p_destroy.restype = None
             L.tir_batcher_start.argtypes = [vp, C.c_uint32, C.c_uint32]
             L.tir_batcher_stop.argtypes = [vp]
             L.tir_search_one.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int, vp]
@@ -321,6 +329,49 @@ class Context:
 def shard_of(uuid16, n_shards: int) -> int:
     u = np.ascontiguousarray(uuid16, dtype=np.uint8)
     return int(lib().tir_shard_of(_p(u), n_shards))
+
+
+class P2P:
+    """tir_p2p wrapper: the cross-GPU winner exchange of the sharded match over NVLink peer memory."""
+
+    def __init__(self, ctx, rank, world, max_queries):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._p = C.c_void_p()
+        ctx._chk(lib().tir_p2p_create(ctx._h, rank, world, max_queries, C.byref(self._p)))
+
+    def handle(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self.ctx._chk(lib().tir_p2p_handle(self._p, buf))
+        return bytes(buf)
+
+    def connect(self, handles):
+        """handles: the 64-byte handles of all ranks, in rank order (one process per GPU)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self.ctx._chk(lib().tir_p2p_connect(self._p, arr))
+
+    def connect_local(self, all_p2p):
+        """all_p2p: the P2P objects of all ranks of THIS process, in rank order."""
+        arr = (C.c_void_p * self.world)(*[x._p for x in all_p2p])
+        self.ctx._chk(lib().tir_p2p_connect_local(self._p, arr))
+
+    def match_dev(self, d_coef, frame_off, d_final, coefs=1, tolerance=0.001, low=-1, high=-1):
+        foff = np.ascontiguousarray(frame_off, dtype=np.uint64)
+        self.ctx._chk(lib().tir_p2p_match_dev(self._p, C.c_void_p(d_coef), _p(foff), foff.size - 1, coefs, float(tolerance), int(low), int(high),
+                                              C.c_void_p(d_final)))
+
+    def error(self) -> int:
+        e = C.c_uint32(0)
+        self.ctx._chk(lib().tir_p2p_error(self._p, C.byref(e)))
+        return int(e.value)
+
+    def close(self):
+        if getattr(self, "_p", None) and _lib is not None:
+            _lib.tir_p2p_destroy(self._p)
+        self._p = None
+
+    __del__ = close
 
 
 class Group:

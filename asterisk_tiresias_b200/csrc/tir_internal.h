@@ -75,6 +75,21 @@ int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, ui
 
 // tir_match.cu
 void tir_db_destroy(TirDb *db);
+// The cross-GPU exchange of the winners, fused into the kernels that produce them (tir_p2p.cu owns
+// the buffers): every hit is also stored into row `rank` of every peer's gather buffer, and the last
+// CTA of the producing kernel releases flag[rank] = epoch on every peer.  peer == nullptr: no exchange.
+struct TirP2PArgs {
+  unsigned char *const *peer; // device table: base of every rank's region
+  int rank, world;
+  uint32_t max_queries, epoch;
+  uint32_t *done; // CTA counter (left at 0)
+};
+#define TIR_P2P_MAX_RANKS 16
+#define TIR_P2P_HDR 256 // bytes of flags before the two gather buffers of a region
+int tir_match_dev_exchange(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
+                           double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_hits, const TirP2PArgs *p2p);
+// tir_p2p.cu: publish finished local hits (used when the shard is empty and no match kernel runs)
+int tir_p2p_publish_launch(tir_ctx *ctx, const tir_hit *d_hits, uint32_t n_queries, const TirP2PArgs &a);
 
 // tir_batcher.cpp
 void tir_batcher_destroy(TirBatcher *b);

@@ -526,22 +526,41 @@ __device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, u
   return false;
 }
 
-// rank -> uuid bytes, tir_hit{uuid, match_count, frame_count}; b = (count << 32 | rank), 0 = no row matched
+// rank -> uuid bytes, tir_hit{uuid, match_count, frame_count}; b = (count << 32 | rank), 0 = no row matched.
+// With an exchange (x.peer != nullptr) the hit also goes into row `rank` of every peer's gather buffer.
 __device__ __forceinline__ void tir_write_hit(unsigned long long b, const uint32_t *__restrict__ order,
                                               const uint8_t *__restrict__ uuids, const uint64_t *__restrict__ frame_off,
-                                              uint32_t q, tir_hit *__restrict__ hits) {
-  tir_hit h;
-  h.match_count = (int32_t)(b >> 32);
-  h.frame_count = (int32_t)(frame_off[q + 1] - frame_off[q]); // all frames, :286,403
+                                              uint32_t q, tir_hit *__restrict__ hits, const TirP2PArgs &x) {
+  union {
+    tir_hit h;
+    unsigned long long w[3];
+  } v;
+  static_assert(sizeof(tir_hit) == 24, "three 8-byte words");
+  v.h.match_count = (int32_t)(b >> 32);
+  v.h.frame_count = (int32_t)(frame_off[q + 1] - frame_off[q]); // all frames, :286,403
   if (b) {
     const uint8_t *u = uuids + (size_t)order[(uint32_t)b] * 16;
 #pragma unroll
-    for (int i = 0; i < 16; i++) h.uuid[i] = u[i];
+    for (int i = 0; i < 16; i++) v.h.uuid[i] = u[i];
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; i++) h.uuid[i] = 0;
+    for (int i = 0; i < 16; i++) v.h.uuid[i] = 0;
   }
-  hits[q] = h;
+  hits[q] = v.h;
+  if (x.peer) {
+    const size_t off = (size_t)TIR_P2P_HDR + ((size_t)(x.epoch & 1u) * x.world + x.rank) * x.max_queries * sizeof(tir_hit) + (size_t)q * sizeof(tir_hit);
+    for (int p = 0; p < x.world; p++) {
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(x.peer[p] + off);
+      dst[0] = v.w[0], dst[1] = v.w[1], dst[2] = v.w[2]; // NVLink peer stores
+    }
+  }
+}
+// after every hit of the batch has been stored (by the caller's last CTA, all threads): flag[rank] = epoch on every peer
+__device__ __forceinline__ void tir_exchange_release(const TirP2PArgs &x) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < (unsigned)x.world)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t *>(x.peer[threadIdx.x]) + x.rank), "r"(x.epoch) : "memory");
 }
 
 // One CTA per index block, everything in shared memory: (1) the 2K bound searches of the K distinct
@@ -680,11 +699,15 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
                                            TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
                                            const uint32_t *__restrict__ g_keys, const uint32_t *__restrict__ g_vals,
                                            const uint32_t *__restrict__ pat_list, const uint32_t *__restrict__ order,
-                                           const uint8_t *__restrict__ uuids, tir_hit *__restrict__ hits) {
+                                           const uint8_t *__restrict__ uuids, tir_hit *__restrict__ hits, const TirP2PArgs x) {
   TIR_PDL_PROLOGUE();
-  if (batch->use_general || batch->overflow) return;
+  // (CTA-uniform decision: overflow can be raised while this kernel runs, and the CTA meets at a barrier below)
+  __shared__ uint32_t s_general, s_last;
+  if (threadIdx.x == 0) s_general = batch->use_general | *reinterpret_cast<volatile uint32_t *>(&batch->overflow);
+  __syncthreads();
+  if (s_general) return; // the per-query kernel produces (and exchanges) the hits
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (q >= n_queries) return;
+  if (q < n_queries) {
   const uint32_t K = batch->n_distinct, nw = n_windows[q];
   const bool hashed = K > TIR_SHARED_DIRECT;
   const TirWindow *wq = windows + frame_off[q];
@@ -728,7 +751,20 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
     if (r1 && score) bestv = max(bestv, ((unsigned long long)score << 32) | (unsigned long long)(r1 - 1));
   }
   for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
-  if (lane == 0) tir_write_hit(bestv, order, uuids, frame_off, q, hits); // (the per-query kernel rewrites it if it runs)
+  if (lane == 0) tir_write_hit(bestv, order, uuids, frame_off, q, hits, x); // (the per-query kernel rewrites it if it runs)
+  } // q < n_queries
+  if (!x.peer) return;
+  // exchange: the last CTA to finish releases the flags -- unless the batch was handed to the
+  // per-query kernel meanwhile (a CTA that saw the hand-over above never counts itself; that kernel
+  // resets the counter)
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(x.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *x.done = 0;
+  if (*reinterpret_cast<volatile uint32_t *>(&batch->overflow)) return;
+  tir_exchange_release(x);
 }
 
 // ---- per-query path -------------------------------------------------------------------------------
@@ -759,7 +795,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
                      TirBatch *__restrict__ batch, const uint32_t *__restrict__ order, const uint8_t *__restrict__ uuids,
-                     tir_hit *__restrict__ hits) {
+                     tir_hit *__restrict__ hits, const TirP2PArgs x) {
   TIR_PDL_PROLOGUE();
   if (!(batch->use_general || batch->overflow)) return;
   extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word; then the warps' bitmaps
@@ -844,14 +880,18 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   if (!s_last) return;
   __threadfence();
   for (uint32_t q = tid; q < n_queries; q += TIR_MATCH_THREADS)
-    tir_write_hit(*reinterpret_cast<volatile unsigned long long *>(best + q), order, uuids, frame_off, q, hits);
+    tir_write_hit(*reinterpret_cast<volatile unsigned long long *>(best + q), order, uuids, frame_off, q, hits, x);
+  if (x.peer) {
+    if (tid == 0) *x.done = 0; // (resolve CTAs that counted themselves before the hand-over)
+    tir_exchange_release(x);
+  }
 }
 
 // empty table: every query gets {no uuid, 0, frame_count}
 __global__ void tir_no_hits_kernel(const uint64_t *__restrict__ frame_off, uint32_t n_queries, tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < n_queries) tir_write_hit(0ull, nullptr, nullptr, frame_off, q, hits);
+  if (q < n_queries) tir_write_hit(0ull, nullptr, nullptr, frame_off, q, hits, TirP2PArgs{nullptr, 0, 1, 0, 0, nullptr});
 }
 
 __global__ void tir_merge_hits_kernel(const tir_hit *__restrict__ gathered, uint32_t n_shards, uint32_t n_queries,
@@ -880,7 +920,9 @@ static int ensure_db(tir_ctx *ctx) {
 }
 
 static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef, const uint64_t *frame_off,
-                           uint32_t n_queries, int coefs, double tolerance, int ign_lo, int ign_hi, tir_hit *d_hits) {
+                           uint32_t n_queries, int coefs, double tolerance, int ign_lo, int ign_hi, tir_hit *d_hits,
+                           const TirP2PArgs *p2p = nullptr) {
+  const TirP2PArgs x = p2p ? *p2p : TirP2PArgs{nullptr, 0, 1, 0, 0, nullptr};
   if (coefs < 1 || coefs > TIR_N_COEFS) return tir_fail(ctx, TIR_ERR_ARG, "Wrong coefs count. max[%d], coefs[%d]", TIR_N_COEFS, coefs);
   if (!ctx->db) return tir_fail(ctx, TIR_ERR_STATE, "no fingerprint DB loaded");
   if (n_queries == 0) return TIR_OK;
@@ -940,7 +982,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
                                  (const uint32_t *)d_nw, d_foff, n_queries, d_batch, (const uint32_t *)d_maxr,
                                  (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist,
-                                 (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits));
+                                 (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits, x));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);
@@ -952,11 +994,11 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     if (coefs >= 2)
       TIR_CUDA(ctx, tir_launch_pdl_smem(tir_match_kernel<2>, dim3(ggrid), dim3(TIR_MATCH_THREADS), TIR_GEN_SMEM, st, k1, uid, k2, bst, (const TirWindow *)d_win,
                                    (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
-                                   (const uint8_t *)db->uuids.p, d_hits));
+                                   (const uint8_t *)db->uuids.p, d_hits, x));
     else
       TIR_CUDA(ctx, tir_launch_pdl_smem(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), TIR_GEN_SMEM, st, k1, uid, k2, bst, (const TirWindow *)d_win,
                                    (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
-                                   (const uint8_t *)db->uuids.p, d_hits));
+                                   (const uint8_t *)db->uuids.p, d_hits, x));
     ctx->launches += 3;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
@@ -965,6 +1007,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   } else {
     TIR_CUDA(ctx, tir_launch_pdl(tir_no_hits_kernel, dim3((n_queries + 127) / 128), dim3(128), st, d_foff, n_queries, d_hits));
     ctx->launches++;
+    if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x))) return rc; // an empty shard still answers
   }
   TIR_CUDA(ctx, cudaGetLastError());
   return TIR_OK;
@@ -1136,6 +1179,17 @@ int tir_match_dev(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, 
   return match_on_device(ctx, nullptr, d_coef, frame_off, n_queries, coefs, tolerance, freq_ignore_low, freq_ignore_high,
                          d_hits);
 }
+
+} // extern "C"
+int tir_match_dev_exchange(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
+                           double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_hits, const TirP2PArgs *p2p) {
+  if (!ctx || !frame_off || !d_hits || !d_coef) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return match_on_device(ctx, nullptr, d_coef, frame_off, n_queries, coefs, tolerance, freq_ignore_low, freq_ignore_high,
+                         d_hits, p2p);
+}
+extern "C" {
 
 int tir_search(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs, double tolerance,
                int freq_ignore_low, int freq_ignore_high, tir_hit *hits) {

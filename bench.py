@@ -217,16 +217,44 @@ def match_bench(ctx, args, rank, world, device, dist):
     d_gather = torch.zeros(world * Q * 24, dtype=torch.uint8, device=device)
     d_final = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
 
-    def step(coefs=1, nq=Q):
+    # N > 1: the per-query winners (nq x 24 B per rank) are the only cross-GPU traffic.  Default: the
+    # library's own exchange over NVLink peer memory (csrc/tir_p2p.cu: P2P stores into every peer's
+    # gather buffer + flags, no collective call); --match-exchange nccl: all_gather + merge kernel.
+    p2p = None
+    exchange = "none (one GPU)"
+    if world > 1:
+        exchange = "nccl all_gather + tir_merge_hits_dev"
+        if args.match_exchange == "p2p":
+            try:
+                p2p = capi.P2P(ctx, rank, world, Q)
+                mine = torch.frombuffer(bytearray(p2p.handle()), dtype=torch.uint8).to(device)
+                allh = torch.zeros(world * 64, dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(allh, mine)
+                blob = allh.cpu().numpy().tobytes()
+                p2p.connect([blob[64 * r: 64 * (r + 1)] for r in range(world)])
+                ok = torch.ones(1, device=device)
+            except Exception as e:   # e.g. no peer access between the devices: say so and use NCCL
+                sys.stderr.write(f"[rank {rank}] tir_p2p unavailable ({e}); NCCL exchange\n")
+                p2p, ok = None, torch.zeros(1, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1.0:
+                p2p = None
+            else:
+                exchange = "tir_p2p (NVLink peer stores + flags, no collective call)"
+
+    def step(coefs=1, nq=Q, use_p2p=True):
+        if p2p is not None and use_p2p:
+            p2p.match_dev(coef.data_ptr(), foff[: nq + 1], d_final.data_ptr(), coefs, 0.001)
+            return
         ctx.match_dev(coef.data_ptr(), foff[: nq + 1], d_hits.data_ptr(), coefs, 0.001)
         if world > 1:
-            dist.all_gather_into_tensor(d_gather[: world * nq * 24], d_hits[: nq * 24])   # nq x 24 B per rank: the only cross-GPU traffic
+            dist.all_gather_into_tensor(d_gather[: world * nq * 24], d_hits[: nq * 24])
             ctx.merge_hits_dev(d_gather.data_ptr(), world, nq, d_final.data_ptr())
         # (one GPU: the shard's winners are the answer, nothing to merge)
 
-    def timed(coefs, nq, steps):
+    def timed(coefs, nq, steps, use_p2p=True):
         for _ in range(3):
-            step(coefs, nq)
+            step(coefs, nq, use_p2p)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -234,7 +262,7 @@ def match_bench(ctx, args, rank, world, device, dist):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(coefs, nq)
+            step(coefs, nq, use_p2p)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -249,7 +277,14 @@ def match_bench(ctx, args, rank, world, device, dist):
     nq2 = max(1, min(Q, args.match_queries_coefs2))
     ms2, k_ms2, _ = timed(2, nq2, max(1, min(args.steps, 3)))
     # headline: coefs = 1, what the dialplan application passes (src/application_handler.c:180)
+    nccl_ms = None
+    if p2p is not None:   # the same batch through NCCL, for comparison (its winners are checked against the p2p ones)
+        nccl_ms, _, _ = timed(1, Q, max(args.steps, 5), use_p2p=False)
+        nccl_hits = d_final.clone()
     ms, kernel_ms, launches = timed(1, Q, max(args.steps, 5))
+    if p2p is not None:
+        same = bool(torch.equal(nccl_hits, d_final)) and p2p.error() == 0
+        exchange += f"; identical to the NCCL exchange: {same}"
     hits = (d_final if world > 1 else d_hits).cpu().numpy().view(capi.HIT_DTYPE)
     search_e2e = search_bench(ctx, args, rank, world, device, dist, Q)
     cpu_match = match_cpu_baseline(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
@@ -269,6 +304,7 @@ def match_bench(ctx, args, rank, world, device, dist):
            "queries_per_batch": Q, "frames_per_query": F_q, "db_fingerprints_total": total_fps, "db_frames_per_fingerprint": F_db,
            "db_rows_this_rank": rows, "index_build_s": build_s, "coefs": 1, "tolerance": 0.001, "kernel_ms_rank0": kernel_ms,
            "launches_per_batch": launches, "found": int((hits["match_count"] > 0).sum()),
+           "exchange": exchange, "nccl_exchange_ms_per_batch": nccl_ms,
            "path": "shared-window scan (distinct windows of the batch scanned once; DESIGN.md 4.3)",
            "per_query_path_coefs2": {"value": nq2 / (ms2 * 1e-3), "unit": "queries/s", "ms_per_batch": ms2, "queries_per_batch": nq2,
                                      "kernel_ms_rank0": k_ms2, "coefs": 2, "tolerance": 0.001},
@@ -413,6 +449,8 @@ def main():
     ap.add_argument("--clips", type=int, default=10000)
     ap.add_argument("--match-fps", type=int, default=0, help="fingerprints (uuids) in the match DB, total over ranks; 0 = 10M")
     ap.add_argument("--match-queries", type=int, default=1000)
+    ap.add_argument("--match-exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: how the per-query winners cross the GPUs (p2p = the library's NVLink peer-memory exchange)")
     ap.add_argument("--match-queries-coefs2", type=int, default=100, help="queries of the coefs=2 (per-query path) leg")
     ap.add_argument("--channels", type=int, default=1000, help="concurrent channel threads of the config[4] leg")
     ap.add_argument("--channels-db-fps", type=int, default=1_000_000)

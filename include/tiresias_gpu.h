@@ -200,6 +200,24 @@ void tir_stream_close(tir_stream *s);
 int tir_merge_hits_dev(tir_ctx *ctx, const tir_hit *d_gathered, uint32_t n_shards, uint32_t n_queries,
                        tir_hit *d_out);
 
+/* The same exchange WITHOUT a collective library: every rank stores its winners straight into every
+ * peer's gather buffer over NVLink peer memory, raises a per-peer flag carrying the batch number, and
+ * folds the candidates of all ranks once their flags have arrived (csrc/tir_p2p.cu).  One process per
+ * GPU: create, exchange the 64-byte handles (tir_p2p_handle) through the launcher, tir_p2p_connect
+ * with all of them in rank order.  Several contexts of one process: tir_p2p_connect_local.
+ * tir_p2p_match_dev = tir_match_dev on the local shard + that exchange; d_final receives the global
+ * winners.  SPMD: all ranks call it the same number of times.  tir_p2p_error reports (after a stream
+ * synchronise) the batch at which a merge gave up waiting for a peer, 0 if none. */
+typedef struct tir_p2p tir_p2p;
+int tir_p2p_create(tir_ctx *ctx, int rank, int world, uint32_t max_queries, tir_p2p **out);
+int tir_p2p_handle(tir_p2p *p, unsigned char handle[64]);
+int tir_p2p_connect(tir_p2p *p, const unsigned char *handles /* world x 64 bytes, rank order */);
+int tir_p2p_connect_local(tir_p2p *p, tir_p2p *const *all /* world entries, rank order */);
+int tir_p2p_match_dev(tir_p2p *p, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
+                      double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_final);
+int tir_p2p_error(tir_p2p *p, uint32_t *epoch_out);
+void tir_p2p_destroy(tir_p2p *p);
+
 /* The same inside ONE process (an Asterisk module cannot be launched one process per GPU): a group
  * owns one context per device, shards the table by uuid over them, and a search extracts on the
  * first device, hands the coefficients to the others over NVLink (cudaMemcpyPeerAsync), matches on
