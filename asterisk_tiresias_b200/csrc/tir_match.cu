@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     const uint64_t f = f0 + i;
     double y1, y2;
     if (FROM_COEF) {
-      y1 = tir_coef_to_y(coef[f * 2]), y2 = tir_coef_to_y(coef[f * 2 + 1]);
+      y1 = tir_coef_to_y(coef[f * 2]);
+      y2 = mp.coefs >= 2 ? tir_coef_to_y(coef[f * 2 + 1]) : 0.0; // max2 is not looked at with coefs == 1 (:321)
     } else {
       y1 = y[f * 2], y2 = y[f * 2 + 1];
     }
