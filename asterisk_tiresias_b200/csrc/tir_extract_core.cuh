@@ -307,17 +307,21 @@ TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp,
   const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
   if (nr == 0) return;
   const float *m = norm + TIR_NORM_IDX(mp.seg_bin0[seg], f);
-  const float2 *wp = w2 + mp.seg_woff[seg];
+  const float4 *wp = reinterpret_cast<const float4 *>(w2 + mp.seg_woff[seg]); // two bins' records per load
   TirP2 acc = tir_pbc(0.f);
   int n = run_bins[r0], fe = run_emit[r0];
   for (int r = 0; r < nr; r++) {
     const int n_next = run_bins[r0 + r + 1], fe_next = run_emit[r0 + r + 1]; // the list ends with a sentinel
-#pragma unroll 4
-    for (int b = 0; b < n; b++) {
-      const float2 wv = wp[b];
-      acc = tir_padd(acc, tir_pmulx(tir_pbc(m[32 * b]), tir_pmk(wv.x, wv.y), nz));
+    // bins in pairs; an odd run's last pair holds a zero-weight record (tir_tables.cpp) and sweeps the
+    // next bin with it: acc + (+-0) is exact, and the magnitude buffer is finite everywhere
+    const int np = (n + 1) >> 1;
+#pragma unroll 2
+    for (int p = 0; p < np; p++) {
+      const float4 wv = wp[p];
+      acc = tir_padd(acc, tir_pmulx(tir_pbc(m[64 * p]), tir_pmk(wv.x, wv.y), nz));
+      acc = tir_padd(acc, tir_pmulx(tir_pbc(m[64 * p + 32]), tir_pmk(wv.z, wv.w), nz));
     }
-    m += 32 * n, wp += n;
+    m += 32 * n, wp += np;
     if (fe & 1) lg[fe * 32 + f] = acc.hi, acc.hi = 0.f;
     else lg[fe * 32 + f] = acc.lo, acc.lo = 0.f;
     n = n_next, fe = fe_next;

@@ -221,25 +221,28 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
       continue;
     }
     const int b0 = first[live[ia]], b1 = last[live[ib - 1]];
-    if (nw2 + (b1 - b0 + 1) > TIR_MAX_W2 || nruns + (ib - ia) + 1 > TIR_MAX_RUNS) return false;
+    nw2 += nw2 & 1; // every run's weight records start 16-byte aligned: the sweep loads two bins' records at once
+    if (nw2 + (b1 - b0 + 1) + (ib - ia) + 1 > TIR_MAX_W2 || nruns + (ib - ia) + 1 > TIR_MAX_RUNS) return false;
     mp.seg_bin0[seg] = (int16_t)b0;
+    mp.seg_woff[seg] = (int16_t)nw2;
     // magnitudes arrive as 2^33 * |X[k]| (FFT scaled by 2, sqrt by 2^32); power-of-two scaling is exact
     const float sc = 1.0f / 8589934592.0f;
-    for (int bin = b0; bin <= b1; bin++) {
-      float2 w{0.f, 0.f};
-      for (int i = ia; i < ib; i++) {
-        const int f = live[i];
-        if (bin < first[f] || bin > last[f]) continue;
-        const float v = o.filters[(size_t)f * o.L + bin] * sc;
-        if (f & 1) w.y = v; else w.x = v;
-      }
-      mp.w2[nw2++] = w;
-    }
     int done = b0; // bins [b0, done) are already covered by earlier runs
     for (int i = ia; i < ib; i++) {
-      const int f = live[i];
-      mp.run_bins[nruns] = (int16_t)(last[f] + 1 - done), mp.run_emit[nruns] = (int8_t)f;
-      done = last[f] + 1, nruns++;
+      const int fr = live[i];
+      for (int bin = done; bin <= last[fr]; bin++) {
+        float2 w{0.f, 0.f};
+        for (int k = ia; k < ib; k++) {
+          const int f = live[k];
+          if (bin < first[f] || bin > last[f]) continue;
+          const float v = o.filters[(size_t)f * o.L + bin] * sc;
+          if (f & 1) w.y = v; else w.x = v;
+        }
+        mp.w2[nw2++] = w;
+      }
+      if (nw2 & 1) mp.w2[nw2++] = float2{0.f, 0.f}; // pad: an odd run sweeps one more bin with zero weights (adds +0: exact)
+      mp.run_bins[nruns] = (int16_t)(last[fr] + 1 - done), mp.run_emit[nruns] = (int8_t)fr;
+      done = last[fr] + 1, nruns++;
     }
     mp.run_bins[nruns] = 0, mp.run_emit[nruns] = 0, nruns++; // sentinel: the sweep fetches one run ahead
     mp.seg_nruns[seg] = (int16_t)(ib - ia);
