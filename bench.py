@@ -534,10 +534,34 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = F * BYTES_PER_FRAME / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 530.2 * F,   # ncu dram__bytes_read+write per launch, scaled from profiles/r1_extract_ncu_full_g.txt (530.2 B/frame)
+                "traffic": 530.2 * F,   # ncu dram__bytes_read+write per launch, scaled from profiles/r1_extract_ncu_full_h.txt (529.6-530.2 B/frame)
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "tir_extract_kernel<512>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": F * BYTES_PER_FRAME,
                 "note": "issue/latency-bound SIMT kernel on packed f32x2 instructions (float32 FFT reproduced operation for operation; FP32-pipe floor of the DAG = 24.7% of the HBM peak); see DESIGN.md 2.3 and profiles/"}
+
+    # SURVEY 8d, config 2 "3 s variant": the same samples cut into ten times as many 3 s clips (94 frames
+    # each, the last tile of every clip 30/32 full) -- exposes tile-tail and per-clip bookkeeping costs
+    short_clips = None
+    try:
+        n3, s3 = n_clips * 10, N_SAMP // 10
+        off3 = np.arange(n3 + 1, dtype=np.uint64) * s3
+        F3 = n3 * ((s3 + HOP - 1) // HOP)
+        d_coef3 = torch.empty((F3, 2), dtype=torch.float32, device=device)
+        d_vq3 = torch.empty((F3, 2), dtype=torch.int32, device=device)
+        for _ in range(6):   # the metadata of 10x as many clips outgrows every slot of the pinned staging ring once
+            ctx.extract_dev(d_pcm.data_ptr(), off3, d_coef3.data_ptr(), d_vq3.data_ptr())
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            ctx.extract_dev(d_pcm.data_ptr(), off3, d_coef3.data_ptr(), d_vq3.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1) / args.steps
+        short_clips = {"clips_per_gpu": n3, "seconds_per_clip": SECONDS / 10, "frames_per_clip": int(F3 // n3),
+                       "value_this_rank": n3 * (SECONDS / 10) / (ms3 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms3}
+        del d_coef3, d_vq3
+    except Exception as e:   # a secondary figure must not take the headline down
+        short_clips = {"error": str(e)}
 
     # parity is reported from the cpu_baseline leg below: the oracle's output for the clips it times
     # is compared with what the timed GPU run produced for the same clips (no other use of oracle/)
@@ -675,7 +699,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_clips), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "frames_per_second": world * F / (ms_step * 1e-3), "match": match, "concurrent_channels": concurrent,
+            "frames_per_second": world * F / (ms_step * 1e-3), "short_clips": short_clips, "match": match, "concurrent_channels": concurrent,
         }
         emit(line)
     if world > 1:
