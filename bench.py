@@ -313,6 +313,11 @@ def match_bench(ctx, args, rank, world, device, dist):
            "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None,
                         "unit": "GB/s", "algorithmic_bytes_per_batch_this_rank": alg,
                         "note": "SURVEY 8d charge F_q*8 + sum_k(16 + 8*R_k) + 24 per QUERY; the shared-window path reads each distinct window once per BATCH (6 B per row in it; the per-uuid patterns live in shared memory), so the charged figure can exceed the HBM peak"}}
+    if p2p is not None:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()      # no rank frees its region while a peer may still store into it
+        p2p.close()
     del uu, v1, v2
     return res
 
