@@ -93,6 +93,9 @@ def lib():
             L.tir_group_db_stats.argtypes = [vp, u64p, u64p]
             L.tir_group_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp]
             L.tir_p2p_create.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(vp)]
+            L.tir_p2p_create2.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(vp)]
+            L.tir_p2p_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_uint32, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp]
+            L.tir_p2p_reserve.argtypes = [vp, C.c_uint64]
             L.tir_p2p_handle.argtypes = [vp, vp]
             L.tir_p2p_connect.argtypes = [vp, vp]
             L.tir_p2p_connect_local.argtypes = [vp, vp]
@@ -334,10 +337,11 @@ def shard_of(uuid16, n_shards: int) -> int:
 class P2P:
     """tir_p2p wrapper: the cross-GPU winner exchange of the sharded match over NVLink peer memory."""
 
-    def __init__(self, ctx, rank, world, max_queries):
+    def __init__(self, ctx, rank, world, max_queries, max_frames=0):
+        """max_frames > 0 also reserves the coefficient buffers of the sharded search (search())."""
         self.ctx, self.rank, self.world = ctx, rank, world
         self._p = C.c_void_p()
-        ctx._chk(lib().tir_p2p_create(ctx._h, rank, world, max_queries, C.byref(self._p)))
+        ctx._chk(lib().tir_p2p_create2(ctx._h, rank, world, max_queries, int(max_frames), C.byref(self._p)))
 
     def handle(self) -> bytes:
         buf = (C.c_ubyte * 64)()
@@ -360,6 +364,28 @@ class P2P:
         foff = np.ascontiguousarray(frame_off, dtype=np.uint64)
         self.ctx._chk(lib().tir_p2p_match_dev(self._p, C.c_void_p(d_coef), _p(foff), foff.size - 1, coefs, float(tolerance), int(low), int(high),
                                               C.c_void_p(d_final)))
+
+    def reserve(self, max_local_samples):
+        """pre-size the context's scratch (needed when one host thread drives several ranks)"""
+        self.ctx._chk(lib().tir_p2p_reserve(self._p, int(max_local_samples)))
+
+    def search(self, pcm, clip_off, first_query, all_frame_off, coefs=1, tolerance=0.001, low=-1, high=-1, d_final=None,
+               want_hits=True, pcm_ptr=None, hits_ptr=None):
+        """tir_p2p_search: this rank's slice of the batch's clips (host PCM16; or pcm_ptr = address of a pinned
+        buffer) -> the winners of ALL queries.  Returns the hits array (or None with want_hits=False / hits_ptr)."""
+        off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        foff = np.ascontiguousarray(all_frame_off, dtype=np.uint64)
+        n_local, n_total = max(off.size - 1, 0), foff.size - 1
+        if pcm_ptr is None:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+            pcm_ptr = pcm.ctypes.data
+        hits = None
+        if hits_ptr is None and want_hits:
+            hits = np.zeros(n_total, dtype=HIT_DTYPE)
+            hits_ptr = hits.ctypes.data
+        self.ctx._chk(lib().tir_p2p_search(self._p, C.c_void_p(pcm_ptr), _p(off), n_local, int(first_query), _p(foff), n_total, coefs,
+                                           float(tolerance), int(low), int(high), C.c_void_p(hits_ptr or 0), C.c_void_p(d_final or 0)))
+        return hits
 
     def error(self) -> int:
         e = C.c_uint32(0)

@@ -13,7 +13,10 @@ int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
-  if (ctx) ctx->err = buf;
+  if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    ctx->err = buf;
+  }
   return code;
 }
 
@@ -157,7 +160,15 @@ void tir_close(tir_ctx *ctx) {
   delete ctx;
 }
 
-const char *tir_last_error(tir_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+// The text is copied into a buffer owned by the calling thread: it stays valid until the same thread
+// asks again, whatever the other threads of the context do meanwhile.
+const char *tir_last_error(tir_ctx *ctx) {
+  if (!ctx) return "null context";
+  static thread_local std::string mine;
+  std::lock_guard<std::mutex> lk(ctx->err_mu);
+  mine = ctx->err;
+  return mine.c_str();
+}
 
 uint64_t tir_launch_count(tir_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "tir_internal.h"
+#include "tir_p2p_dev.cuh"
 
 // one tile = T consecutive frames of one clip
 struct __align__(16) TirTile {
@@ -31,6 +32,7 @@ struct TirExtractArgs {
   uint32_t pcm_aligned8; // base pointer is 8-byte aligned
   float2 neg_zero;       // (-0, -0): see tir_pmulx
   uint32_t *tile_counter; // zeroed before the launch: tiles beyond the first two of every CTA are claimed dynamically
+  TirCoefX cx;            // sharded search: coefficients also go to every rank's buffer (cx.peer == nullptr: off)
 };
 
 __device__ const double2 k_logf_tab[16] = TIR_LOGF_TAB_INIT;
@@ -165,6 +167,10 @@ __device__ __forceinline__ void tir_emit_coefs(const float *lg, const TirMelPara
     const uint64_t o = (td.out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
     if (a.coef) a.coef[o] = c;
     if (a.vq) a.vq[o] = v;
+    if (a.cx.peer) { // NVLink peer stores: 4 bytes per coefficient and rank, issued as P4 produces them
+      const unsigned long long g = (a.cx.frame_base + td.out0 + (uint64_t)lane) * (uint64_t)mp.n_coefs + (uint64_t)warp;
+      for (int p = 0; p < a.cx.world; p++) reinterpret_cast<float *>(a.cx.peer[p] + a.cx.off)[g] = c;
+    }
   }
 }
 
@@ -249,6 +255,16 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   TIR_TRACE_END();
   __syncthreads();
   if (warp < mp.n_coefs) tir_emit_coefs(sm.lg[b], mp, a, cur, warp, lane);
+  if (a.cx.peer) { // the last CTA to finish tells every rank that this rank's coefficients are in place
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && atomicAdd(a.cx.done, 1u) == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < a.cx.world; p++)
+        tir_st_release_sys(reinterpret_cast<uint32_t *>(a.cx.peer[p]) + TIR_P2P_COEF_FLAG0 + a.cx.rank, a.cx.epoch);
+      *a.cx.done = 0;
+    }
+  }
 }
 
 // G.711 mu-law -> PCM16 (what a channel's native ulaw frames decode to; same table as Asterisk's
@@ -340,7 +356,7 @@ size_t tir_extract_smem_bytes(int win) {
 
 template <int WIN>
 static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,
-                                float *d_coef, int32_t *d_vq, uint64_t *n_frames) {
+                                float *d_coef, int32_t *d_vq, uint64_t *n_frames, const TirCoefX *cx) {
   using C = TirCfg<WIN>;
   // ---- host-side tile bookkeeping (metadata only) -> one pinned staging buffer -> device
   const size_t nc1 = (size_t)n_clips + 1;
@@ -392,6 +408,7 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
   if ((rc = tir_reserve(ctx, ctx->d_counter, 256))) return rc;
   TIR_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(uint32_t), ctx->stream));
   a.tile_counter = (uint32_t *)ctx->d_counter.p;
+  a.cx = cx ? *cx : TirCoefX{nullptr, 0, 0, 1, 0, nullptr, 0};
 
   const size_t smem = sizeof(TirSmem<WIN>);
   if (!ctx->smem_attr_set) { // per context: the attribute belongs to the device the context is on
@@ -426,9 +443,9 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
 }
 
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
-                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames) {
+                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames, const TirCoefX *cx) {
   (void)total_samples;
-  if (ctx->cfg.win == 512) return tir_extract_launch_t<512>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames);
-  if (ctx->cfg.win == 1024) return tir_extract_launch_t<1024>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames);
+  if (ctx->cfg.win == 512) return tir_extract_launch_t<512>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, cx);
+  if (ctx->cfg.win == 1024) return tir_extract_launch_t<1024>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, cx);
   return tir_fail(ctx, TIR_ERR_ARG, "extraction kernels exist for win 512 / hop 256 and win 1024 / hop 512");
 }

@@ -12,7 +12,12 @@
 #include "tir_tables.h"
 
 struct TirDb;      // tir_match.cu
-struct TirBatcher; // tir_batcher.cpp
+struct TirBatcher; // tir_match.cu: pre-size the scratch of a search (no allocation / free inside the calls afterwards) and
+// rebuild a dirty index now rather than inside the next match
+int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_samples);
+int tir_db_ensure_index(tir_ctx *ctx);
+
+// tir_batcher.cpp
 
 struct DevBuf {
   void *p = nullptr;
@@ -26,6 +31,7 @@ struct tir_ctx {
   bool own_stream = false;
   cudaStream_t s_in = nullptr, s_out = nullptr; // copy-in / copy-out queues of tir_extract's pipeline
   std::mutex mu;
+  std::mutex err_mu; // guards `err` alone: tir_fail is called with and without `mu` held, from any thread
   std::string err;
   uint64_t launches = 0;
   bool profiling = false;
@@ -67,8 +73,20 @@ int tir_stage_acquire(tir_ctx *ctx, size_t bytes, void **p, int *slot);
 int tir_stage_release(tir_ctx *ctx, int slot);
 
 // tir_extract.cu
+// Sharded search: the coefficients of a rank's own query clips are stored, as P4 computes them, into
+// every rank's coefficient buffer over NVLink peer memory (frame index = frame_base + local frame), and
+// the kernel's last CTA releases flag[TIR_P2P_COEF_FLAG0 + rank] = epoch on every peer.  peer == nullptr:
+// no exchange.
+struct TirCoefX {
+  unsigned char *const *peer; // device table: base of every rank's region
+  unsigned long long off;     // byte offset of this batch's coefficient buffer inside a region
+  int rank, world;
+  uint32_t epoch;
+  uint32_t *done;             // CTA counter (left at 0)
+  unsigned long long frame_base;
+};
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
-                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames);
+                       uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames, const TirCoefX *cx = nullptr);
 size_t tir_extract_smem_bytes(int win);
 int tir_selftest_launch(tir_ctx *ctx, uint64_t *sqrt_mismatches, uint32_t first, uint32_t step, uint32_t count, float *log10f_out);
 int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, uint64_t n);
@@ -78,18 +96,32 @@ void tir_db_destroy(TirDb *db);
 // The cross-GPU exchange of the winners, fused into the kernels that produce them (tir_p2p.cu owns
 // the buffers): every hit is also stored into row `rank` of every peer's gather buffer, and the last
 // CTA of the producing kernel releases flag[rank] = epoch on every peer.  peer == nullptr: no exchange.
+// With `final_out` set the last CTA goes on to acquire the flags of all ranks and folds the candidates
+// into final_out itself (tir_p2p_dev.cuh): no separate merge launch.
 struct TirP2PArgs {
   unsigned char *const *peer; // device table: base of every rank's region
   int rank, world;
   uint32_t max_queries, epoch;
   uint32_t *done; // CTA counter (left at 0)
+  unsigned char *local = nullptr; // this rank's own region
+  tir_hit *final_out = nullptr;   // [n_queries] global winners
 };
 #define TIR_P2P_MAX_RANKS 16
-#define TIR_P2P_HDR 256 // bytes of flags before the two gather buffers of a region
+#define TIR_P2P_HDR 256 // bytes of flags before the two gather buffers of a region:
+                        // u32[0..15] winners flags | u32[16] error word | u32[32..47] coefficient flags
+#define TIR_P2P_ERR_WORD 16
+#define TIR_P2P_COEF_FLAG0 32
 int tir_match_dev_exchange(tir_ctx *ctx, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
                            double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_hits, const TirP2PArgs *p2p);
 // tir_p2p.cu: publish finished local hits (used when the shard is empty and no match kernel runs)
 int tir_p2p_publish_launch(tir_ctx *ctx, const tir_hit *d_hits, uint32_t n_queries, const TirP2PArgs &a);
+// ... and fold the ranks' candidates into a.final_out in a launch of its own (the match kernels do it in their last CTA)
+int tir_p2p_merge_launch(tir_ctx *ctx, const TirP2PArgs &a, uint32_t n_queries);
+
+// tir_match.cu: pre-size the scratch of a search (no allocation / free inside the calls afterwards) and
+// rebuild a dirty index now rather than inside the next match
+int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_samples);
+int tir_db_ensure_index(tir_ctx *ctx);
 
 // tir_batcher.cpp
 void tir_batcher_destroy(TirBatcher *b);

@@ -30,6 +30,7 @@
 #include <unordered_map>
 
 #include "tir_internal.h"
+#include "tir_p2p_dev.cuh"
 
 // Programmatic dependent launch: the query pipeline is seven small kernels whose launch gaps cost as
 // much as the kernels.  Each kernel of the chain lets its successor be scheduled at once
@@ -370,9 +371,16 @@ __device__ __forceinline__ uint32_t tir_pat_hash(uint32_t p) { return (p * 0x9e3
 
 // One CTA per query: windows of all frames, identical windows folded into one with a weight
 // (a uuid gets one vote per frame, so frames with the same window vote identically).
+// coefs == 1 -- what the dialplan passes -- : the window of a frame is a function of the INTEGER
+// trunc(max1) (src/fp_handler.c:290), so folding is a histogram over that integer: one shared-memory
+// atomic per frame, the first frame to touch a bin appends it to the query's leader list, and the
+// "%f" bounds are computed once per leader.  O(frames) whatever the length of the recording.
+// coefs == 2: the max2 bounds are real numbers, two frames practically never share a window; every
+// frame that passes the ignore test is its own window of weight 1 (the votes are the same either way:
+// folding only saves work).
 // FROM_COEF: y is recomputed from the float mfcc coefficients as the reference does (:651).
 #define TIR_QPREP_THREADS 128
-#define TIR_QPREP_SMEM_FRAMES 1024 // queries up to this many frames are folded in shared memory
+#define TIR_QPREP_BINS 1024 // trunc(max1) in [-512, 512): every value 10*log10|float| can take, and then some
 
 template <bool FROM_COEF>
 __global__ void __launch_bounds__(TIR_QPREP_THREADS)
@@ -384,69 +392,89 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
   const uint64_t f0 = frame_off[q], f1 = frame_off[q + 1];
   const uint32_t nf = (uint32_t)(f1 - f0);
   TirWindow *wq = windows + f0;
-  __shared__ TirWindow s_w[TIR_QPREP_SMEM_FRAMES];
-  __shared__ uint32_t s_warp[TIR_QPREP_THREADS / 32], s_base, s_last;
-  TirWindow *ws = nf <= TIR_QPREP_SMEM_FRAMES ? s_w : wq; // long queries work in place in global memory
-  // pass 1: every frame computes its own window (weight 0 = skipped)
-  for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
-    const uint64_t f = f0 + i;
-    double y1, y2;
-    if (FROM_COEF) {
-      y1 = tir_coef_to_y(coef[f * 2]);
-      y2 = mp.coefs >= 2 ? tir_coef_to_y(coef[f * 2 + 1]) : 0.0; // max2 is not looked at with coefs == 1 (:321)
-    } else {
-      y1 = y[f * 2], y2 = y[f * 2 + 1];
-    }
-    TirWindow w;
-    if (!tir_frame_window(y1, y2, mp, w)) w.lo1 = 0, w.hi1 = -1, w.lo2 = 0, w.hi2 = -1, w.weight = 0, w.pad = 0;
-    ws[i] = w;
-  }
-  if (threadIdx.x == 0) s_base = 0;
+  __shared__ uint32_t s_hist[TIR_QPREP_BINS];
+  __shared__ uint16_t s_lead[TIR_QPREP_BINS];
+  __shared__ uint32_t s_warp[TIR_QPREP_THREADS / 32], s_base, s_nlead, s_last;
+  for (int i = threadIdx.x; i < TIR_QPREP_BINS; i += blockDim.x) s_hist[i] = 0;
+  if (threadIdx.x == 0) s_base = 0, s_nlead = 0;
   __syncthreads();
-  // pass 2: every frame looks for the first frame with its window (itself: a leader) and adds one to
-  // that frame's multiplicity (kept in .pad; 0 = not a leader, or a skipped frame)
-  for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
-    const TirWindow w = ws[i];
-    if (w.weight == 0) continue;
-    uint32_t j = 0;
-    for (; j < i; j++) {
-      const TirWindow o = ws[j];
-      if (o.weight != 0 && o.lo1 == w.lo1 && o.hi1 == w.hi1 && o.lo2 == w.lo2 && o.hi2 == w.hi2) break;
-    }
-    atomicAdd(&ws[j].pad, 1u);
-  }
-  __syncthreads();
-  // pass 3: leaders to the front of the query's slice, in frame order (ballot prefix per chunk of
-  // blockDim frames).  In the in-place case a chunk's writes land at indices <= its first frame, which
-  // were consumed by earlier chunks; its own entries are read before the barrier.
   bool claimed = false;
-  for (uint32_t c0 = 0; c0 < nf; c0 += blockDim.x) {
-    const uint32_t i = c0 + threadIdx.x;
-    TirWindow w;
-    bool leader = false;
-    if (i < nf) {
-      w = ws[i];
-      leader = w.pad != 0;
+  if (mp.coefs == 1) {
+    // pass 1: histogram of trunc(max1) over the frames that pass the ignore test.  A value outside the
+    // histogram (only a caller-supplied y can be: 10*log10|float| lies in [-449, 386]) is left to the
+    // serial tail below.
+    bool far = false;
+    for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) {
+      const uint64_t f = f0 + i;
+      const double y1 = FROM_COEF ? tir_coef_to_y(coef[f * 2]) : y[f * 2];
+      const double v1 = (y1 == y1 && fabs(y1) != INFINITY) ? y1 : 0.0; // a missing JSON key reads 0.0
+      const double freq = (double)(int)v1;                              // :290 C truncation
+      if ((mp.use_lo && freq < mp.thr_lo) || (mp.use_hi && freq > mp.thr_hi)) continue; // :293-306
+      const int bin = (int)freq + TIR_QPREP_BINS / 2;
+      if (bin >= 0 && bin < TIR_QPREP_BINS) {
+        if (atomicAdd(&s_hist[bin], 1u) == 0) s_lead[atomicAdd(&s_nlead, 1u)] = (uint16_t)bin;
+      } else {
+        far = true;
+      }
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, leader);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
-    uint32_t pos = s_base + __popc(bal & ((1u << lane) - 1u));
-    for (int k = 0; k < wid; k++) pos += s_warp[k];
-    if (leader) {
-      w.weight = w.pad;
-      w.pad = tir_wset_insert(batch, w, claimed); // slot in the batch's window set
-      wq[pos] = w;
+    const int any_far = __syncthreads_or(far);
+    const uint32_t nlead = s_nlead;
+    for (uint32_t j = threadIdx.x; j < nlead; j += blockDim.x) {
+      const int bin = s_lead[j];
+      TirWindow w;
+      tir_frame_window((double)(bin - TIR_QPREP_BINS / 2), 0.0, mp, w); // trunc(freq) == freq: the leader's own window
+      w.weight = s_hist[bin];
+      w.pad = tir_wset_insert(batch, w, claimed);
+      wq[j] = w;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t t = s_base;
-      for (int k = 0; k < TIR_QPREP_THREADS / 32; k++) t += s_warp[k];
-      s_base = t;
+    uint32_t n_out = nlead;
+    if (any_far && threadIdx.x == 0) { // serial tail, unfolded (leaders + far frames <= frames: the slice holds them)
+      for (uint32_t i = 0; i < nf; i++) {
+        const double y1 = y[(f0 + i) * 2]; // (never FROM_COEF)
+        const double v1 = (y1 == y1 && fabs(y1) != INFINITY) ? y1 : 0.0;
+        const int bin = (int)v1 + TIR_QPREP_BINS / 2;
+        if (bin >= 0 && bin < TIR_QPREP_BINS) continue;
+        TirWindow w;
+        if (!tir_frame_window(y1, 0.0, mp, w)) continue;
+        w.pad = tir_wset_insert(batch, w, claimed);
+        wq[n_out++] = w;
+      }
     }
-    __syncthreads();
+    if (threadIdx.x == 0) s_base = n_out;
+  } else {
+    // every frame that passes the max1 ignore test is a leader; compacted in frame order (ballot prefix
+    // per chunk of blockDim frames)
+    for (uint32_t c0 = 0; c0 < nf; c0 += blockDim.x) {
+      const uint32_t i = c0 + threadIdx.x;
+      TirWindow w;
+      bool leader = false;
+      if (i < nf) {
+        const uint64_t f = f0 + i;
+        double y1, y2;
+        if (FROM_COEF) y1 = tir_coef_to_y(coef[f * 2]), y2 = tir_coef_to_y(coef[f * 2 + 1]);
+        else y1 = y[f * 2], y2 = y[f * 2 + 1];
+        leader = tir_frame_window(y1, y2, mp, w);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, leader);
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      if (lane == 0) s_warp[wid] = __popc(bal);
+      __syncthreads();
+      uint32_t pos = s_base + __popc(bal & ((1u << lane) - 1u));
+      for (int k = 0; k < wid; k++) pos += s_warp[k];
+      if (leader) {
+        w.pad = tir_wset_insert(batch, w, claimed); // slot in the batch's window set
+        wq[pos] = w;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t t = s_base;
+        for (int k = 0; k < TIR_QPREP_THREADS / 32; k++) t += s_warp[k];
+        s_base = t;
+      }
+      __syncthreads();
+    }
   }
+  __syncthreads();
   if (threadIdx.x == 0) n_windows[q] = s_base;
   // the last CTA to finish numbers the occupied slots of the window set (a CTA that claimed a slot
   // makes the window it stored there visible before it counts itself done)
@@ -560,8 +588,7 @@ __device__ __forceinline__ void tir_write_hit(unsigned long long b, const uint32
 __device__ __forceinline__ void tir_exchange_release(const TirP2PArgs &x) {
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < (unsigned)x.world)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t *>(x.peer[threadIdx.x]) + x.rank), "r"(x.epoch) : "memory");
+  if (threadIdx.x < (unsigned)x.world) tir_st_release_sys(reinterpret_cast<uint32_t *>(x.peer[threadIdx.x]) + x.rank, x.epoch);
 }
 
 // One CTA per index block, everything in shared memory: (1) the 2K bound searches of the K distinct
@@ -766,6 +793,7 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
   if (threadIdx.x == 0) *x.done = 0;
   if (*reinterpret_cast<volatile uint32_t *>(&batch->overflow)) return;
   tir_exchange_release(x);
+  tir_p2p_fused_merge(x, n_queries); // this CTA also folds the ranks' candidates once their flags arrive
 }
 
 // ---- per-query path -------------------------------------------------------------------------------
@@ -778,7 +806,9 @@ __global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows
 // in flight per lane (uid, 2 B/row; key2 too for coefs == 2); a warp clears its bitmap only after a
 // window that voted.
 #define TIR_GEN_CHUNK 128
-#define TIR_GEN_SMEM (TIR_BLOCK_UUIDS * 2 + (TIR_MATCH_THREADS / 32) * (TIR_BLOCK_UUIDS / 8))
+// WIDE: u32 counters (64 KB) for batches that hold a query of more than 65 535 frames -- a u16 counter
+// could wrap (35 min of audio at 8 kHz / hop 256, but only 6 min at 44.1 kHz)
+#define TIR_GEN_SMEM_OF(wide) (TIR_BLOCK_UUIDS * ((wide) ? 4 : 2) + (TIR_MATCH_THREADS / 32) * (TIR_BLOCK_UUIDS / 8))
 template <bool UPPER>
 __device__ __forceinline__ uint64_t tir_thread_bound(const int32_t *__restrict__ key, uint64_t lo, uint64_t hi, int32_t target) {
   while (lo < hi) {
@@ -789,7 +819,7 @@ __device__ __forceinline__ uint64_t tir_thread_bound(const int32_t *__restrict__
   return lo;
 }
 
-template <int COEFS>
+template <int COEFS, bool WIDE>
 __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_match_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
                      const uint64_t *__restrict__ block_start, const TirWindow *__restrict__ windows,
@@ -799,8 +829,10 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      tir_hit *__restrict__ hits, const TirP2PArgs x) {
   TIR_PDL_PROLOGUE();
   if (!(batch->use_general || batch->overflow)) return;
-  extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word; then the warps' bitmaps
-  uint32_t *s_seen = s_cnt + TIR_BLOCK_UUIDS / 2 + (threadIdx.x >> 5) * (TIR_BLOCK_UUIDS / 32);
+  extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word (WIDE: u32); then the warps' bitmaps
+  constexpr int CNT_WORDS = WIDE ? TIR_BLOCK_UUIDS : TIR_BLOCK_UUIDS / 2;
+  constexpr int TIR_GEN_SMEM = TIR_GEN_SMEM_OF(WIDE);
+  uint32_t *s_seen = s_cnt + CNT_WORDS + (threadIdx.x >> 5) * (TIR_BLOCK_UUIDS / 32);
   __shared__ uint64_t s_range[TIR_GEN_CHUNK][2];
   __shared__ unsigned long long s_best[TIR_MATCH_THREADS / 32];
   __shared__ uint32_t s_last;
@@ -844,7 +876,10 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
             if (!ok[e]) continue;
             const uint32_t bit = 1u << (u[e] & 31);
             const uint32_t old = atomicOr(&s_seen[u[e] >> 5], bit); // group by audio_uuid: one vote per frame
-            if (!(old & bit)) atomicAdd(&s_cnt[u[e] >> 1], w.weight << ((u[e] & 1) * 16)); // total <= 65535: no carry
+            if (!(old & bit)) {
+              if (WIDE) atomicAdd(&s_cnt[u[e]], w.weight);
+              else atomicAdd(&s_cnt[u[e] >> 1], w.weight << ((u[e] & 1) * 16)); // total <= 65535: no carry
+            }
             voted = true;
           }
         }
@@ -858,12 +893,16 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     __syncthreads();
     // winner of this block: greatest count, ties -> greatest rank (== greatest uuid)
     unsigned long long bestv = 0;
-    for (int i = tid; i < TIR_BLOCK_UUIDS / 2; i += TIR_MATCH_THREADS) {
+    for (int i = tid; i < CNT_WORDS; i += TIR_MATCH_THREADS) {
       const uint32_t pair = s_cnt[i];
-      const uint32_t c0v = pair & 0xffffu, c1v = pair >> 16;
-      const uint64_t rank0 = (uint64_t)blk * TIR_BLOCK_UUIDS + 2 * i;
-      if (c0v) bestv = max(bestv, ((unsigned long long)c0v << 32) | rank0);
-      if (c1v) bestv = max(bestv, ((unsigned long long)c1v << 32) | (rank0 + 1));
+      if (WIDE) {
+        if (pair) bestv = max(bestv, ((unsigned long long)pair << 32) | ((uint64_t)blk * TIR_BLOCK_UUIDS + i));
+      } else {
+        const uint32_t c0v = pair & 0xffffu, c1v = pair >> 16;
+        const uint64_t rank0 = (uint64_t)blk * TIR_BLOCK_UUIDS + 2 * i;
+        if (c0v) bestv = max(bestv, ((unsigned long long)c0v << 32) | rank0);
+        if (c1v) bestv = max(bestv, ((unsigned long long)c1v << 32) | (rank0 + 1));
+      }
     }
     for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
     if (lane == 0) s_best[warp] = bestv;
@@ -885,6 +924,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   if (x.peer) {
     if (tid == 0) *x.done = 0; // (resolve CTAs that counted themselves before the hand-over)
     tir_exchange_release(x);
+    tir_p2p_fused_merge(x, n_queries);
   }
 }
 
@@ -920,6 +960,46 @@ static int ensure_db(tir_ctx *ctx) {
   return ctx->db ? TIR_OK : tir_fail(ctx, TIR_ERR_NOMEM, "out of memory");
 }
 
+struct TirMatchScratch {
+  size_t o_foff, o_nw, o_best, o_batch, o_maxr, o_gkeys, o_gvals, o_plist, o_win, bytes;
+};
+static TirMatchScratch match_scratch_layout(uint32_t n_queries, uint64_t F) {
+  TirMatchScratch L;
+  L.o_foff = 0, L.o_nw = L.o_foff + ((size_t)n_queries + 1) * 8, L.o_best = (L.o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
+  L.o_batch = (L.o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
+  L.o_maxr = (L.o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
+  L.o_gkeys = L.o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), L.o_gvals = L.o_gkeys + (size_t)4 * TIR_PAT_HASH_GLOBAL;
+  L.o_plist = L.o_gvals + (size_t)4 * TIR_PAT_HASH_GLOBAL; // (first bytes that need no clearing)
+  L.o_win = L.o_plist + (size_t)4 * TIR_PAT_HASH_GLOBAL;
+  L.bytes = L.o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
+  return L;
+}
+static size_t match_scratch_bytes(uint32_t n_queries, uint64_t F) { return match_scratch_layout(n_queries, F).bytes; }
+
+
+// Pre-size every scratch buffer a search of up to n_queries queries / F frames / n_samples samples needs, so
+// that the calls themselves neither allocate nor free (cudaFree waits for the whole device -- fatal when the
+// ranks of an exchange are driven from ONE host thread and an earlier rank's kernel is waiting for a later one).
+int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_samples) {
+  int rc;
+  if ((rc = tir_reserve(ctx, ctx->d_qmeta, match_scratch_bytes(n_queries, F)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_hits, (size_t)std::max<uint32_t>(n_queries, 1) * sizeof(tir_hit)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_pcm, n_samples * sizeof(int16_t) + 16))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_coef, std::max<uint64_t>(F, 1) * TIR_N_COEFS * sizeof(float)))) return rc;
+  const size_t nc1 = (size_t)n_queries + 1;
+  if ((rc = tir_reserve(ctx, ctx->d_clipmeta, nc1 * 20 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_tilemeta, (size_t)(F / 32 + n_queries + 1) * 32))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_counter, 256))) return rc;
+  for (int k = 0; k < tir_ctx::kStageSlots; k++)
+    if ((rc = tir_reserve_host(ctx, ctx->h_stage[k], nc1 * 20 + 64))) return rc;
+  return TIR_OK;
+}
+
+int tir_db_ensure_index(tir_ctx *ctx) {
+  if (!ctx->db || !ctx->db->dirty) return TIR_OK;
+  return db_build_index(ctx, ctx->db);
+}
+
 static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef, const uint64_t *frame_off,
                            uint32_t n_queries, int coefs, double tolerance, int ign_lo, int ign_hi, tir_hit *d_hits,
                            const TirP2PArgs *p2p = nullptr) {
@@ -933,17 +1013,16 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   cudaStream_t st = ctx->stream;
   const uint64_t F = frame_off[n_queries] - frame_off[0];
   if (frame_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "frame_off[0] must be 0");
-  for (uint32_t q = 0; q < n_queries; q++)
-    if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 65535)
-      return tir_fail(ctx, TIR_ERR_ARG, "a query may have at most 65535 frames (u16 vote counters)");
+  bool wide = false; // a query of more than 65 535 frames: the per-query kernel counts in u32
+  for (uint32_t q = 0; q < n_queries; q++) {
+    if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 0x7fffffffull)
+      return tir_fail(ctx, TIR_ERR_ARG, "frame_off must be non-decreasing (and a query shorter than 2^31 frames)");
+    wide |= frame_off[q + 1] - frame_off[q] > 65535;
+  }
   // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | pattern hash keys | values | pattern list | windows
-  const size_t o_foff = 0, o_nw = o_foff + ((size_t)n_queries + 1) * 8, o_best = (o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
-  const size_t o_batch = (o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
-  const size_t o_maxr = (o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
-  const size_t o_gkeys = o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), o_gvals = o_gkeys + (size_t)4 * TIR_PAT_HASH_GLOBAL;
-  const size_t o_plist = o_gvals + (size_t)4 * TIR_PAT_HASH_GLOBAL; // (first bytes that need no clearing)
-  const size_t o_win = o_plist + (size_t)4 * TIR_PAT_HASH_GLOBAL;
-  const size_t bytes = o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
+  const TirMatchScratch L = match_scratch_layout(n_queries, F);
+  const size_t o_foff = L.o_foff, o_nw = L.o_nw, o_best = L.o_best, o_batch = L.o_batch, o_maxr = L.o_maxr, o_gkeys = L.o_gkeys,
+               o_gvals = L.o_gvals, o_plist = L.o_plist, o_win = L.o_win, bytes = L.bytes;
   if ((rc = tir_reserve(ctx, ctx->d_qmeta, bytes))) return rc;
   unsigned char *d = (unsigned char *)ctx->d_qmeta.p;
   void *hp;
@@ -988,18 +1067,17 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     const uint64_t items = (uint64_t)db->n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);
     if (!ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM));
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM));
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(true)));
+      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(true)));
       ctx->match_smem_attr_set = true;
     }
-    if (coefs >= 2)
-      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_match_kernel<2>, dim3(ggrid), dim3(TIR_MATCH_THREADS), TIR_GEN_SMEM, st, k1, uid, k2, bst, (const TirWindow *)d_win,
-                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
-                                   (const uint8_t *)db->uuids.p, d_hits, x));
-    else
-      TIR_CUDA(ctx, tir_launch_pdl_smem(tir_match_kernel<1>, dim3(ggrid), dim3(TIR_MATCH_THREADS), TIR_GEN_SMEM, st, k1, uid, k2, bst, (const TirWindow *)d_win,
-                                   (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch, (const uint32_t *)db->order.p,
-                                   (const uint8_t *)db->uuids.p, d_hits, x));
+    auto gen = coefs >= 2 ? (wide ? tir_match_kernel<2, true> : tir_match_kernel<2, false>)
+                          : (wide ? tir_match_kernel<1, true> : tir_match_kernel<1, false>);
+    TIR_CUDA(ctx, tir_launch_pdl_smem(gen, dim3(ggrid), dim3(TIR_MATCH_THREADS), (size_t)TIR_GEN_SMEM_OF(wide), st, k1, uid, k2, bst,
+                                      (const TirWindow *)d_win, (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch,
+                                      (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits, x));
     ctx->launches += 3;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
@@ -1009,6 +1087,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     TIR_CUDA(ctx, tir_launch_pdl(tir_no_hits_kernel, dim3((n_queries + 127) / 128), dim3(128), st, d_foff, n_queries, d_hits));
     ctx->launches++;
     if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x))) return rc; // an empty shard still answers
+    if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x, n_queries))) return rc;
   }
   TIR_CUDA(ctx, cudaGetLastError());
   return TIR_OK;

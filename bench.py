@@ -47,25 +47,26 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------ inputs
 
-def synth_clips_gpu(n_clips, seed, device):
+def synth_clips_gpu(n_clips, seed, device, sr=SR):
     """Synthetic corpus generated on the GPU with torch (plumbing, not the product):
     40 % tone, 30 % noise, 20 % chirp, 10 % composite; all passed through G.711 mu-law."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(20180610 + seed)
+    N_SAMP = int(sr * SECONDS)
     out = torch.empty((n_clips, N_SAMP), dtype=torch.int16, device=device)
-    t = torch.arange(N_SAMP, device=device, dtype=torch.float32) / SR
+    t = torch.arange(N_SAMP, device=device, dtype=torch.float32) / sr
     chunk = 250
     for c0 in range(0, n_clips, chunk):
         n = min(chunk, n_clips - c0)
         u = torch.rand((n, 8), device=device, generator=g)
         kind = u[:, 0:1]
-        f = 200.0 + u[:, 1:2] * 3200.0
+        f = 200.0 + u[:, 1:2] * (3200.0 if sr <= 8000 else 6800.0)
         amp = 0.05 + u[:, 2:3] * 0.85
         tone = amp * torch.sin(2 * torch.pi * f * t + 2 * torch.pi * u[:, 3:4])
         sigma = 0.01 + u[:, 4:5] * 0.29
         noise = torch.clamp(torch.randn((n, N_SAMP), device=device, generator=g) * sigma, -1, 1)
-        f0, f1 = 200.0, 0.85 * SR / 2
+        f0, f1 = 200.0, 0.85 * sr / 2
         chirp = (0.1 + 0.7 * u[:, 5:6]) * torch.sin(2 * torch.pi * (f0 * t + 0.5 * (f1 - f0) / SECONDS * t * t))
         comp = 0.5 * tone + 0.3 * chirp + 0.2 * noise
         x = torch.where(kind < 0.4, tone, torch.where(kind < 0.7, noise, torch.where(kind < 0.9, chirp, comp)))
@@ -140,11 +141,8 @@ def run_reference(args):
     n_thr = os.cpu_count() or 1
     plan = po.Plan(WIN, HOP, 40, 2, SR)
     pool = synth_clips_cpu(32, 1)
-    # calibrate: one thread, 4 clips
-    t = time.time(); plan.extract_batch(pool[:4].reshape(-1), np.arange(5, dtype=np.uint64) * N_SAMP, n_threads=1, want_y=False)
-    per_clip = (time.time() - t) / 4
-    target_s = 4.0
-    n_clips = int(max(n_thr, min(10000, target_s / per_clip * n_thr)))
+    # the stated config: every clip of the step (10 000 x 30 s; a few seconds per step on the box's cores)
+    n_clips = args.clips
     pcm = pool[np.arange(n_clips) % pool.shape[0]].reshape(-1)
     off = np.arange(n_clips + 1, dtype=np.uint64) * N_SAMP
     for _ in range(args.warmup):
@@ -154,7 +152,7 @@ def run_reference(args):
         plan.extract_batch(pcm, off, n_threads=n_thr, want_y=False)
     dt = (time.time() - t0) / args.steps
     value = n_clips * SECONDS / dt
-    sample = f"{n_clips} of 10000 clips per step (32 distinct synthetic clips tiled), {n_thr} threads, oracle restatement of libaubio"
+    sample = f"all {n_clips} clips per step (32 distinct synthetic clips tiled), {n_thr} threads, oracle restatement of libaubio"
     line = {
         "impl": "reference", "metric": "audio_seconds_fingerprinted_per_second", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -176,57 +174,207 @@ def workload_config(n_clips):
 
 # ------------------------------------------------------------------------------------ match bench
 
+def _uuid_keys(uu):
+    """[n,16] uint8 (cuda) -> two int64 keys whose signed order is the byte order of the uuids."""
+    import torch
+    w = uu.to(torch.int64)
+    hi = torch.zeros(uu.shape[0], dtype=torch.int64, device=uu.device)
+    lo = torch.zeros_like(hi)
+    for i in range(8):
+        hi = (hi << 8) | w[:, i]
+        lo = (lo << 8) | w[:, 8 + i]
+    flip = torch.tensor(-(2 ** 63), dtype=torch.int64, device=uu.device)
+    return hi ^ flip, lo ^ flip
+
+
+def _uuid_sort(uu):
+    """ascending byte order of the shard's uuids (== SQLite's text order of the canonical form)"""
+    import torch
+    hi, lo = _uuid_keys(uu)
+    o1 = torch.sort(lo, stable=True).indices
+    o2 = torch.sort(hi[o1], stable=True).indices
+    return o1[o2]
+
+
+class BruteForce:
+    """torch restatement of the vote (src/fp_handler.c:287-373) over this rank's shard, independent of the
+    library's index and kernels: 'uuid has a row in window k' by comparing every stored row, votes =
+    weights . bits, winner = greatest (count, uuid bytes).  Used only to verify the timed results."""
+
+    def __init__(self, v1, v2, uu, F_db):
+        self.v1, self.v2, self.F_db = v1.view(-1, F_db), v2.view(-1, F_db), F_db
+        self.order = _uuid_sort(uu)
+        self.uu_sorted = uu[self.order]
+        self.n = uu.shape[0]
+
+    def windows_bits(self, ks, T):
+        """-> [K, n] float16 in sorted-uuid order: uuid has a row with |v1 - k*1e6| <= T"""
+        import torch
+        out = torch.zeros((len(ks), self.n), dtype=torch.float16, device=self.v1.device)
+        step = max(1, (64 << 20) // self.F_db)
+        for a0 in range(0, self.n, step):
+            blk = self.v1[a0:a0 + step]
+            for i, k in enumerate(ks):
+                c = int(k) * 1_000_000
+                out[i, a0:a0 + step] = ((blk >= c - T) & (blk <= c + T)).any(dim=1).to(torch.float16)
+        return out[:, self.order]
+
+    def winners_coefs1(self, y1, T):
+        """y1 [Q, F] float64 (max1 of every query frame) -> (count int64 [Q], uuid uint8 [Q,16])"""
+        import torch
+        qk = torch.trunc(torch.where(torch.isfinite(y1), y1, torch.zeros_like(y1))).to(torch.int64)
+        ks = torch.unique(qk)
+        W = (qk[:, :, None] == ks[None, None, :]).sum(dim=1).to(torch.float16)          # [Q, K]
+        B = self.windows_bits(ks.tolist(), T)                                            # [K, n]
+        Q = y1.shape[0]
+        best = torch.zeros(Q, dtype=torch.int64, device=y1.device)
+        arg = torch.zeros(Q, dtype=torch.int64, device=y1.device)
+        C = max(1, (256 << 20) // max(Q, 1))
+        for c0 in range(0, self.n, C):
+            votes = W @ B[:, c0:c0 + C]                                                  # exact: small integers in fp16
+            m = votes.max(dim=1).values
+            last = votes.shape[1] - 1 - torch.argmax((votes == m[:, None]).flip(1).to(torch.uint8), dim=1)
+            mi = m.to(torch.int64)
+            take = (mi >= best) & (mi > 0)        # later chunks hold greater uuids: ties go to them
+            best = torch.where(take, mi, best)
+            arg = torch.where(take, last + c0, arg)
+        uuid = self.uu_sorted[arg] if self.n else torch.zeros((Q, 16), dtype=torch.uint8, device=y1.device)
+        uuid = torch.where((best > 0)[:, None], uuid, torch.zeros_like(uuid))
+        return best, uuid
+
+    def winners_coefs2(self, y1, y2, T):
+        """per-frame windows on both columns (coefs = 2), one vote per frame and uuid"""
+        import torch
+        dev = y1.device
+        qk = torch.trunc(y1).to(torch.int64)
+        ks = torch.unique(qk).tolist()
+        rank_of = torch.empty(self.n, dtype=torch.int64, device=dev)
+        rank_of[self.order] = torch.arange(self.n, device=dev)
+        cand = []
+        step = max(1, (64 << 20) // self.F_db)
+        for a0 in range(0, self.n, step):
+            blk = self.v1[a0:a0 + step]
+            m = torch.zeros_like(blk, dtype=torch.bool)
+            for k in ks:
+                c = int(k) * 1_000_000
+                m |= (blk >= c - T) & (blk <= c + T)
+            idx = torch.nonzero(m)
+            cand.append((rank_of[idx[:, 0] + a0], blk[m], self.v2[a0:a0 + step][m]))
+        cu = torch.cat([c[0] for c in cand]); c1 = torch.cat([c[1] for c in cand]).to(torch.int64); c2 = torch.cat([c[2] for c in cand]).to(torch.int64)
+        Q = y1.shape[0]
+        best = torch.zeros(Q, dtype=torch.int64, device=dev)
+        arg = torch.zeros(Q, dtype=torch.int64, device=dev)
+        lo2 = torch.round((y2 - T * 1e-6) * 1e6).to(torch.int64)
+        hi2 = torch.round((y2 + T * 1e-6) * 1e6).to(torch.int64)
+        for q in range(Q):
+            kc = qk[q] * 1_000_000
+            m = (c1[None, :] >= (kc - T)[:, None]) & (c1[None, :] <= (kc + T)[:, None]) & \
+                (c2[None, :] >= lo2[q][:, None]) & (c2[None, :] <= hi2[q][:, None])
+            fj = torch.nonzero(m)
+            if fj.shape[0] == 0:
+                continue
+            key = torch.unique(fj[:, 0] * self.n + cu[fj[:, 1]])                        # (frame, uuid) once
+            u, cnt = torch.unique(key % self.n, return_counts=True)
+            mx = cnt.max()
+            best[q] = mx
+            arg[q] = u[cnt == mx].max()
+        uuid = self.uu_sorted[arg]
+        uuid = torch.where((best > 0)[:, None], uuid, torch.zeros_like(uuid))
+        return best, uuid
+
+
+def _global_winners(best, uuid, world, dist):
+    """fold the per-rank (count, uuid) candidates: greatest count, ties -> greatest uuid bytes"""
+    import torch
+    if world == 1:
+        return best, uuid
+    Q = best.shape[0]
+    gb = torch.zeros((world, Q), dtype=torch.int64, device=best.device)
+    gu = torch.zeros((world, Q, 16), dtype=torch.uint8, device=best.device)
+    dist.all_gather_into_tensor(gb, best.contiguous())
+    dist.all_gather_into_tensor(gu, uuid.contiguous())
+    b, u = gb[0].clone(), gu[0].clone()
+    for r in range(1, world):
+        hi_a, lo_a = _uuid_keys(u)
+        hi_b, lo_b = _uuid_keys(gu[r])
+        greater = (hi_b > hi_a) | ((hi_b == hi_a) & (lo_b > lo_a))
+        take = (gb[r] > b) | ((gb[r] == b) & (b > 0) & greater)
+        b = torch.where(take, gb[r], b)
+        u = torch.where(take[:, None], gu[r], u)
+    return b, u
+
+
+def _compare(d_hits_bytes, best, uuid, F_q=None):
+    """the library's tir_hit array (device bytes) against the brute-force winners -> identical count"""
+    import torch
+    from asterisk_tiresias_b200 import capi
+    h = d_hits_bytes.cpu().numpy().view(capi.HIT_DTYPE)
+    b, u = best.cpu().numpy(), uuid.cpu().numpy()
+    same = (h["match_count"] == b) & (h["uuid"] == u).all(axis=1)
+    if F_q is not None:
+        same &= h["frame_count"] == F_q
+    return {"checked": int(b.shape[0]), "identical": int(same.sum())}
+
+
 def match_bench(ctx, args, rank, world, device, dist):
-    """Secondary: match queries/s against a synthetic DB sharded by uuid over the ranks."""
+    """Secondary metric: match queries/s against a synthetic DB sharded by uuid over the ranks.  Every timed
+    result is compared, for EVERY query and at every N, with a torch brute force over the stored rows."""
     import torch
     from asterisk_tiresias_b200 import capi
     total_fps = args.match_fps if args.match_fps > 0 else 10_000_000     # BASELINE metric: 10M-fingerprint DB at every N
-    F_db, Q, F_q = 94, args.match_queries, 94
-    # uuids are random 128-bit values; shard s owns the uuids with tir_shard_of == s.  Generating the
-    # shard directly (same distribution, n/world each) avoids materialising the whole DB on every rank.
-    n_local = total_fps // world + (1 if rank < total_fps % world else 0)
-    g = torch.Generator(device=device); g.manual_seed(991 + rank)
-    rows = n_local * F_db
-    uu = torch.randint(0, 256, (n_local, 16), dtype=torch.uint8, device=device, generator=g)
-    # y1 ~ U(15.5, 18.5) (the ranges SURVEY.md 8a measured on 8 kHz material), in micro-units
-    v1 = torch.randint(15_500_000, 18_500_000, (rows,), dtype=torch.int32, device=device, generator=g)
-    v2 = torch.randint(-5_000_000, 20_000_000, (rows,), dtype=torch.int32, device=device, generator=g)
-    row_off = (torch.arange(n_local + 1, device=device, dtype=torch.int64) * F_db)
-    torch.cuda.synchronize()
-    t0 = time.time()
-    ctx.db_load_dev(n_local, uu.data_ptr(), row_off.data_ptr(), v1.data_ptr(), v2.data_ptr(), rows)
-    build_s = time.time() - t0
+    Q, F_q = args.match_queries, 94
+    qv_box = {}
+
+    def make_db(F_db, seed):
+        # uuids are random 128-bit values; shard s owns the uuids with tir_shard_of == s.  Generating the
+        # shard directly (same distribution, n/world each) avoids materialising the whole DB on every rank.
+        n_local = total_fps // world + (1 if rank < total_fps % world else 0)
+        g = torch.Generator(device=device); g.manual_seed(seed + rank)
+        rows = n_local * F_db
+        uu = torch.randint(0, 256, (n_local, 16), dtype=torch.uint8, device=device, generator=g)
+        # y1 ~ U(15.5, 18.5) (the ranges SURVEY.md 8a measured on 8 kHz material), in micro-units
+        v1 = torch.randint(15_500_000, 18_500_000, (rows,), dtype=torch.int32, device=device, generator=g)
+        v2 = torch.randint(-5_000_000, 20_000_000, (rows,), dtype=torch.int32, device=device, generator=g)
+        row_off = (torch.arange(n_local + 1, device=device, dtype=torch.int64) * F_db)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ctx.db_load_dev(n_local, uu.data_ptr(), row_off.data_ptr(), v1.data_ptr(), v2.data_ptr(), rows)
+        torch.cuda.synchronize()
+        return uu, v1, v2, n_local, rows, time.time() - t0
+
+    F_db = 94
+    uu, v1, v2, n_local, rows, build_s = make_db(F_db, 991)
     # queries (identical on every rank): 10 % exact copies of DB entries of rank 0, 10 % noisy copies, 80 % unrelated
     gq = torch.Generator(device=device); gq.manual_seed(4242)
     qv = torch.randint(15_500_000, 18_500_000, (Q, F_q), dtype=torch.int32, device=device, generator=gq).double() * 1e-6
+    src = v1.view(n_local, F_db)[: Q // 5].double() * 1e-6
     if world > 1:
-        src = torch.zeros((Q // 5, F_q), dtype=torch.float64, device=device)
-        if rank == 0:
-            src = v1.view(n_local, F_db)[: Q // 5].double() * 1e-6
+        if rank != 0:
+            src = torch.zeros_like(src)
         dist.broadcast(src, 0)
-    else:
-        src = v1.view(n_local, F_db)[: Q // 5].double() * 1e-6
     qv[: Q // 10] = src[: Q // 10]
     qv[Q // 10: Q // 5] = src[Q // 10: Q // 5] + torch.randn((Q // 5 - Q // 10, F_q), device=device, generator=gq, dtype=torch.float64) * 3e-4
     # the engine takes mfcc coefficients; invert y = 10*log10|c| so that the device recomputes exactly these y
     q2 = torch.rand((Q, F_q), device=device, generator=gq, dtype=torch.float64) * 25.0 - 5.0   # max2 of every frame: all distinct
     coef = torch.stack([torch.pow(10.0, qv / 10.0).float(), torch.pow(10.0, q2 / 10.0).float()], dim=2).contiguous()
     qv = 10.0 * torch.log10(coef[:, :, 0].double())     # the y the device will recompute from the float coefficients
+    q2 = 10.0 * torch.log10(coef[:, :, 1].double())
     foff = np.arange(Q + 1, dtype=np.uint64) * F_q
     d_hits = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
     d_gather = torch.zeros(world * Q * 24, dtype=torch.uint8, device=device)
     d_final = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
 
-    # N > 1: the per-query winners (nq x 24 B per rank) are the only cross-GPU traffic.  Default: the
-    # library's own exchange over NVLink peer memory (csrc/tir_p2p.cu: P2P stores into every peer's
-    # gather buffer + flags, no collective call); --match-exchange nccl: all_gather + merge kernel.
+    # N > 1: the per-query winners (nq x 24 B per rank) are the only cross-GPU traffic of the match.  Default: the
+    # library's own exchange over NVLink peer memory (csrc/tir_p2p.cu: P2P stores into every peer's gather buffer
+    # + flags, folded by the last CTA of the match chain, no collective call); --match-exchange nccl: all_gather +
+    # merge kernel.
     p2p = None
     exchange = "none (one GPU)"
     if world > 1:
         exchange = "nccl all_gather + tir_merge_hits_dev"
         if args.match_exchange == "p2p":
             try:
-                p2p = capi.P2P(ctx, rank, world, Q)
+                p2p = capi.P2P(ctx, rank, world, Q, max_frames=Q * F_q)
                 mine = torch.frombuffer(bytearray(p2p.handle()), dtype=torch.uint8).to(device)
                 allh = torch.zeros(world * 64, dtype=torch.uint8, device=device)
                 dist.all_gather_into_tensor(allh, mine)
@@ -240,21 +388,21 @@ def match_bench(ctx, args, rank, world, device, dist):
             if float(ok.item()) < 1.0:
                 p2p = None
             else:
-                exchange = "tir_p2p (NVLink peer stores + flags, no collective call)"
+                exchange = "tir_p2p (NVLink peer stores + flags, folded in the last CTA of the match chain; no collective call)"
 
-    def step(coefs=1, nq=Q, use_p2p=True):
+    def step(coefs=1, nq=Q, use_p2p=True, tol=0.001):
         if p2p is not None and use_p2p:
-            p2p.match_dev(coef.data_ptr(), foff[: nq + 1], d_final.data_ptr(), coefs, 0.001)
+            p2p.match_dev(coef.data_ptr(), foff[: nq + 1], d_final.data_ptr(), coefs, tol)
             return
-        ctx.match_dev(coef.data_ptr(), foff[: nq + 1], d_hits.data_ptr(), coefs, 0.001)
+        ctx.match_dev(coef.data_ptr(), foff[: nq + 1], d_hits.data_ptr(), coefs, tol)
         if world > 1:
             dist.all_gather_into_tensor(d_gather[: world * nq * 24], d_hits[: nq * 24])
             ctx.merge_hits_dev(d_gather.data_ptr(), world, nq, d_final.data_ptr())
         # (one GPU: the shard's winners are the answer, nothing to merge)
 
-    def timed(coefs, nq, steps, use_p2p=True):
+    def timed(coefs, nq, steps, use_p2p=True, tol=0.001):
         for _ in range(3):
-            step(coefs, nq, use_p2p)
+            step(coefs, nq, use_p2p, tol)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -262,7 +410,7 @@ def match_bench(ctx, args, rank, world, device, dist):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(coefs, nq, use_p2p)
+            step(coefs, nq, use_p2p, tol)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -272,10 +420,16 @@ def match_bench(ctx, args, rank, world, device, dist):
             tt = torch.tensor([ms], device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
         return ms, k_ms, launches
 
+    def result():
+        return (d_final if world > 1 else d_hits)
+
     ctx.set_profiling(True)
+    bf = BruteForce(v1, v2, uu, F_db)
     # per-query path (coefs = 2: every frame has its own max2 bounds), on a slice of the queries
     nq2 = max(1, min(Q, args.match_queries_coefs2))
     ms2, k_ms2, _ = timed(2, nq2, max(1, min(args.steps, 3)))
+    b2, u2 = _global_winners(*bf.winners_coefs2(qv[:nq2], q2[:nq2], 1000), world, dist)
+    verified2 = _compare(result()[: nq2 * 24], b2, u2, F_q)
     # headline: coefs = 1, what the dialplan application passes (src/application_handler.c:180)
     nccl_ms = None
     if p2p is not None:   # the same batch through NCCL, for comparison (its winners are checked against the p2p ones)
@@ -285,40 +439,74 @@ def match_bench(ctx, args, rank, world, device, dist):
     if p2p is not None:
         same = bool(torch.equal(nccl_hits, d_final)) and p2p.error() == 0
         exchange += f"; identical to the NCCL exchange: {same}"
-    hits = (d_final if world > 1 else d_hits).cpu().numpy().view(capi.HIT_DTYPE)
-    search_e2e = search_bench(ctx, args, rank, world, device, dist, Q)
+    hits = result().cpu().numpy().view(capi.HIT_DTYPE)
+    b1, u1 = _global_winners(*bf.winners_coefs1(qv, 1000), world, dist)
+    verified = _compare(result(), b1, u1, F_q)
+    # tolerance sweep: wider windows hold more rows -- the DB-bound regime, where the sharding pays
+    sweep = {}
+    for tol, T in ((0.01, 10_000), (0.05, 50_000)):
+        ms_t, k_t, _ = timed(1, Q, max(args.steps, 5), tol=tol)
+        bt, ut = _global_winners(*bf.winners_coefs1(qv, T), world, dist)
+        sweep[str(tol)] = {"value": Q / (ms_t * 1e-3), "unit": "queries/s", "ms_per_batch": ms_t, "kernel_ms_rank0": k_t,
+                           "verified_queries": _compare(result(), bt, ut, F_q)}
+    # honest roofline of the shared-window path: the bytes the algorithm must move per BATCH on this rank
+    # (every distinct window's rows once: 2 B uid each, one 16 B range header per window and index block,
+    # the coefficients in and the hits out) over the chain time
+    ks = torch.unique(torch.trunc(qv).to(torch.int64)).tolist()
+    R = [int(((v1 >= int(k) * 1_000_000 - 1000) & (v1 <= int(k) * 1_000_000 + 1000)).sum().item()) for k in ks]
+    n_blocks = (n_local + 16383) // 16384
+    alg = sum(R) * 2 + len(ks) * n_blocks * 16 + Q * F_q * 8 + Q * 24
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak))
+    except OSError:
+        pass
+    achieved = alg / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "algorithmic_bytes_per_batch_this_rank": alg, "rows_in_windows_this_rank": sum(R), "distinct_windows": len(ks),
+                "traffic": None, "traffic_note": "ncu dram bytes of the chain: see profiles/ (not measured in this run)",
+                "note": "latency/launch-bound at this batch size: four dependent launches over a few MB; bytes = rows of the distinct windows x 2 B + range headers + coefficients + hits, per batch; time = the whole chain"}
+    search_e2e = search_bench(ctx, args, rank, world, device, dist, Q, p2p, bf)
     cpu_match = match_cpu_baseline(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-    # verification on rank 0 / single GPU: brute-force restatement of the vote for a few queries
-    verified = None
-    if world == 1:
-        verified = verify_match(hits, qv.cpu().numpy(), v1.view(n_local, F_db), uu, n_check=4)
-    # algorithmic bytes: F_q*8 + sum_k (16 + 8*R_k) + 24 per query; R_k from the data
-    v1s = v1  # rows in window k of a query = rows with |v1 - k*1e6| <= 1000
-    ks = torch.unique(torch.trunc(qv).to(torch.int64))
-    R = {int(k): int(((v1s >= int(k) * 1_000_000 - 1000) & (v1s <= int(k) * 1_000_000 + 1000)).sum().item()) for k in ks}
-    qk = torch.trunc(qv).to(torch.int64).cpu().numpy()
-    alg = 0
-    for q in range(Q):
-        alg += F_q * 8 + 24 + sum(16 + 8 * R[int(k)] for k in np.unique(qk[q]))
     res = {"metric": "match_queries_per_second", "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms,
            "queries_per_batch": Q, "frames_per_query": F_q, "db_fingerprints_total": total_fps, "db_frames_per_fingerprint": F_db,
            "db_rows_this_rank": rows, "index_build_s": build_s, "coefs": 1, "tolerance": 0.001, "kernel_ms_rank0": kernel_ms,
            "launches_per_batch": launches, "found": int((hits["match_count"] > 0).sum()),
            "exchange": exchange, "nccl_exchange_ms_per_batch": nccl_ms,
            "path": "shared-window scan (distinct windows of the batch scanned once; DESIGN.md 4.3)",
+           "verified_queries": verified, "verification": "torch brute force over every stored row of every rank, all queries (bench.py BruteForce)",
            "per_query_path_coefs2": {"value": nq2 / (ms2 * 1e-3), "unit": "queries/s", "ms_per_batch": ms2, "queries_per_batch": nq2,
-                                     "kernel_ms_rank0": k_ms2, "coefs": 2, "tolerance": 0.001},
-           "self_matches_top": int((hits["match_count"][: Q // 10] > 0).sum()), "verified_queries": verified,
-           "search_e2e": search_e2e, "cpu_baseline": cpu_match,
-           "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None,
-                        "unit": "GB/s", "algorithmic_bytes_per_batch_this_rank": alg,
-                        "note": "SURVEY 8d charge F_q*8 + sum_k(16 + 8*R_k) + 24 per QUERY; the shared-window path reads each distinct window once per BATCH (6 B per row in it; the per-uuid patterns live in shared memory), so the charged figure can exceed the HBM peak"}}
+                                     "kernel_ms_rank0": k_ms2, "coefs": 2, "tolerance": 0.001, "verified_queries": verified2},
+           "tolerance_sweep": sweep, "self_matches_top": int((hits["match_count"][: Q // 10] > 0).sum()),
+           "search_e2e": search_e2e, "cpu_baseline": cpu_match, "roofline": roofline}
+    del bf, uu, v1, v2
+    torch.cuda.empty_cache()
+    # BASELINE config[3]/[4]'s table: 10 M fingerprints x 938 frames (30 s of audio each; 9.38 G rows, 94 GB of index)
+    # -- only fits sharded: run where a rank's share and its build scratch fit (N >= 4)
+    res["db_938_frames"] = None
+    if world >= 4 and not args.no_db938:
+        try:
+            F2 = 938
+            uu, v1, v2, n_local, rows2, build2 = make_db(F2, 1991)
+            ms9, k9, _ = timed(1, Q, max(args.steps, 5))
+            bf9 = BruteForce(v1, v2, uu, F2)
+            b9, u9 = _global_winners(*bf9.winners_coefs1(qv, 1000), world, dist)
+            v9 = _compare(result(), b9, u9, F_q)
+            ms9b, _, _ = timed(1, Q, max(args.steps, 5), tol=0.01)
+            b9b, u9b = _global_winners(*bf9.winners_coefs1(qv, 10_000), world, dist)
+            res["db_938_frames"] = {"value": Q / (ms9 * 1e-3), "unit": "queries/s", "ms_per_batch": ms9, "kernel_ms_rank0": k9,
+                                    "db_frames_per_fingerprint": F2, "db_rows_this_rank": rows2, "db_rows_total": total_fps * F2,
+                                    "index_build_s": build2, "tolerance": 0.001, "verified_queries": v9,
+                                    "tolerance_0.01": {"value": Q / (ms9b * 1e-3), "ms_per_batch": ms9b, "verified_queries": _compare(result(), b9b, u9b, F_q)}}
+            del bf9, uu, v1, v2
+        except Exception as ex:  # noqa: BLE001
+            res["db_938_frames"] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
     if p2p is not None:
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()      # no rank frees its region while a peer may still store into it
         p2p.close()
-    del uu, v1, v2
     return res
 
 
@@ -346,30 +534,47 @@ def match_cpu_baseline(args):
             "ingest_rows_per_s": n_fp * F / ingest_s, "found": found}
 
 
-def search_bench(ctx, args, rank, world, device, dist, Q):
-    """fp_search_fingerprint_info end to end through the C ABI (tir_search): Q query clips of 3 s
-    (the dialplan default, src/application_handler.c:60) in pinned HOST memory -> extraction ->
-    match against this rank's shard -> hits in host memory; with N ranks every rank searches its
-    shard and the per-query winners are merged after an all-gather."""
+def search_bench(ctx, args, rank, world, device, dist, Q, p2p, bf):
+    """fp_search_fingerprint_info end to end through the C ABI: Q query clips of 3 s (the dialplan default,
+    src/application_handler.c:60) in pinned HOST memory -> extraction -> match -> hits in host memory.
+    One GPU: tir_search.  N ranks: tir_p2p_search -- every rank uploads and extracts only ITS Q/N clips, the
+    coefficients cross the ranks inside the extraction kernel, every rank matches all Q against its shard and the
+    winners are folded inside the match chain; every rank ends with all Q hits in host memory."""
     import ctypes as C
     import torch
     from asterisk_tiresias_b200 import capi, synth
     n = 3 * SR
+    F_q = -(-n // HOP)
     pool = np.stack([synth.make_clip(880000 + i, 3.0, SR, ulaw=True) for i in range(50)])
-    h_pcm = torch.from_numpy(pool[np.arange(Q) % 50].reshape(-1).copy()).pin_memory()
-    off = np.arange(Q + 1, dtype=np.uint64) * n
+    per = (Q + world - 1) // world
+    a, b = min(Q, rank * per), min(Q, (rank + 1) * per)
+    h_pcm = torch.from_numpy(pool[np.arange(a, b) % 50].reshape(-1).copy()).pin_memory()
+    off = np.arange(b - a + 1, dtype=np.uint64) * n
+    all_foff = np.arange(Q + 1, dtype=np.uint64) * F_q
     h_hits = torch.zeros(Q * 24, dtype=torch.uint8).pin_memory()
-    d_loc = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
-    d_all = torch.zeros(world * Q * 24, dtype=torch.uint8, device=device)
-    d_out = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
     L = capi.lib()
+    fallback = world > 1 and p2p is None
+    d_loc = d_all = d_out = h_all = off_all = None
+    if fallback:   # no peer access: every rank searches all clips against its shard, NCCL all_gather + merge
+        d_loc = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
+        d_all = torch.zeros(world * Q * 24, dtype=torch.uint8, device=device)
+        d_out = torch.zeros(Q * 24, dtype=torch.uint8, device=device)
+        h_all = torch.from_numpy(pool[np.arange(Q) % 50].reshape(-1).copy()).pin_memory()
+        off_all = np.arange(Q + 1, dtype=np.uint64) * n
 
     def step():
-        rc = L.tir_search(ctx._h, C.c_void_p(h_pcm.data_ptr()), off.ctypes.data_as(C.c_void_p), Q, 1, C.c_double(0.001), -1, -1,
-                          C.c_void_p(h_hits.data_ptr()))
-        if rc != 0:
-            raise capi.TirError(rc, L.tir_last_error(ctx._h).decode())
-        if world > 1:
+        if world == 1:
+            rc = L.tir_search(ctx._h, C.c_void_p(h_pcm.data_ptr()), off.ctypes.data_as(C.c_void_p), Q, 1, C.c_double(0.001), -1, -1,
+                              C.c_void_p(h_hits.data_ptr()))
+            if rc != 0:
+                raise capi.TirError(rc, L.tir_last_error(ctx._h).decode())
+        elif not fallback:
+            p2p.search(None, off, a, all_foff, 1, 0.001, pcm_ptr=h_pcm.data_ptr(), hits_ptr=h_hits.data_ptr())
+        else:
+            rc = L.tir_search(ctx._h, C.c_void_p(h_all.data_ptr()), off_all.ctypes.data_as(C.c_void_p), Q, 1, C.c_double(0.001), -1, -1,
+                              C.c_void_p(h_hits.data_ptr()))
+            if rc != 0:
+                raise capi.TirError(rc, L.tir_last_error(ctx._h).decode())
             d_loc.copy_(h_hits, non_blocking=True)
             dist.all_gather_into_tensor(d_all, d_loc)
             ctx.merge_hits_dev(d_all.data_ptr(), world, Q, d_out.data_ptr())
@@ -392,35 +597,19 @@ def search_bench(ctx, args, rank, world, device, dist, Q):
     if world > 1:
         tt = torch.tensor([ms], device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
     hits = h_hits.numpy().view(capi.HIT_DTYPE)
+    # verification of every query: the brute force on the coefficients of the same clips (a separate extraction
+    # through tir_extract on this rank; extraction parity itself is the parity object's business)
+    pcm_all = pool[np.arange(Q) % 50].reshape(-1)
+    cf, _ = ctx.extract(pcm_all, np.arange(Q + 1, dtype=np.uint64) * n)
+    y1 = 10.0 * torch.log10(torch.from_numpy(cf[:, 0].astype(np.float64)).abs()).to(device).view(Q, F_q)
+    bb, bu = _global_winners(*bf.winners_coefs1(y1, 1000), world, dist)
+    verified = _compare(torch.from_numpy(h_hits.numpy().copy()), bb, bu, F_q)
     return {"value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "queries_per_batch": Q, "seconds_per_query_clip": 3.0,
-            "h2d_bytes_per_step": int(h_pcm.numel() * 2), "d2h_bytes_per_step": Q * 24, "found": int((hits["match_count"] > 0).sum()),
-            "api": "tir_search (host PCM16 -> winner uuid / match_count / frame_count in host memory)"}
-
-
-def verify_match(hits, qv, v1, uu, n_check=4):
-    """numpy/torch restatement of the vote for a few queries (the SQLite oracle cannot ingest a
-    1M-fingerprint DB inside a bench run; it covers this path at small sizes in tests/)."""
-    import torch
-    from asterisk_tiresias_b200 import capi
-    ok = 0
-    uub = uu.cpu().numpy()
-    order = np.lexsort(uub.T[::-1])
-    rank_of = np.empty(len(order), np.int64); rank_of[order] = np.arange(len(order))
-    rank_t = torch.from_numpy(rank_of).to(v1.device)
-    for q in list(range(n_check // 2)) + list(range(len(qv) - n_check // 2, len(qv))):
-        ks, w = np.unique(np.trunc(qv[q]).astype(np.int64), return_counts=True)
-        votes = torch.zeros(v1.shape[0], dtype=torch.int64, device=v1.device)
-        for k, wk in zip(ks, w):
-            inwin = ((v1 >= int(k) * 1_000_000 - 1000) & (v1 <= int(k) * 1_000_000 + 1000)).any(dim=1)
-            votes += inwin.to(torch.int64) * int(wk)
-        best = int(votes.max().item())
-        if best == 0:
-            ok += int(hits["match_count"][q] == 0)
-            continue
-        cand = torch.nonzero(votes == best).flatten()
-        win = int(cand[torch.argmax(rank_t[cand])].item())
-        ok += int(hits["match_count"][q] == best and bytes(hits["uuid"][q].tolist()) == bytes(uub[win].tolist()))
-    return {"checked": n_check, "identical": ok}
+            "h2d_bytes_per_step_this_rank": int(h_pcm.numel() * 2) if not fallback else int(h_all.numel() * 2), "d2h_bytes_per_step": Q * 24,
+            "found": int((hits["match_count"] > 0).sum()), "verified_queries": verified,
+            "api": "tir_search (host PCM16 -> winner uuid / match_count / frame_count in host memory)" if world == 1 else
+                   ("tir_p2p_search (each rank uploads + extracts its Q/N clips; coefficients and winners cross NVLink inside the kernels)" if not fallback
+                    else "tir_search on every rank + NCCL all_gather + tir_merge_hits_dev (no peer access)")}
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -460,6 +649,8 @@ def main():
     ap.add_argument("--channels", type=int, default=1000, help="concurrent channel threads of the config[4] leg")
     ap.add_argument("--channels-db-fps", type=int, default=1_000_000)
     ap.add_argument("--no-match", action="store_true")
+    ap.add_argument("--no-db938", action="store_true", help="skip the 10 M x 938-frame table leg (runs at N >= 4 only)")
+    ap.add_argument("--no-wideband", action="store_true", help="skip the config[3] extraction leg (1024/512 at 16 kHz)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -490,7 +681,7 @@ def main():
 
     n_clips = args.clips
     t0 = time.time()
-    d_pcm = synth_clips_gpu(n_clips, rank, device)
+    d_pcm = synth_clips_gpu(n_clips, 0, device)   # the same batch on every rank: the ranks' output checksums must agree
     torch.cuda.synchronize()
     log(f"[rank {rank}] synthetic corpus: {n_clips} clips, {d_pcm.numel() * 2 / 1e9:.2f} GB, {time.time() - t0:.1f} s")
     off = np.arange(n_clips + 1, dtype=np.uint64) * N_SAMP
@@ -539,7 +730,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = F * BYTES_PER_FRAME / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 530.2 * F,   # ncu dram__bytes_read+write per launch, scaled from profiles/r1_extract_ncu_full_h.txt (529.6-530.2 B/frame)
+                "traffic": 530.2 * F,   # ncu dram__bytes_read+write per launch, scaled from the capture below (529.6-530.2 B/frame)
+                "traffic_source": "profiles/r1_extract_ncu_full_h.txt (ncu --set full capture of the same kernel; not measured in this run)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "tir_extract_kernel<512>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": F * BYTES_PER_FRAME,
                 "note": "issue/latency-bound SIMT kernel on packed f32x2 instructions (float32 FFT reproduced operation for operation; FP32-pipe floor of the DAG = 24.7% of the HBM peak); see DESIGN.md 2.3 and profiles/"}
@@ -568,11 +760,58 @@ def main():
     except Exception as e:   # a secondary figure must not take the headline down
         short_clips = {"error": str(e)}
 
+    # BASELINE config[3]'s extraction: 16 kHz wideband audio with the larger window / hop (src/fp_handler.c:35-36,
+    # the commented 1024 / 512 pair), half as many clips so that a step moves the same 4.8 GB
+    wideband = None
+    if not args.no_wideband:
+        try:
+            wsr, wwin, whop = 16000, 1024, 512
+            wn = max(1, n_clips // 2)
+            wctx = capi.Context(device=local_rank, win=wwin, hop=whop, samplerate=wsr, stream=stream.cuda_stream)
+            wctx.set_profiling(True)
+            w_pcm = synth_clips_gpu(wn, 7, device, sr=wsr)
+            wsamp = int(wsr * SECONDS)
+            woff = np.arange(wn + 1, dtype=np.uint64) * wsamp
+            wF = wn * (-(-wsamp // whop))
+            w_coef = torch.empty((wF, 2), dtype=torch.float32, device=device)
+            w_vq = torch.empty((wF, 2), dtype=torch.int32, device=device)
+            for _ in range(3):
+                wctx.extract_dev(w_pcm.data_ptr(), woff, w_coef.data_ptr(), w_vq.data_ptr())
+            torch.cuda.synchronize()
+            wk = []
+            e0.record()
+            for _ in range(args.steps):
+                wctx.extract_dev(w_pcm.data_ptr(), woff, w_coef.data_ptr(), w_vq.data_ptr())
+                wk.append(wctx.last_kernel_ms(0))
+            e1.record()
+            torch.cuda.synchronize()
+            wms = e0.elapsed_time(e1) / args.steps
+            wbytes = wF * (whop * 2 + 16)
+            wach = wbytes / (float(np.mean(wk)) * 1e-3) / 1e9
+            wideband = {"workload": "BASELINE config[3] extraction: 16 kHz wideband, win 1024 / hop 512", "clips_per_gpu": wn, "seconds_per_clip": SECONDS,
+                        "samplerate": wsr, "win": wwin, "hop": whop, "value_this_rank": wn * SECONDS / (wms * 1e-3), "unit": "audio-s/s",
+                        "ms_per_step": wms, "frames_per_second": wF / (wms * 1e-3),
+                        "roofline": {"bound": "hbm", "achieved": wach, "peak": peak, "unit": "GB/s", "frac": wach / peak, "kernel": "tir_extract_kernel<1024>",
+                                     "kernel_ms": float(np.mean(wk)), "algorithmic_bytes_per_launch": wbytes, "traffic": None}}
+            del w_pcm, w_coef, w_vq
+            wctx.close()
+            torch.cuda.empty_cache()
+        except Exception as e:   # a secondary figure must not take the headline down
+            wideband = {"error": repr(e)[:300]}
+
     # parity is reported from the cpu_baseline leg below: the oracle's output for the clips it times
     # is compared with what the timed GPU run produced for the same clips (no other use of oracle/)
     parity = None
     g_coef_head = g_vq_head = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # every rank ran the same batch: one 64-bit checksum of all its hashes and coefficient bit patterns; the ranks
+    # must agree with rank 0, whose first 500 clips are compared with the oracle below
+    ck = (d_vq.view(-1).to(torch.int64) * 1_000_003 + d_coef.view(torch.int32).view(-1).to(torch.int64)).sum()
+    ck_all = [int(ck.item())]
+    if world > 1:
+        gl = torch.zeros(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gl, ck.view(1))
+        ck_all = [int(x) for x in gl.tolist()]
+    if rank == 0 and not args.no_cpu_baseline:
         n_s = min(n_clips, 500)
         g_coef_head = d_coef.view(n_clips, FRAMES_PER_CLIP, 2)[:n_s].cpu().numpy().reshape(-1, 2)
         g_vq_head = d_vq.view(n_clips, FRAMES_PER_CLIP, 2)[:n_s].cpu().numpy().reshape(-1, 2)
@@ -651,7 +890,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample, one thread --------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:   # (the oracle run yields the parity object at every N; it is REPORTED as cpu_baseline at N = 1 only)
         from oracle import pyoracle as po
         plan = po.Plan(WIN, HOP, 40, 2, SR)
         n_s = min(n_clips, 500)
@@ -670,8 +909,10 @@ def main():
                   "coef_bit_identical": float((gc.view(np.uint32) == oc.view(np.uint32)).mean()),
                   "mfcc_max_rel_err": float(relerr.max()), "hash_identical": float((gv == ov).mean()),
                   "hash_flips": int((gv != ov).sum()), "trunc_max1_identical": float((k_g == k_o).mean()),
-                  "window_membership_identical": float((in_g == in_o).mean())}
-        cpu_baseline = {"value": n_s * SECONDS / dt, "unit": "audio-s/s", "cores": 1, "kind": "port", "seconds": dt,
+                  "window_membership_identical": float((in_g == in_o).mean()),
+                  "ranks_output_checksums_identical": len(set(ck_all)) == 1, "ranks_checked": len(ck_all),
+                  "checksum": "sum over all frames of vq*1000003 + coefficient bits (int64), whole batch, every rank"}
+        cpu_baseline = None if world > 1 else {"value": n_s * SECONDS / dt, "unit": "audio-s/s", "cores": 1, "kind": "port", "seconds": dt,
                         "host_cores_available": os.cpu_count(),
                         "sample": f"first {n_s} of the {n_clips} clips of this run, oracle restatement of libaubio pvoc+mfcc (float32 scalar C, -O2), 1 thread as in the reference"}
 
@@ -704,8 +945,21 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_clips), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "frames_per_second": world * F / (ms_step * 1e-3), "short_clips": short_clips, "match": match, "concurrent_channels": concurrent,
+            "frames_per_second": world * F / (ms_step * 1e-3), "short_clips": short_clips, "wideband_config3": wideband, "match": match,
+            "concurrent_channels": concurrent,
         }
+        # last in the line (the driver keeps the tail): the second half of the BASELINE metric, per N, with its verification
+        if isinstance(match, dict) and "value" in match:
+            v = lambda d: None if not d else f'{d["identical"]}/{d["checked"]}'   # noqa: E731
+            line["match_scaling"] = {
+                "n_gpus": world, "db": f'{match["db_fingerprints_total"]} fingerprints x {match["db_frames_per_fingerprint"]} frames',
+                "coefs1_qps": match["value"], "coefs1_ms_per_batch": match["ms_per_batch"], "coefs1_verified": v(match["verified_queries"]),
+                "coefs2_qps": match["per_query_path_coefs2"]["value"], "coefs2_verified": v(match["per_query_path_coefs2"]["verified_queries"]),
+                "tol_0.01_qps": match["tolerance_sweep"]["0.01"]["value"], "tol_0.01_verified": v(match["tolerance_sweep"]["0.01"]["verified_queries"]),
+                "tol_0.05_qps": match["tolerance_sweep"]["0.05"]["value"], "tol_0.05_verified": v(match["tolerance_sweep"]["0.05"]["verified_queries"]),
+                "search_e2e_qps": match["search_e2e"]["value"], "search_e2e_verified": v(match["search_e2e"]["verified_queries"]),
+                "db938_qps": (match.get("db_938_frames") or {}).get("value"), "db938_verified": v((match.get("db_938_frames") or {}).get("verified_queries")),
+            }
         emit(line)
     if world > 1:
         dist.barrier()

@@ -62,7 +62,9 @@ void tir_cfg_default(tir_cfg *cfg); /* 512 / 256 / 40 / 8000 Hz, device 0 */
 
 int tir_open(const tir_cfg *cfg, tir_ctx **out); /* fp_init() device side, src/fp_handler.c:68 */
 void tir_close(tir_ctx *ctx);                    /* fp_term(),             src/fp_handler.c:92 */
-const char *tir_last_error(tir_ctx *ctx);        /* text of the last failure on this context    */
+/* text of the last failure on this context; the pointer belongs to the calling thread and stays
+ * valid until that thread calls tir_last_error again (other threads may fail meanwhile) */
+const char *tir_last_error(tir_ctx *ctx);
 int tir_abi_version(void);
 
 /* ---- seam (A): extraction ------------------------------------------------------------------ */
@@ -206,8 +208,10 @@ int tir_merge_hits_dev(tir_ctx *ctx, const tir_hit *d_gathered, uint32_t n_shard
  * GPU: create, exchange the 64-byte handles (tir_p2p_handle) through the launcher, tir_p2p_connect
  * with all of them in rank order.  Several contexts of one process: tir_p2p_connect_local.
  * tir_p2p_match_dev = tir_match_dev on the local shard + that exchange; d_final receives the global
- * winners.  SPMD: all ranks call it the same number of times.  tir_p2p_error reports (after a stream
- * synchronise) the batch at which a merge gave up waiting for a peer, 0 if none. */
+ * winners (folded by the last CTA of the kernel that produced the local ones).  SPMD: all ranks call it
+ * the same number of times.  tir_p2p_error reports (after a stream synchronise) the batch at which a
+ * merge gave up waiting for a peer, 0 if none; such a batch leaves match_count = -1 in d_final.  A rank
+ * whose local match fails still publishes "no winner" rows so that its peers complete. */
 typedef struct tir_p2p tir_p2p;
 int tir_p2p_create(tir_ctx *ctx, int rank, int world, uint32_t max_queries, tir_p2p **out);
 int tir_p2p_handle(tir_p2p *p, unsigned char handle[64]);
@@ -216,6 +220,28 @@ int tir_p2p_connect_local(tir_p2p *p, tir_p2p *const *all /* world entries, rank
 int tir_p2p_match_dev(tir_p2p *p, const float *d_coef, const uint64_t *frame_off, uint32_t n_queries, int coefs,
                       double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *d_final);
 int tir_p2p_error(tir_p2p *p, uint32_t *epoch_out);
+/* Sharded SEARCH (fp_search_fingerprint_info for a batch, src/fp_handler.c:207-408, over N GPUs): the
+ * queries are sharded as well as the table.  Rank r brings only ITS OWN slice of the batch's clips --
+ * queries [first_query, first_query + n_local) of n_total, pcm/clip_off in host memory -- uploads and
+ * extracts that slice; the extraction kernel stores every coefficient it produces into all ranks'
+ * coefficient buffers over NVLink (8 bytes per frame and rank) and its last CTA raises a flag; every
+ * rank then matches ALL n_total queries against its shard, and the kernel that produces the winners
+ * exchanges them and folds the ranks' candidates (no collective call, no separate merge launch).
+ * all_frame_off[n_total + 1] are the frame offsets of the whole batch (every rank knows every clip's
+ * length: ceil(samples / hop) frames each).  Results: hits (host, [n_total], may be NULL) and/or
+ * d_final (device, may be NULL), identical on every rank.  SPMD like tir_p2p_match_dev; needs
+ * tir_p2p_create2 with max_frames >= all_frame_off[n_total].  A merge or wait that timed out leaves
+ * match_count = -1 in every hit of the batch and is reported by tir_p2p_error. */
+int tir_p2p_create2(tir_ctx *ctx, int rank, int world, uint32_t max_queries, uint64_t max_frames, tir_p2p **out);
+/* Pre-size every scratch buffer the context needs for batches of up to max_queries queries / max_frames
+ * frames / max_local_samples own samples (and rebuild a dirty index now), so that the exchange calls neither
+ * allocate nor free.  REQUIRED when several ranks are driven from ONE host thread (contexts of one process):
+ * cudaFree waits for the whole device, and an earlier rank's kernel may be waiting for a rank the thread has
+ * not enqueued yet.  One process or thread per rank does not need it. */
+int tir_p2p_reserve(tir_p2p *p, uint64_t max_local_samples);
+int tir_p2p_search(tir_p2p *p, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_local, uint32_t first_query,
+                   const uint64_t *all_frame_off, uint32_t n_total, int coefs, double tolerance, int freq_ignore_low,
+                   int freq_ignore_high, tir_hit *hits, tir_hit *d_final);
 void tir_p2p_destroy(tir_p2p *p);
 
 /* The same inside ONE process (an Asterisk module cannot be launched one process per GPU): a group

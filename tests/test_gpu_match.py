@@ -167,6 +167,32 @@ def test_long_queries_fold_in_place(gpu_ctx, oracle):
             assert gpu_result(h) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, y.shape)
 
 
+def test_very_long_queries_and_far_values(gpu_ctx, oracle):
+    """A recording of more than 65 535 frames (6 min at 44.1 kHz) must not fail nor wrap a counter: a uuid
+    that is hit by every frame collects more votes than a u16 holds (the per-query kernel switches to u32
+    counters; the shared-window path counts in u32 anyway).  And max1 values outside the histogram qprep
+    folds with (|y| >= 512: only a caller-supplied y can be) take the serial tail."""
+    rng = np.random.default_rng(99)
+    db = synth_db.make_db(40, 10, 20, seed=17, lo=10.0, hi=60.0, near_int_frac=0.7)
+    allk = np.arange(10, 60, dtype=np.float64)
+    db.append((synth.uuid_for(77_000_001), np.stack([allk + 0.0002, np.full(allk.size, 3.0)], axis=1)))   # a row next to every integer
+    db.append((synth.uuid_for(77_000_002), np.array([[600.0004, 1.0], [-700.0003, 2.0]])))               # far values
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    n_long = 70_000
+    y_long = np.stack([rng.integers(10, 60, n_long) + rng.uniform(0.0, 0.9, n_long), np.full(n_long, 3.0)], axis=1)   # 50 distinct windows: per-query path
+    y_far = np.array([[600.7, 0.0], [-700.2, 0.0], [15.5, 0.0], [600.1, 0.0], [2000.0, 0.0]])
+    ys = [y_long, y_far, db[2][1]]
+    foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    for coefs, tol in ((1, 0.001), (2, 0.5)):
+        hits = gpu_ctx.match(np.concatenate(ys), foff, coefs, tol)
+        for y, h in zip(ys, hits):
+            assert gpu_result(h) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, y.shape)
+    assert gpu_result(gpu_ctx.match(y_long, None, 1, 0.001)[0])[1] == n_long      # every frame votes for the all-integers audio
+
+
 def test_ties_resolve_to_greatest_uuid(gpu_ctx, oracle):
     # many audios with identical rows, spread over several index blocks (> 16384 uuids)
     n = 40000
