@@ -163,6 +163,81 @@ class Plan:
         return coef, y, vq
 
 
+class LibAubio:
+    """The REAL libaubio, if one is ever installed (it is not in this image: SURVEY.md 8c): the same calls
+    src/fp_handler.c:604-668 makes -- new_aubio_pvoc / new_aubio_mfcc / aubio_pvoc_do / aubio_mfcc_do -- on hops
+    fed the way aubio_source does (PCM16 / 32768, last hop zero padded).  tests/test_oracle_extract.py pins the
+    restatement against it the day the library exists; until then parity at the libaubio boundary is unpinned."""
+
+    class _FVec(C.Structure):
+        _fields_ = [("length", C.c_uint), ("data", C.POINTER(C.c_float))]
+
+    class _CVec(C.Structure):
+        _fields_ = [("length", C.c_uint), ("norm", C.POINTER(C.c_float)), ("phas", C.POINTER(C.c_float))]
+
+    _lib = None
+
+    @classmethod
+    def load(cls):
+        """-> the CDLL or None"""
+        if cls._lib is None:
+            for name in (os.environ.get("TIR_LIBAUBIO"), "libaubio.so.5", "libaubio.so"):
+                if not name:
+                    continue
+                try:
+                    L = C.CDLL(name)
+                except OSError:
+                    continue
+                L.new_fvec.restype = C.POINTER(cls._FVec); L.new_fvec.argtypes = [C.c_uint]
+                L.new_cvec.restype = C.POINTER(cls._CVec); L.new_cvec.argtypes = [C.c_uint]
+                L.new_aubio_pvoc.restype = C.c_void_p; L.new_aubio_pvoc.argtypes = [C.c_uint, C.c_uint]
+                L.new_aubio_mfcc.restype = C.c_void_p; L.new_aubio_mfcc.argtypes = [C.c_uint] * 4
+                L.aubio_pvoc_do.argtypes = [C.c_void_p, C.POINTER(cls._FVec), C.POINTER(cls._CVec)]
+                L.aubio_mfcc_do.argtypes = [C.c_void_p, C.POINTER(cls._CVec), C.POINTER(cls._FVec)]
+                for f, t in (("del_aubio_pvoc", C.c_void_p), ("del_aubio_mfcc", C.c_void_p), ("del_fvec", C.POINTER(cls._FVec)), ("del_cvec", C.POINTER(cls._CVec))):
+                    getattr(L, f).argtypes = [t]
+                cls._lib = L
+                break
+        return cls._lib
+
+    @classmethod
+    def available(cls) -> bool:
+        return cls.load() is not None
+
+    def __init__(self, win=512, hop=256, n_filters=40, n_coefs=2, samplerate=8000):
+        self.L = self.load()
+        if self.L is None:
+            raise RuntimeError("libaubio is not installed")
+        self.win, self.hop, self.n_filters, self.n_coefs, self.sr = win, hop, n_filters, n_coefs, samplerate
+
+    def extract(self, pcm):
+        """create_audio_fingerprints() (src/fp_handler.c:577-671) for in-memory PCM16 -> coef f32 [F,2], y f64 [F,2]"""
+        L = self.L
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        F = (pcm.size + self.hop - 1) // self.hop
+        pv, mf = L.new_aubio_pvoc(self.win, self.hop), L.new_aubio_mfcc(self.win, self.n_filters, self.n_coefs, self.sr)
+        buf, out, grain = L.new_fvec(self.hop), L.new_fvec(self.n_coefs), L.new_cvec(self.win)
+        coef = np.zeros((F, self.n_coefs), np.float32)
+        x = np.zeros(F * self.hop, np.float32)
+        x[:pcm.size] = pcm.astype(np.float32) / np.float32(32768.0)
+        try:
+            for f in range(F):
+                C.memmove(buf.contents.data, x[f * self.hop:].ctypes.data, self.hop * 4)
+                L.aubio_pvoc_do(pv, buf, grain)
+                L.aubio_mfcc_do(mf, grain, out)
+                coef[f] = np.ctypeslib.as_array(out.contents.data, (self.n_coefs,))
+        finally:
+            L.del_aubio_pvoc(pv), L.del_aubio_mfcc(mf), L.del_fvec(buf), L.del_fvec(out), L.del_cvec(grain)
+        with np.errstate(divide="ignore"):
+            y = 10.0 * np.log10(np.abs(coef.astype(np.float64)))
+        return coef, y
+
+
+def set_fft_kind(kind: int) -> None:
+    """0 = TIR-FFT (default), 1 = Ooura-style, 2 = float64 rounded (FFT-order sensitivity study)"""
+    lib().tiro_set_fft_kind(int(kind))
+
+
 def quantize(y: float) -> int:
     return int(lib().tiro_quantize(float(y)))
 

@@ -49,6 +49,10 @@ size_t tiro_n_frames(size_t n_samples, int hop);
 void tiro_pvoc_norm(const tiro_plan *p, const float *data, float *norm /*[win/2+1]*/);
 /* the float32 FFT used by the oracle ("TIR-FFT"): complex spectrum bins 0..win/2 of a real frame */
 void tiro_rfft(const tiro_plan *p, const float *frame, float *re, float *im);
+/* which float32 FFT runs under the pipeline: 0 = TIR-FFT (default), 1 = Ooura-style radix-2 + rftfsub
+ * untangling, 2 = float64 rounded.  Process-wide; for the FFT-order sensitivity study only. */
+void tiro_set_fft_kind(int kind);
+int tiro_get_fft_kind(void);
 /* aubio_mfcc_do on one magnitude spectrum */
 void tiro_mfcc(const tiro_plan *p, const float *norm, float *mel /*[n_filters] or NULL*/,
                float *coef /*[n_coefs]*/);

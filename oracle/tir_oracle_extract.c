@@ -310,11 +310,97 @@ static void tir_rfft_scaled(const tiro_plan *p, const float *frame, cpx *P) {
   }
 }
 
+static int g_fft_kind;
+static void alt_rfft_ooura_style(int M, const float *frame, float *re, float *im);
+static void alt_rfft_double(int M, const float *frame, float *re, float *im);
+
 void tiro_rfft(const tiro_plan *p, const float *frame, float *re, float *im) {
+  if (g_fft_kind == 1) { alt_rfft_ooura_style(p->M, frame, re, im); return; }
+  if (g_fft_kind == 2) { alt_rfft_double(p->M, frame, re, im); return; }
   cpx P[513];
   tir_rfft_scaled(p, frame, P);
   re[0] = P[0].r, im[0] = 0.f, re[p->M] = P[p->M].r, im[p->M] = 0.f;
   for (int k = 1; k < p->M; k++) re[k] = 0.5f * P[k].r, im[k] = 0.5f * P[k].i;
+}
+
+/* ==========================================================================================
+ * Alternative FFT orders (SENSITIVITY STUDY ONLY, tools/oracle_fft_sensitivity.py, tests/test_oracle_fft_orders.py).
+ * aubio delegates the FFT to FFTW3f or to Ooura's rdft depending on the distro build, so two legitimate
+ * libaubio builds already differ in float32 rounding.  tiro_set_fft_kind() swaps the FFT under the unchanged
+ * rest of the pipeline so that the identity rates between legitimate float32 FFTs can be measured:
+ *   0  TIR-FFT (default; what the GPU kernel reproduces operation for operation)
+ *   1  "Ooura-style": the frame packed as M complex points, an iterative radix-2 decimation-in-time complex FFT
+ *      (bit reversal, float twiddle table), then the real untangling in the form Ooura's rftfsub uses
+ *      (wkr = 0.5 - cos/2, wki = sin/2; a[j] -= yr ...).  Written from the published description of the
+ *      algorithm; NOT an operation-for-operation copy of aubio's bundled ooura_fft8g.c (radix-8/4/2).
+ *   2  float64 reference: the DFT evaluated in double with a radix-2 FFT, rounded to float32 at the end --
+ *      the value every float32 FFT approximates.
+ * ======================================================================================== */
+void tiro_set_fft_kind(int kind) { g_fft_kind = kind; }
+int tiro_get_fft_kind(void) { return g_fft_kind; }
+
+static unsigned bitrev(unsigned x, int bits) {
+  unsigned r = 0;
+  for (int i = 0; i < bits; i++) r = (r << 1) | ((x >> i) & 1u);
+  return r;
+}
+
+/* kind 1: X[k], k = 0..M, of the real frame (length 2M) */
+static void alt_rfft_ooura_style(int M, const float *frame, float *re, float *im) {
+  float ar[512], ai[512];
+  int bits = 0;
+  while ((1 << bits) < M) bits++;
+  for (int n = 0; n < M; n++) {
+    const unsigned r = bitrev((unsigned)n, bits);
+    ar[r] = frame[2 * n], ai[r] = frame[2 * n + 1];
+  }
+  for (int len = 2; len <= M; len <<= 1) {
+    const int half = len / 2;
+    for (int j = 0; j < half; j++) {
+      const float wr = (float)cos(TWO_PI_D * j / len), wi = (float)(-sin(TWO_PI_D * j / len));
+      for (int b = j; b < M; b += len) {
+        const int c = b + half;
+        const float tr = ar[c] * wr - ai[c] * wi, ti = ar[c] * wi + ai[c] * wr;
+        ar[c] = ar[b] - tr, ai[c] = ai[b] - ti;
+        ar[b] = ar[b] + tr, ai[b] = ai[b] + ti;
+      }
+    }
+  }
+  /* untangling in the "Z[k] - w * (Z[k] - conj Z[M-k])" form Ooura's rftfsub uses, w = ((1 + sin)/2, cos/2):
+   *   X[k] = Z[k] - w (Z[k] - conj(Z[M-k])),  k = 1..M-1 */
+  re[0] = ar[0] + ai[0], im[0] = 0.f, re[M] = ar[0] - ai[0], im[M] = 0.f;
+  for (int k = 1; k < M; k++) {
+    const int m = M - k;
+    const float wkr = 0.5f + 0.5f * (float)sin(PI_D * k / M), wki = 0.5f * (float)cos(PI_D * k / M);
+    const float xr = ar[k] - ar[m], xi = ai[k] + ai[m];
+    const float yr = wkr * xr - wki * xi, yi = wkr * xi + wki * xr;
+    re[k] = ar[k] - yr, im[k] = ai[k] - yi;
+  }
+}
+
+/* kind 2: float64 FFT of the float32 frame, rounded at the end */
+static void alt_rfft_double(int M, const float *frame, float *re, float *im) {
+  const int N = 2 * M;
+  double xr[1024], xi[1024];
+  int bits = 0;
+  while ((1 << bits) < N) bits++;
+  for (int n = 0; n < N; n++) {
+    const unsigned r = bitrev((unsigned)n, bits);
+    xr[r] = frame[n], xi[r] = 0.0;
+  }
+  for (int len = 2; len <= N; len <<= 1) {
+    const int half = len / 2;
+    for (int j = 0; j < half; j++) {
+      const double wr = cos(TWO_PI_D * j / len), wi = -sin(TWO_PI_D * j / len);
+      for (int b = j; b < N; b += len) {
+        const int c = b + half;
+        const double tr = xr[c] * wr - xi[c] * wi, ti = xr[c] * wi + xi[c] * wr;
+        xr[c] = xr[b] - tr, xi[c] = xi[b] - ti;
+        xr[b] += tr, xi[b] += ti;
+      }
+    }
+  }
+  for (int k = 0; k <= M; k++) re[k] = (float)xr[k], im[k] = (float)xi[k];
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -330,6 +416,14 @@ void tiro_pvoc_norm(const tiro_plan *p, const float *data, float *norm) {
   cpx P[513];
   for (int i = 0; i < win; i++) buf[i] = data[i] * p->w[i]; /* fvec_weight */
   for (int i = 0; i < win / 2; i++) sh[i] = buf[i + win / 2], sh[i + win / 2] = buf[i]; /* fvec_shift */
+  if (g_fft_kind != 0) { /* sensitivity study: another FFT order under the same pipeline */
+    float re[513], im[513];
+    if (g_fft_kind == 1) alt_rfft_ooura_style(M, sh, re, im);
+    else alt_rfft_double(M, sh, re, im);
+    norm[0] = fabsf(re[0]), norm[M] = fabsf(re[M]);
+    for (int k = 1; k < M; k++) norm[k] = sqrtf(re[k] * re[k] + im[k] * im[k]);
+    return;
+  }
   tir_rfft_scaled(p, sh, P);
   norm[0] = fabsf(P[0].r);
   norm[M] = fabsf(P[M].r);
