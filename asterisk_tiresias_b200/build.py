@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtiresias_gpu.so")
 TOOL = os.path.join(HERE, "..", "tools", "tir_concurrent_bench.bin")
 HOST_LIB = os.path.join(HERE, "libtiresias_host.so")
-SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_p2p.cu", "tir_tables.cpp", "tir_batcher.cpp", "tir_sqlite.cpp", "tir_group.cpp"]
+SOURCES = ["tir_api.cu", "tir_extract.cu", "tir_match.cu", "tir_p2p.cu", "tir_stream.cu", "tir_tables.cpp", "tir_batcher.cpp", "tir_sqlite.cpp", "tir_group.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 unless told not to; every fused

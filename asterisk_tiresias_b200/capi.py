@@ -113,6 +113,9 @@ def lib():
             L.tir_stream_samples.argtypes = [vp]
             L.tir_stream_finish.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, vp]
             L.tir_stream_close.argtypes = [vp]
+            L.tir_stream_frames_done.restype = C.c_uint64
+            L.tir_stream_frames_done.argtypes = [vp]
+            L.tir_stream_stats.argtypes = [vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -485,6 +488,11 @@ class Stream:
     @property
     def samples(self):
         return int(lib().tir_stream_samples(self._s))
+
+    @property
+    def frames_done(self):
+        """frames already extracted on the device (while the recording is still being fed)"""
+        return int(lib().tir_stream_frames_done(self._s))
 
     def finish(self, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
         hit = np.zeros(1, HIT_DTYPE)

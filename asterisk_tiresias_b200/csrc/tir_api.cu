@@ -138,6 +138,7 @@ int tir_open(const tir_cfg *cfg, tir_ctx **out) {
 
 void tir_close(tir_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->stream_hub) tir_stream_hub_destroy(ctx->stream_hub), ctx->stream_hub = nullptr;
   if (ctx->batcher) tir_batcher_destroy(ctx->batcher), ctx->batcher = nullptr; // serves what is queued, then joins
   if (ctx->num_sms) {
     cudaSetDevice(ctx->cfg.device);

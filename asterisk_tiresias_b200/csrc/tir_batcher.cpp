@@ -7,10 +7,7 @@
 // tir_search batch -- one H2D copy, one extraction launch, one match pass -- and hands every caller
 // its own tir_hit.  A request never waits longer than max_wait_us for company.
 //
-// tir_stream_* replaces the WAV-file round trip of the application (record_voice writes
-// /tmp/tiresias-<uuid>.wav, src/application_handler.c:153-155,248-312, which
-// create_audio_fingerprints reopens): the channel's frames are appended to a host buffer as
-// ast_read delivers them and tir_stream_finish submits the recording to the batcher.
+// (The streaming entry points tir_stream_* live in tir_stream.cu.)
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -129,11 +126,6 @@ void tir_batcher_destroy(TirBatcher *b) {
   delete b;
 }
 
-struct tir_stream {
-  tir_ctx *ctx;
-  std::vector<int16_t> pcm;
-};
-
 extern "C" {
 
 int tir_batcher_start(tir_ctx *ctx, uint32_t max_batch, uint32_t max_wait_us) {
@@ -240,33 +232,5 @@ int tir_batcher_stats(tir_ctx *ctx, uint64_t *n_requests, uint64_t *n_batches, u
   if (max_batch_seen) *max_batch_seen = m;
   return TIR_OK;
 }
-
-int tir_stream_open(tir_ctx *ctx, tir_stream **out) {
-  if (!ctx || !out) return TIR_ERR_ARG;
-  tir_stream *s = new (std::nothrow) tir_stream();
-  if (!s) return tir_fail(ctx, TIR_ERR_NOMEM, "out of memory");
-  s->ctx = ctx;
-  *out = s;
-  return TIR_OK;
-}
-
-int tir_stream_feed(tir_stream *s, const int16_t *pcm, uint32_t n_samples) {
-  if (!s || (!pcm && n_samples)) return TIR_ERR_ARG;
-  try {
-    s->pcm.insert(s->pcm.end(), pcm, pcm + n_samples);
-  } catch (const std::bad_alloc &) {
-    return tir_fail(s->ctx, TIR_ERR_NOMEM, "out of memory");
-  }
-  return TIR_OK;
-}
-
-uint64_t tir_stream_samples(const tir_stream *s) { return s ? s->pcm.size() : 0; }
-
-int tir_stream_finish(tir_stream *s, int coefs, double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hit) {
-  if (!s) return TIR_ERR_ARG;
-  return tir_search_one(s->ctx, s->pcm.data(), s->pcm.size(), coefs, tolerance, freq_ignore_low, freq_ignore_high, hit);
-}
-
-void tir_stream_close(tir_stream *s) { delete s; }
 
 } // extern "C"

@@ -12,12 +12,8 @@
 #include "tir_tables.h"
 
 struct TirDb;      // tir_match.cu
-struct TirBatcher; // tir_match.cu: pre-size the scratch of a search (no allocation / free inside the calls afterwards) and
-// rebuild a dirty index now rather than inside the next match
-int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_samples);
-int tir_db_ensure_index(tir_ctx *ctx);
-
-// tir_batcher.cpp
+struct TirBatcher; // tir_batcher.cpp
+struct TirStreamHub; // tir_stream.cu
 
 struct DevBuf {
   void *p = nullptr;
@@ -53,7 +49,8 @@ struct tir_ctx {
   int h_stage_next = 0;
   TirDb *db = nullptr;
   TirBatcher *batcher = nullptr;
-  std::mutex batcher_mu; // guards `batcher` itself (never held across GPU work)
+  TirStreamHub *stream_hub = nullptr; // streaming front-end (pump thread), created by the first tir_stream_open
+  std::mutex batcher_mu; // guards `batcher` / `stream_hub` themselves (never held across GPU work)
 };
 
 int tir_fail(tir_ctx *ctx, int code, const char *fmt, ...);
@@ -125,3 +122,5 @@ int tir_db_ensure_index(tir_ctx *ctx);
 
 // tir_batcher.cpp
 void tir_batcher_destroy(TirBatcher *b);
+// tir_stream.cu
+void tir_stream_hub_destroy(TirStreamHub *h);

@@ -186,14 +186,22 @@ int tir_search_one(tir_ctx *ctx, const int16_t *pcm, uint64_t n_samples, int coe
 int tir_batcher_stats(tir_ctx *ctx, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen);
 
 /* Streaming recording: replaces record_voice()'s /tmp/tiresias-<uuid>.wav round trip
- * (src/application_handler.c:153-155,248-312).  Feed the channel's slinear frames as ast_read
- * delivers them; tir_stream_finish() is tir_search_one() on everything fed so far. */
+ * (src/application_handler.c:153-155,248-312).  Feed the channel's slinear frames as ast_read delivers
+ * them: the hop loop (src/fp_handler.c:632-661) runs WHILE the call is recorded -- a pump thread of the
+ * context gathers, every TIR_STREAM_PERIOD_US (default 2000) microseconds, the completed hops of all live
+ * streams into one batched extraction launch; a stream keeps one hop of PCM as state and its coefficients on
+ * the device.  tir_stream_finish() adds the final zero-padded hop and waits for ONE batched match over the
+ * finishing streams of equal parameters: the time from the last feed to the result does not depend on the
+ * length of the recording.  Results equal tir_search_one() on everything fed.  One feeder thread per
+ * stream; any number of streams.  tir_stream_frames_done: frames already extracted (monitoring, tests). */
 typedef struct tir_stream tir_stream;
 int tir_stream_open(tir_ctx *ctx, tir_stream **out);
 int tir_stream_feed(tir_stream *s, const int16_t *pcm, uint32_t n_samples);
 uint64_t tir_stream_samples(const tir_stream *s);
+uint64_t tir_stream_frames_done(const tir_stream *s);
 int tir_stream_finish(tir_stream *s, int coefs, double tolerance, int freq_ignore_low, int freq_ignore_high,
                       tir_hit *hit);
+int tir_stream_stats(tir_ctx *ctx, uint64_t *n_extract_batches, uint64_t *n_frames, uint64_t *n_match_batches);
 void tir_stream_close(tir_stream *s);
 
 /* Multi-GPU (DB sharded by uuid, one context per GPU): fold the per-shard winners of the same
