@@ -96,6 +96,7 @@ def lib():
             L.tir_p2p_create2.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(vp)]
             L.tir_p2p_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_uint32, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp]
             L.tir_p2p_reserve.argtypes = [vp, C.c_uint64]
+            L.tir_db_index_stats.argtypes = [vp, vp, vp, vp, vp]
             L.tir_p2p_handle.argtypes = [vp, vp]
             L.tir_p2p_connect.argtypes = [vp, vp]
             L.tir_p2p_connect_local.argtypes = [vp, vp]
@@ -263,6 +264,12 @@ class Context:
         a, r = C.c_uint64(), C.c_uint64()
         self._chk(lib().tir_db_stats(self._h, C.byref(a), C.byref(r)))
         return int(a.value), int(r.value)
+
+    def db_index_stats(self):
+        """-> dict(full_builds, tail_builds, tail_audios, tombstones)"""
+        v = [C.c_uint64() for _ in range(4)]
+        self._chk(lib().tir_db_index_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("full_builds", "tail_builds", "tail_audios", "tombstones"), (int(x.value) for x in v)))
 
     # ---- match ------------------------------------------------------------------------------
     def match(self, y, frame_off=None, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):

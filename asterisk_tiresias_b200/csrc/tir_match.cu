@@ -78,6 +78,19 @@ static UuidKey uuid_key(const uint8_t *u) {
   return k;
 }
 
+// One sorted index over the audios [a0, a1) of the master copy.  The table has two: `main` (built by a load or
+// a full rebuild) and `tail` (the audios added since: a few, re-indexed in about a millisecond when one is
+// added), so that tir_db_add never forces the 10^9-row sort; tir_db_remove marks the audio's rank in `dead`
+// (consulted where a block's winners are picked), its rows stay in the index until the next full rebuild.
+struct TirIndex {
+  bool built = false;
+  uint32_t a0 = 0, a1 = 0; // audio range
+  uint32_t n_blocks = 0;
+  uint64_t n_indexed = 0;  // rows in the index (NULL max1 rows and rows of audios dead at build time are left out)
+  uint32_t n_dead = 0;     // audios removed since the build
+  DevBuf order, rank_of, dead, key1, uid, key2, block_start;
+};
+
 struct TirDb {
   // master copy (device) + small host mirrors
   uint64_t n_audio = 0, n_rows = 0;
@@ -88,18 +101,24 @@ struct TirDb {
   std::unordered_map<UuidKey, uint32_t, UuidKeyHash> by_uuid;
   bool lookup_ready = false;
   uint64_t n_alive = 0;
-  // index
-  bool dirty = true;
-  uint32_t n_blocks = 0;
-  uint64_t n_indexed = 0;
-  DevBuf order, key1, uid, key2, block_start;
+  // indices
+  bool dirty = true;      // main must be rebuilt over everything (after a load, or when the tail / the dead outgrew their budget)
+  bool tail_dirty = false; // the tail's audio range grew
+  TirIndex main, tail;
+  uint64_t n_full_builds = 0, n_tail_builds = 0;
 };
+
+static void index_free(TirIndex &x) {
+  for (DevBuf *b : {&x.order, &x.rank_of, &x.dead, &x.key1, &x.uid, &x.key2, &x.block_start})
+    if (b->p) cudaFree(b->p), b->p = nullptr, b->cap = 0;
+  x.built = false, x.n_blocks = 0, x.n_indexed = 0, x.n_dead = 0, x.a0 = x.a1 = 0;
+}
 
 void tir_db_destroy(TirDb *db) {
   if (!db) return;
-  for (DevBuf *b : {&db->uuids, &db->row_off, &db->v1, &db->v2, &db->alive, &db->order, &db->key1, &db->uid, &db->key2,
-                    &db->block_start})
+  for (DevBuf *b : {&db->uuids, &db->row_off, &db->v1, &db->v2, &db->alive})
     if (b->p) cudaFree(b->p);
+  index_free(db->main), index_free(db->tail);
   delete db;
 }
 
@@ -146,8 +165,9 @@ __global__ void tir_invert_kernel(const uint32_t *__restrict__ order, uint32_t n
 // they get the all-ones key, sort to the end and are cut off.
 __global__ void tir_row_keys_kernel(const uint64_t *__restrict__ row_off, const int32_t *__restrict__ v1,
                                     const int32_t *__restrict__ v2, const uint8_t *__restrict__ alive,
-                                    const uint32_t *__restrict__ rank_of, uint32_t n_audio, uint64_t *__restrict__ keys,
-                                    uint64_t *__restrict__ vals, unsigned long long *__restrict__ n_valid) {
+                                    const uint32_t *__restrict__ rank_of, uint32_t n_audio, uint64_t r_begin,
+                                    uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
+                                    unsigned long long *__restrict__ n_valid) {
   const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (a >= n_audio) return;
   const uint64_t r0 = row_off[a], r1 = row_off[a + 1];
@@ -158,8 +178,8 @@ __global__ void tir_row_keys_kernel(const uint64_t *__restrict__ row_off, const 
   for (uint64_t r = r0 + lane; r < r1; r += 32) {
     const int32_t a1 = v1[r], a2 = v2[r];
     const bool ok = live && a1 != TIR_NULL_V;
-    keys[r] = ok ? ((blk << 32) | (uint64_t)((uint32_t)a1 ^ 0x80000000u)) : ~0ull;
-    vals[r] = ((uint64_t)(uint32_t)a2 << 32) | local;
+    keys[r - r_begin] = ok ? ((blk << 32) | (uint64_t)((uint32_t)a1 ^ 0x80000000u)) : ~0ull; // (key / value arrays start at the range's first row)
+    vals[r - r_begin] = ((uint64_t)(uint32_t)a2 << 32) | local;
     cnt += ok;
   }
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -189,81 +209,123 @@ __global__ void tir_block_start_kernel(const uint64_t *__restrict__ keys, uint64
   block_start[b] = lo;
 }
 
-static int db_build_index(tir_ctx *ctx, TirDb *db) {
+// device temporaries of a build, freed on every exit path
+struct TirTmp {
+  std::vector<void *> p;
+  ~TirTmp() {
+    for (void *q : p)
+      if (q) cudaFree(q);
+  }
+  template <typename T>
+  cudaError_t get(T **out, size_t bytes) {
+    void *q = nullptr;
+    const cudaError_t e = cudaMalloc(&q, std::max<size_t>(bytes, 16));
+    if (e == cudaSuccess) p.push_back(q);
+    *out = (T *)q;
+    return e;
+  }
+};
+
+// (re)build index `x` over the audios [a0, a1) of the master copy
+static int db_build_index(tir_ctx *ctx, TirDb *db, TirIndex &x, uint32_t a0, uint32_t a1) {
   cudaStream_t st = ctx->stream;
-  const uint32_t n = (uint32_t)db->n_audio;
-  const uint64_t rows = db->n_rows;
-  db->n_blocks = (n + TIR_BLOCK_UUIDS - 1) / TIR_BLOCK_UUIDS;
-  db->n_indexed = 0;
+  const uint32_t n = a1 - a0;
+  x.built = false, x.a0 = a0, x.a1 = a1, x.n_dead = 0, x.n_indexed = 0;
+  x.n_blocks = (n + TIR_BLOCK_UUIDS - 1) / TIR_BLOCK_UUIDS;
   int rc;
-  if ((rc = tir_reserve(ctx, db->order, (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
-  if ((rc = tir_reserve(ctx, db->block_start, ((size_t)db->n_blocks + 1) * 8))) return rc;
+  if ((rc = tir_reserve(ctx, x.order, (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
+  if ((rc = tir_reserve(ctx, x.rank_of, (size_t)std::max<uint32_t>(n, 1) * 4))) return rc;
+  if ((rc = tir_reserve(ctx, x.dead, (size_t)std::max<uint32_t>(n, 1)))) return rc;
+  if ((rc = tir_reserve(ctx, x.block_start, ((size_t)x.n_blocks + 1) * 8))) return rc;
+  TIR_CUDA(ctx, cudaMemsetAsync(x.dead.p, 0, std::max<uint32_t>(n, 1), st));
+  const uint64_t r_begin = n ? db->h_row_off[a0] : 0, rows = n ? db->h_row_off[a1] - r_begin : 0;
   if (n == 0 || rows == 0) {
-    TIR_CUDA(ctx, cudaMemsetAsync(db->block_start.p, 0, ((size_t)db->n_blocks + 1) * 8, st));
-    db->dirty = false;
+    TIR_CUDA(ctx, cudaMemsetAsync(x.block_start.p, 0, ((size_t)x.n_blocks + 1) * 8, st));
+    x.built = true;
     return TIR_OK;
   }
+  const uint8_t *uu = (const uint8_t *)db->uuids.p + (size_t)a0 * 16;
+  const uint64_t *roff = (const uint64_t *)db->row_off.p + a0; // absolute row offsets: v1 / v2 are indexed as they are
+  const uint8_t *alive = (const uint8_t *)db->alive.p + a0;
+  TirTmp tmpbuf;
   // ---- rank audios by uuid bytes: two stable 64-bit radix passes (low half, then high half)
   uint64_t *hi, *lo, *k_in, *k_out;
-  uint32_t *idx_a, *idx_b, *rank_of;
-  TIR_CUDA(ctx, cudaMalloc(&hi, (size_t)n * 8));
-  TIR_CUDA(ctx, cudaMalloc(&lo, (size_t)n * 8));
-  TIR_CUDA(ctx, cudaMalloc(&k_in, (size_t)n * 8));
-  TIR_CUDA(ctx, cudaMalloc(&k_out, (size_t)n * 8));
-  TIR_CUDA(ctx, cudaMalloc(&idx_a, (size_t)n * 4));
-  TIR_CUDA(ctx, cudaMalloc(&idx_b, (size_t)n * 4));
-  TIR_CUDA(ctx, cudaMalloc(&rank_of, (size_t)n * 4));
+  uint32_t *idx_a, *idx_b;
+  TIR_CUDA(ctx, tmpbuf.get(&hi, (size_t)n * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&lo, (size_t)n * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&k_in, (size_t)n * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&k_out, (size_t)n * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&idx_a, (size_t)n * 4));
+  TIR_CUDA(ctx, tmpbuf.get(&idx_b, (size_t)n * 4));
+  uint32_t *rank_of = (uint32_t *)x.rank_of.p;
   const uint32_t gb = (n + 255) / 256;
-  tir_uuid_keys_kernel<<<gb, 256, 0, st>>>((const uint8_t *)db->uuids.p, n, hi, lo, idx_a);
+  tir_uuid_keys_kernel<<<gb, 256, 0, st>>>(uu, n, hi, lo, idx_a);
   size_t tmp_bytes = 0, tmp2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lo, k_out, idx_a, idx_b, (int)n, 0, 64, st);
   cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint64_t *)nullptr,
                                   (uint64_t *)nullptr, (long long)rows, 0, 64, st);
   tmp_bytes = std::max(tmp_bytes, tmp2);
   void *tmp = nullptr;
-  TIR_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes));
+  TIR_CUDA(ctx, tmpbuf.get(&tmp, tmp_bytes));
   TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lo, k_out, idx_a, idx_b, (int)n, 0, 64, st));
   tir_gather_u64_kernel<<<gb, 256, 0, st>>>(hi, idx_b, n, k_in);
-  TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, idx_b, (uint32_t *)db->order.p, (int)n, 0, 64, st));
-  tir_invert_kernel<<<gb, 256, 0, st>>>((const uint32_t *)db->order.p, n, rank_of);
+  TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, idx_b, (uint32_t *)x.order.p, (int)n, 0, 64, st));
+  tir_invert_kernel<<<gb, 256, 0, st>>>((const uint32_t *)x.order.p, n, rank_of);
   ctx->launches += 5;
-  TIR_CUDA(ctx, cudaFree(hi));
-  TIR_CUDA(ctx, cudaFree(lo));
-  TIR_CUDA(ctx, cudaFree(k_in));
-  TIR_CUDA(ctx, cudaFree(k_out));
-  TIR_CUDA(ctx, cudaFree(idx_a));
-  TIR_CUDA(ctx, cudaFree(idx_b));
-  // ---- rows: (block, v1) keys -> radix sort -> SoA
+  // ---- rows: (block, v1) keys -> radix sort -> SoA.  Row arrays are indexed from the range's first row.
   uint64_t *rk, *rv, *rk2, *rv2;
   unsigned long long *d_nvalid;
-  TIR_CUDA(ctx, cudaMalloc(&rk, rows * 8));
-  TIR_CUDA(ctx, cudaMalloc(&rv, rows * 8));
-  TIR_CUDA(ctx, cudaMalloc(&rk2, rows * 8));
-  TIR_CUDA(ctx, cudaMalloc(&rv2, rows * 8));
-  TIR_CUDA(ctx, cudaMalloc(&d_nvalid, 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rk, rows * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rv, rows * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rk2, rows * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rv2, rows * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&d_nvalid, 8));
   TIR_CUDA(ctx, cudaMemsetAsync(d_nvalid, 0, 8, st));
   tir_row_keys_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, st>>>(
-      (const uint64_t *)db->row_off.p, (const int32_t *)db->v1.p, (const int32_t *)db->v2.p, (const uint8_t *)db->alive.p,
-      rank_of, n, rk, rv, d_nvalid);
+      roff, (const int32_t *)db->v1.p, (const int32_t *)db->v2.p, alive, rank_of, n, r_begin, rk, rv, d_nvalid);
   // block ids need ceil(log2(n_blocks)) bits above the 32 key bits; the all-ones tail sorts last anyway
   TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rk, rk2, rv, rv2, (long long)rows, 0, 64, st));
   unsigned long long nvalid = 0;
   TIR_CUDA(ctx, cudaMemcpyAsync(&nvalid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
   TIR_CUDA(ctx, cudaStreamSynchronize(st));
-  db->n_indexed = nvalid;
-  if ((rc = tir_reserve(ctx, db->key1, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
-  if ((rc = tir_reserve(ctx, db->uid, std::max<size_t>(nvalid, 1) * 2 + 64))) return rc;
-  if ((rc = tir_reserve(ctx, db->key2, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
+  x.n_indexed = nvalid;
+  if ((rc = tir_reserve(ctx, x.key1, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, x.uid, std::max<size_t>(nvalid, 1) * 2 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, x.key2, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
   if (nvalid)
-    tir_split_rows_kernel<<<(uint32_t)((nvalid + 255) / 256), 256, 0, st>>>(rk2, rv2, nvalid, (int32_t *)db->key1.p,
-                                                                            (uint16_t *)db->uid.p, (int32_t *)db->key2.p);
-  tir_block_start_kernel<<<(db->n_blocks + 1 + 255) / 256, 256, 0, st>>>(rk2, nvalid, db->n_blocks,
-                                                                         (uint64_t *)db->block_start.p);
+    tir_split_rows_kernel<<<(uint32_t)((nvalid + 255) / 256), 256, 0, st>>>(rk2, rv2, nvalid, (int32_t *)x.key1.p,
+                                                                            (uint16_t *)x.uid.p, (int32_t *)x.key2.p);
+  tir_block_start_kernel<<<(x.n_blocks + 1 + 255) / 256, 256, 0, st>>>(rk2, nvalid, x.n_blocks, (uint64_t *)x.block_start.p);
   ctx->launches += 4;
   TIR_CUDA(ctx, cudaStreamSynchronize(st));
   TIR_CUDA(ctx, cudaGetLastError());
-  cudaFree(rk), cudaFree(rv), cudaFree(rk2), cudaFree(rv2), cudaFree(d_nvalid), cudaFree(tmp), cudaFree(rank_of);
-  db->dirty = false;
+  x.built = true;
+  return TIR_OK;
+}
+
+// Bring the indices up to date.  A full rebuild (main over everything alive) happens after a load and when
+// the tail or the tombstones have outgrown their budget; otherwise only the small tail is re-indexed.
+static int db_refresh(tir_ctx *ctx, TirDb *db) {
+  int rc;
+  const uint32_t n = (uint32_t)db->n_audio;
+  if (!db->dirty && db->main.built) {
+    const uint64_t main_rows = db->main.a1 ? db->h_row_off[db->main.a1] : 0, tail_rows = db->n_rows - main_rows;
+    if (tail_rows > std::max<uint64_t>(1u << 20, main_rows / 16) || (uint64_t)db->main.n_dead * 4 > (uint64_t)(db->main.a1 - db->main.a0) + 64) db->dirty = true;
+  }
+  if (db->dirty || !db->main.built) {
+    if ((rc = db_build_index(ctx, db, db->main, 0, n))) return rc;
+    index_free(db->tail);
+    db->tail.a0 = db->tail.a1 = n, db->tail.built = true;
+    db->dirty = false, db->tail_dirty = false;
+    db->n_full_builds++;
+    return TIR_OK;
+  }
+  if (db->tail_dirty || !db->tail.built) {
+    if ((rc = db_build_index(ctx, db, db->tail, db->main.a1, n))) return rc;
+    // audios of the new range that were removed before this build are simply not indexed (alive == 0)
+    db->tail_dirty = false;
+    db->n_tail_builds++;
+  }
   return TIR_OK;
 }
 
@@ -610,7 +672,7 @@ template <int COEFS, typename PW>
 __device__ __forceinline__ void tir_pblock_pass(const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
                                                 const TirBatch *__restrict__ batch, const uint64_t (*s_range)[2], uint32_t K,
                                                 uint32_t *s_pat, uint32_t *s_tab, uint32_t *s_full, bool hashed, uint32_t uid0,
-                                                uint32_t n_uuid, uint32_t rank0, int tid) {
+                                                uint32_t n_uuid, uint32_t rank0, int tid, const uint8_t *__restrict__ dead) {
   uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
   for (uint32_t i = tid; i < n_uuid * sizeof(PW) / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_pat)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -653,6 +715,7 @@ __device__ __forceinline__ void tir_pblock_pass(const uint16_t *__restrict__ uid
       const uint32_t pv = sizeof(PW) == 2 ? (pw[e >> 1] >> ((e & 1) * 16)) & 0xffffu : pw[e & 3];
       if (!pv) continue;
       const uint32_t r1v = rank0 + uid0 + PER16 * i + e;
+      if (dead && dead[r1v - 1]) continue; // removed since the index was built (tir_db_remove): never a winner
       if (!hashed) atomicMax(&s_tab[pv], r1v);
       else if (!tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, pv, r1v, nullptr, nullptr)) *s_full = 1;
     }
@@ -665,7 +728,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_pattern_block_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
                              const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
                              TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys,
-                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list) {
+                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list, const uint8_t *__restrict__ dead) {
   TIR_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: keys | values
@@ -694,10 +757,10 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   if (!any) return; // (CTA-uniform) no row of this block lies in any window
   const uint32_t rank0 = blk * TIR_BLOCK_UUIDS + 1;
   if (K <= 16) {
-    tir_pblock_pass<COEFS, uint16_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid);
+    tir_pblock_pass<COEFS, uint16_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid, dead);
   } else {
-    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS / 2, rank0, tid);
-    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, TIR_BLOCK_UUIDS / 2, TIR_BLOCK_UUIDS / 2, rank0, tid);
+    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS / 2, rank0, tid, dead);
+    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, TIR_BLOCK_UUIDS / 2, TIR_BLOCK_UUIDS / 2, rank0, tid, dead);
   }
   if (!hashed) {
     const uint32_t np = 1u << K;
@@ -826,7 +889,7 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
                      TirBatch *__restrict__ batch, const uint32_t *__restrict__ order, const uint8_t *__restrict__ uuids,
-                     tir_hit *__restrict__ hits, const TirP2PArgs x) {
+                     tir_hit *__restrict__ hits, const TirP2PArgs x, const uint8_t *__restrict__ dead) {
   TIR_PDL_PROLOGUE();
   if (!(batch->use_general || batch->overflow)) return;
   extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word (WIDE: u32); then the warps' bitmaps
@@ -896,12 +959,13 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     for (int i = tid; i < CNT_WORDS; i += TIR_MATCH_THREADS) {
       const uint32_t pair = s_cnt[i];
       if (WIDE) {
-        if (pair) bestv = max(bestv, ((unsigned long long)pair << 32) | ((uint64_t)blk * TIR_BLOCK_UUIDS + i));
+        const uint64_t rk = (uint64_t)blk * TIR_BLOCK_UUIDS + i;
+        if (pair && !(dead && dead[rk])) bestv = max(bestv, ((unsigned long long)pair << 32) | rk);
       } else {
         const uint32_t c0v = pair & 0xffffu, c1v = pair >> 16;
         const uint64_t rank0 = (uint64_t)blk * TIR_BLOCK_UUIDS + 2 * i;
-        if (c0v) bestv = max(bestv, ((unsigned long long)c0v << 32) | rank0);
-        if (c1v) bestv = max(bestv, ((unsigned long long)c1v << 32) | (rank0 + 1));
+        if (c0v && !(dead && dead[rank0])) bestv = max(bestv, ((unsigned long long)c0v << 32) | rank0);
+        if (c1v && !(dead && dead[rank0 + 1])) bestv = max(bestv, ((unsigned long long)c1v << 32) | (rank0 + 1));
       }
     }
     for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
@@ -983,6 +1047,8 @@ static size_t match_scratch_bytes(uint32_t n_queries, uint64_t F) { return match
 int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_samples) {
   int rc;
   if ((rc = tir_reserve(ctx, ctx->d_qmeta, match_scratch_bytes(n_queries, F)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_qmeta2, match_scratch_bytes(n_queries, F)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_hits2, (size_t)2 * std::max<uint32_t>(n_queries, 1) * sizeof(tir_hit)))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_hits, (size_t)std::max<uint32_t>(n_queries, 1) * sizeof(tir_hit)))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_pcm, n_samples * sizeof(int16_t) + 16))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_coef, std::max<uint64_t>(F, 1) * TIR_N_COEFS * sizeof(float)))) return rc;
@@ -996,35 +1062,23 @@ int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_
 }
 
 int tir_db_ensure_index(tir_ctx *ctx) {
-  if (!ctx->db || !ctx->db->dirty) return TIR_OK;
-  return db_build_index(ctx, ctx->db);
+  if (!ctx->db) return TIR_OK;
+  return db_refresh(ctx, ctx->db);
 }
 
-static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef, const uint64_t *frame_off,
-                           uint32_t n_queries, int coefs, double tolerance, int ign_lo, int ign_hi, tir_hit *d_hits,
-                           const TirP2PArgs *p2p = nullptr) {
-  const TirP2PArgs x = p2p ? *p2p : TirP2PArgs{nullptr, 0, 1, 0, 0, nullptr};
-  if (coefs < 1 || coefs > TIR_N_COEFS) return tir_fail(ctx, TIR_ERR_ARG, "Wrong coefs count. max[%d], coefs[%d]", TIR_N_COEFS, coefs);
-  if (!ctx->db) return tir_fail(ctx, TIR_ERR_STATE, "no fingerprint DB loaded");
-  if (n_queries == 0) return TIR_OK;
-  TirDb *db = ctx->db;
-  int rc;
-  if (db->dirty && (rc = db_build_index(ctx, db))) return rc;
+// the match chain of one index: qprep -> pattern_block -> resolve -> per-query kernel (PDL-chained), hits to d_hits
+static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, const double *d_y, const float *d_coef,
+                     const uint64_t *frame_off, uint32_t n_queries, uint64_t F, const TirMatchParams &mp, bool wide,
+                     tir_hit *d_hits, const TirP2PArgs &x) {
   cudaStream_t st = ctx->stream;
-  const uint64_t F = frame_off[n_queries] - frame_off[0];
-  if (frame_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "frame_off[0] must be 0");
-  bool wide = false; // a query of more than 65 535 frames: the per-query kernel counts in u32
-  for (uint32_t q = 0; q < n_queries; q++) {
-    if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 0x7fffffffull)
-      return tir_fail(ctx, TIR_ERR_ARG, "frame_off must be non-decreasing (and a query shorter than 2^31 frames)");
-    wide |= frame_off[q + 1] - frame_off[q] > 65535;
-  }
+  int rc;
+  const int coefs = mp.coefs;
   // scratch: frame_off (device) | n_windows | best | batch | max_rank1 | pattern hash keys | values | pattern list | windows
   const TirMatchScratch L = match_scratch_layout(n_queries, F);
   const size_t o_foff = L.o_foff, o_nw = L.o_nw, o_best = L.o_best, o_batch = L.o_batch, o_maxr = L.o_maxr, o_gkeys = L.o_gkeys,
                o_gvals = L.o_gvals, o_plist = L.o_plist, o_win = L.o_win, bytes = L.bytes;
-  if ((rc = tir_reserve(ctx, ctx->d_qmeta, bytes))) return rc;
-  unsigned char *d = (unsigned char *)ctx->d_qmeta.p;
+  if ((rc = tir_reserve(ctx, scratch, bytes))) return rc;
+  unsigned char *d = (unsigned char *)scratch.p;
   void *hp;
   int slot;
   if ((rc = tir_stage_acquire(ctx, ((size_t)n_queries + 1) * 8, &hp, &slot))) return rc;
@@ -1032,12 +1086,6 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, hp, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
   if ((rc = tir_stage_release(ctx, slot))) return rc;
   TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_plist - o_best, st)); // best, batch, max_rank1, pattern hash table
-  TirMatchParams mp;
-  mp.coefs = coefs;
-  mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
-  mp.use_lo = ign_lo > 0, mp.use_hi = ign_hi > 0;
-  mp.thr_lo = mp.use_lo ? 10 * log10((double)ign_lo) : 0.0; // :294, :300
-  mp.thr_hi = mp.use_hi ? 10 * log10((double)ign_hi) : 0.0;
   const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
   unsigned long long *d_best = (unsigned long long *)(d + o_best);
@@ -1050,21 +1098,23 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   else
     TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw, d_batch));
   ctx->launches++;
-  if (db->n_blocks && db->n_indexed) {
-    const int32_t *k1 = (const int32_t *)db->key1.p, *k2 = (const int32_t *)db->key2.p;
-    const uint16_t *uid = (const uint16_t *)db->uid.p;
-    const uint64_t *bst = (const uint64_t *)db->block_start.p;
+  if (idx.n_blocks && idx.n_indexed) {
+    const int32_t *k1 = (const int32_t *)idx.key1.p, *k2 = (const int32_t *)idx.key2.p;
+    const uint16_t *uid = (const uint16_t *)idx.uid.p;
+    const uint64_t *bst = (const uint64_t *)idx.block_start.p;
+    const uint32_t *order = (const uint32_t *)idx.order.p;
+    const uint8_t *uuids = (const uint8_t *)db->uuids.p + (size_t)idx.a0 * 16; // `order` holds audio numbers relative to the range
+    const uint8_t *dead = idx.n_dead ? (const uint8_t *)idx.dead.p : nullptr;
     if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
-    const dim3 pgrid(db->n_blocks), pthr(TIR_MATCH_THREADS);
-    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
-    else TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist));
+    const dim3 pgrid(idx.n_blocks), pthr(TIR_MATCH_THREADS);
+    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
+    else TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
     TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
                                  (const uint32_t *)d_nw, d_foff, n_queries, d_batch, (const uint32_t *)d_maxr,
-                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist,
-                                 (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits, x));
+                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, order, uuids, d_hits, x));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
-    const uint64_t items = (uint64_t)db->n_blocks * n_queries;
+    const uint64_t items = (uint64_t)idx.n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);
     if (!ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
       TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
@@ -1076,8 +1126,8 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     auto gen = coefs >= 2 ? (wide ? tir_match_kernel<2, true> : tir_match_kernel<2, false>)
                           : (wide ? tir_match_kernel<1, true> : tir_match_kernel<1, false>);
     TIR_CUDA(ctx, tir_launch_pdl_smem(gen, dim3(ggrid), dim3(TIR_MATCH_THREADS), (size_t)TIR_GEN_SMEM_OF(wide), st, k1, uid, k2, bst,
-                                      (const TirWindow *)d_win, (const uint32_t *)d_nw, d_foff, d_best, db->n_blocks, n_queries, d_batch,
-                                      (const uint32_t *)db->order.p, (const uint8_t *)db->uuids.p, d_hits, x));
+                                      (const TirWindow *)d_win, (const uint32_t *)d_nw, d_foff, d_best, idx.n_blocks, n_queries, d_batch,
+                                      order, uuids, d_hits, x, dead));
     ctx->launches += 3;
     if (ctx->profiling) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
@@ -1090,6 +1140,48 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x, n_queries))) return rc;
   }
   TIR_CUDA(ctx, cudaGetLastError());
+  return TIR_OK;
+}
+
+static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef, const uint64_t *frame_off,
+                           uint32_t n_queries, int coefs, double tolerance, int ign_lo, int ign_hi, tir_hit *d_hits,
+                           const TirP2PArgs *p2p = nullptr) {
+  const TirP2PArgs none{nullptr, 0, 1, 0, 0, nullptr};
+  const TirP2PArgs x = p2p ? *p2p : none;
+  if (coefs < 1 || coefs > TIR_N_COEFS) return tir_fail(ctx, TIR_ERR_ARG, "Wrong coefs count. max[%d], coefs[%d]", TIR_N_COEFS, coefs);
+  if (!ctx->db) return tir_fail(ctx, TIR_ERR_STATE, "no fingerprint DB loaded");
+  if (n_queries == 0) return TIR_OK;
+  TirDb *db = ctx->db;
+  int rc;
+  if ((rc = db_refresh(ctx, db))) return rc;
+  const uint64_t F = frame_off[n_queries] - frame_off[0];
+  if (frame_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "frame_off[0] must be 0");
+  bool wide = false; // a query of more than 65 535 frames: the per-query kernel counts in u32
+  for (uint32_t q = 0; q < n_queries; q++) {
+    if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 0x7fffffffull)
+      return tir_fail(ctx, TIR_ERR_ARG, "frame_off must be non-decreasing (and a query shorter than 2^31 frames)");
+    wide |= frame_off[q + 1] - frame_off[q] > 65535;
+  }
+  TirMatchParams mp;
+  mp.coefs = coefs;
+  mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
+  mp.use_lo = ign_lo > 0, mp.use_hi = ign_hi > 0;
+  mp.thr_lo = mp.use_lo ? 10 * log10((double)ign_lo) : 0.0; // :294, :300
+  mp.thr_hi = mp.use_hi ? 10 * log10((double)ign_hi) : 0.0;
+  const bool have_tail = db->tail.n_blocks && db->tail.n_indexed, have_main = db->main.n_blocks && db->main.n_indexed;
+  if (!have_tail) return run_chain(ctx, db, db->main, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, d_hits, x);
+  if (!have_main) return run_chain(ctx, db, db->tail, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, d_hits, x);
+  // audios added since the last full build live in the small tail index: both chains run, the two winners of
+  // every query are folded like the winners of two shards (greatest count, ties -> greatest uuid)
+  if ((rc = tir_reserve(ctx, ctx->d_hits2, (size_t)2 * n_queries * sizeof(tir_hit)))) return rc;
+  tir_hit *h2 = (tir_hit *)ctx->d_hits2.p;
+  if ((rc = run_chain(ctx, db, db->main, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, h2, none))) return rc;
+  if ((rc = run_chain(ctx, db, db->tail, ctx->d_qmeta2, d_y, d_coef, frame_off, n_queries, F, mp, wide, h2 + n_queries, none))) return rc;
+  tir_merge_hits_kernel<<<(n_queries + 127) / 128, 128, 0, ctx->stream>>>(h2, 2, n_queries, d_hits);
+  TIR_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x))) return rc;
+  if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x, n_queries))) return rc;
   return TIR_OK;
 }
 
@@ -1131,7 +1223,7 @@ static int db_load_common(tir_ctx *ctx, uint32_t n_audio, const void *uuid, cons
   db->h_alive.assign(n_audio, 1);
   db->by_uuid.clear(), db->lookup_ready = false;
   db->dirty = true;
-  return db_build_index(ctx, db);
+  return db_refresh(ctx, db);
 }
 
 int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const uint64_t *row_off, const int32_t *v1,
@@ -1192,7 +1284,7 @@ int tir_db_add(tir_ctx *ctx, const uint8_t uuid[16], const int32_t *v1, const in
   db->h_alive.push_back(1);
   if (db->lookup_ready) db->by_uuid[uuid_key(uuid)] = (uint32_t)n;
   db->n_audio = n + 1, db->n_rows = rows + n_rows, db->n_alive++;
-  db->dirty = true; // the index is rebuilt by the next match
+  db->tail_dirty = true; // the next match re-indexes the small tail only (db_refresh)
   return TIR_OK;
 }
 
@@ -1212,7 +1304,34 @@ int tir_db_remove(tir_ctx *ctx, const uint8_t uuid[16]) {
   TIR_CUDA(ctx, cudaMemcpyAsync((uint8_t *)db->alive.p + a, &zero, 1, cudaMemcpyHostToDevice, ctx->stream));
   TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   db->n_alive--;
-  db->dirty = true;
+  // tombstone in the index that holds the audio (consulted where a block's winners are picked); an audio of a
+  // range that is not indexed yet is left out by the build itself
+  for (TirIndex *x : {&db->main, &db->tail}) {
+    if (!x->built || a < x->a0 || a >= x->a1 || (x == &db->tail && db->tail_dirty)) continue;
+    uint32_t rank = 0;
+    const uint8_t one = 1;
+    TIR_CUDA(ctx, cudaMemcpyAsync(&rank, (const uint32_t *)x->rank_of.p + (a - x->a0), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TIR_CUDA(ctx, cudaMemcpyAsync((uint8_t *)x->dead.p + rank, &one, 1, cudaMemcpyHostToDevice, ctx->stream));
+    TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    x->n_dead++;
+  }
+  return TIR_OK;
+}
+
+int tir_db_index_stats(tir_ctx *ctx, uint64_t *n_full_builds, uint64_t *n_tail_builds, uint64_t *tail_audios, uint64_t *tombstones) {
+  if (!ctx) return TIR_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  uint64_t a = 0, b = 0, c = 0, d = 0;
+  if (TirDb *db = ctx->db) {
+    a = db->n_full_builds, b = db->n_tail_builds;
+    c = db->main.built ? db->n_audio - db->main.a1 : 0;
+    d = (uint64_t)db->main.n_dead + db->tail.n_dead;
+  }
+  if (n_full_builds) *n_full_builds = a;
+  if (n_tail_builds) *n_tail_builds = b;
+  if (tail_audios) *tail_audios = c;
+  if (tombstones) *tombstones = d;
   return TIR_OK;
 }
 

@@ -118,11 +118,18 @@ int tir_db_load(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*uuid)[16], const
  * output of tir_extract_dev); the library keeps its own copy. */
 int tir_db_load_dev(tir_ctx *ctx, uint32_t n_audio, const uint8_t (*d_uuid)[16], const uint64_t *d_row_off,
                     const int32_t *d_v1, const int32_t *d_v2, uint64_t n_rows);
-/* create_audio_fingerprint_info(): the rows of one new audio, src/fp_handler.c:538-575 */
+/* create_audio_fingerprint_info(): the rows of one new audio, src/fp_handler.c:538-575 (no full re-sort: see
+ * tir_db_index_stats) */
 int tir_db_add(tir_ctx *ctx, const uint8_t uuid[16], const int32_t *v1, const int32_t *v2, uint32_t n_rows);
 /* delete from audio_fingerprint where audio_uuid=..., src/fp_handler.c:147 */
 int tir_db_remove(tir_ctx *ctx, const uint8_t uuid[16]);
 int tir_db_stats(tir_ctx *ctx, uint64_t *n_audio, uint64_t *n_rows);
+/* How the index follows tir_db_add / tir_db_remove: an added audio goes into a small TAIL index (re-sorted in about
+ * a millisecond by the next search; its winners are folded with the main index's like those of a second shard), a
+ * removed audio gets a tombstone that the kernels consult where they pick a block's winners.  The full sort of the
+ * table runs only after a load, or when the tail holds more than max(2^20, rows/16) rows or a quarter of the main
+ * index is dead.  Counters: full sorts so far, tail sorts, audios in the tail, tombstones. */
+int tir_db_index_stats(tir_ctx *ctx, uint64_t *n_full_builds, uint64_t *n_tail_builds, uint64_t *tail_audios, uint64_t *tombstones);
 
 /* ---- SQLite <-> device table -----------------------------------------------------------------
  * SQLite stays the system of record (schema src/fp_handler.c:686-753).  `sqlite3_db` is the

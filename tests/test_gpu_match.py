@@ -236,6 +236,65 @@ def test_add_remove_follow_sqlite(gpu_ctx, oracle):
     assert e.value.code == capi.ERR_NOTFOUND
 
 
+def test_add_remove_are_incremental_on_a_large_table(oracle):
+    """tir_db_add / tir_db_remove against a 1 M-fingerprint table (94 M rows): no full re-sort -- the added audios
+    live in the tail index, the removed ones get tombstones -- the first search after a change costs about a
+    millisecond instead of the table's sort, and the results follow SQLite (on the part of the table SQLite can
+    hold: the probes below only involve audios that exist in both)."""
+    import time
+    import torch
+    ctx = capi.Context(device=0)
+    try:
+        n, F = 1_000_000, 94
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        uu = torch.randint(0, 256, (n, 16), dtype=torch.uint8, device="cuda", generator=g)
+        v1 = torch.randint(20_100_000, 29_900_000, (n * F,), dtype=torch.int32, device="cuda", generator=g)   # never within 0.1 of an integer <= 19
+        v1 = v1 - (v1 % 1_000_000) + 100_000 + (v1 % 800_000)                                                 # ... nor of any integer at all
+        v2 = torch.randint(-5_000_000, 20_000_000, (n * F,), dtype=torch.int32, device="cuda", generator=g)
+        ro = torch.arange(n + 1, device="cuda", dtype=torch.int64) * F
+        ctx.db_load_dev(n, uu.data_ptr(), ro.data_ptr(), v1.data_ptr(), v2.data_ptr(), n * F)
+        assert ctx.db_index_stats()["full_builds"] == 1
+        # the big table cannot match anything at tolerance 0.01 (no max1 within 0.1 of an integer): the small DB decides
+        db = synth_db.make_db(40, 10, 30, seed=31, lo=14.0, hi=19.0, near_int_frac=0.7)
+        sq = oracle.SqliteDB()
+        rng = np.random.default_rng(8)
+        queries = [db[i][1] for i in (0, 5, 17)] + [synth_db.random_y(rng, 50, lo=14.0, hi=19.0, near_int_frac=0.6) for _ in range(5)]
+
+        def check():
+            for y in queries:
+                assert gpu_result(ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01))
+
+        ctx.match(queries[0], tolerance=0.01)      # warm
+        for i, (u, y) in enumerate(db):
+            v = synth_db.quantize_y(y)
+            sq.add_audio(u, y)
+            ctx.db_add(capi.uuid_to_bytes(u), v[:, 0], v[:, 1])
+            if i in (0, 1, 20):
+                t0 = time.perf_counter(); ctx.match(queries[0], tolerance=0.01); dt = time.perf_counter() - t0
+                assert dt < 0.05, dt                # (a full sort of 94 M rows takes ~10x that)
+                check()
+        check()
+        st = ctx.db_index_stats()
+        assert st["full_builds"] == 1 and st["tail_audios"] == 40 and st["tail_builds"] >= 3
+        for i in (5, 0, 33):                        # tombstones in the tail; one in the main index too
+            sq.delete_audio(db[i][0])
+            ctx.db_remove(capi.uuid_to_bytes(db[i][0]))
+        ctx.db_remove(uu[12345].cpu().numpy())
+        t0 = time.perf_counter(); ctx.match(queries[0], tolerance=0.01); dt = time.perf_counter() - t0
+        assert dt < 0.05, dt
+        check()
+        st = ctx.db_index_stats()
+        assert st["full_builds"] == 1 and st["tombstones"] == 4 and ctx.db_stats()[0] == n + 40 - 4
+        # a removed audio of the MAIN index really stops winning: give a probe that only it can match
+        probe = np.stack([np.full(5, 7.0), np.zeros(5)], axis=1)
+        ctx.db_add(capi.uuid_to_bytes(synth.uuid_for(88_000_001)), np.full(3, 7_000_300, np.int32), np.zeros(3, np.int32))
+        assert ctx.match(probe, tolerance=0.001)[0]["match_count"] == 5
+        ctx.db_remove(capi.uuid_to_bytes(synth.uuid_for(88_000_001)))
+        assert ctx.match(probe, tolerance=0.001)[0]["match_count"] == 0
+    finally:
+        ctx.close()
+
+
 def test_argument_rules(gpu_ctx):
     db = synth_db.make_db(5, 5, 5, seed=4)
     gpu_ctx.db_load(*synth_db.db_arrays(db))
