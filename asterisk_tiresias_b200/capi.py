@@ -95,6 +95,11 @@ def lib():
             L.tir_p2p_create.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(vp)]
             L.tir_p2p_create2.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(vp)]
             L.tir_p2p_search.argtypes = [vp, vp, u64p, C.c_uint32, C.c_uint32, u64p, C.c_uint32, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp]
+            L.tir_group_stats.argtypes = [vp, vp, vp]
+            L.tir_group_batcher_start.argtypes = [vp, C.c_uint32, C.c_uint32]
+            L.tir_group_batcher_stop.argtypes = [vp]
+            L.tir_group_search_one.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_int, vp]
+            L.tir_group_batcher_stats.argtypes = [vp, vp, vp, vp]
             L.tir_p2p_reserve.argtypes = [vp, C.c_uint64]
             L.tir_db_index_stats.argtypes = [vp, vp, vp, vp, vp]
             L.tir_p2p_handle.argtypes = [vp, vp]
@@ -458,6 +463,28 @@ class Group:
         a, r = C.c_uint64(), C.c_uint64()
         self._chk(lib().tir_group_db_stats(self._g, C.byref(a), C.byref(r)))
         return int(a.value), int(r.value)
+
+    def stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(lib().tir_group_stats(self._g, C.byref(a), C.byref(b)))
+        return {"fused": int(a.value), "copy_path": int(b.value)}
+
+    def batcher_start(self, max_batch=1024, max_wait_us=300):
+        self._chk(lib().tir_group_batcher_start(self._g, max_batch, max_wait_us))
+
+    def batcher_stop(self):
+        self._chk(lib().tir_group_batcher_stop(self._g))
+
+    def batcher_stats(self):
+        v = [C.c_uint64() for _ in range(3)]
+        self._chk(lib().tir_group_batcher_stats(self._g, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    def search_one(self, pcm, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        hit = np.zeros(1, HIT_DTYPE)
+        self._chk(lib().tir_group_search_one(self._g, _p(pcm), pcm.size, coefs, float(tolerance), int(freq_ignore_low), int(freq_ignore_high), _p(hit)))
+        return hit[0]
 
     def search(self, pcm, clip_off=None, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)

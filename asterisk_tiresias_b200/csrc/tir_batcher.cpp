@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <new>
 #include <thread>
@@ -53,7 +54,10 @@ struct Slot {
 } // namespace
 
 struct TirBatcher {
-  tir_ctx *ctx = nullptr;
+  // what one sealed batch runs: tir_search of a context, or tir_group_search of a group of devices
+  std::function<int(const int16_t *, const uint64_t *, uint32_t, int, double, int, int, tir_hit *)> search;
+  std::function<std::string()> last_error;
+  int device = 0; // where the pinned staging buffers are registered
   uint32_t max_batch = 1024, max_wait_us = 200;
   std::mutex mu;
   std::condition_variable cv_work, cv_space, cv_done;
@@ -95,10 +99,9 @@ void TirBatcher::run() {
     for (size_t i = 0; i < nb; i++) off[i] = s.members[i]->off;
     off[nb] = s.used; // members were appended in offset order
     hits.resize(nb);
-    const int rc = tir_search(ctx, s.h_pcm, off.data(), (uint32_t)nb, s.params.coefs, s.params.tol, s.params.ign_lo,
-                              s.params.ign_hi, hits.data());
+    const int rc = search(s.h_pcm, off.data(), (uint32_t)nb, s.params.coefs, s.params.tol, s.params.ign_lo, s.params.ign_hi, hits.data());
     lk.lock();
-    if (rc != TIR_OK) last_err = tir_last_error(ctx);
+    if (rc != TIR_OK) last_err = last_error();
     n_batches++, n_requests += nb;
     if (nb > max_seen) max_seen = nb;
     for (size_t i = 0; i < nb; i++) {
@@ -128,31 +131,94 @@ void tir_batcher_destroy(TirBatcher *b) {
 
 extern "C" {
 
-int tir_batcher_start(tir_ctx *ctx, uint32_t max_batch, uint32_t max_wait_us) {
-  if (!ctx || max_batch == 0) return tir_fail(ctx, TIR_ERR_ARG, "bad batcher arguments");
-  std::lock_guard<std::mutex> lk(ctx->batcher_mu);
-  if (ctx->batcher) return tir_fail(ctx, TIR_ERR_STATE, "batcher already running");
+} // extern "C"
+
+// a dispatcher over any batched search function (tir_internal.h)
+TirBatcher *tir_batcher_create(int device, uint32_t max_batch, uint32_t max_wait_us,
+                               std::function<int(const int16_t *, const uint64_t *, uint32_t, int, double, int, int, tir_hit *)> search,
+                               std::function<std::string()> last_error) {
   TirBatcher *b = new (std::nothrow) TirBatcher();
-  if (!b) return tir_fail(ctx, TIR_ERR_NOMEM, "out of memory");
-  b->ctx = ctx, b->max_batch = max_batch, b->max_wait_us = max_wait_us;
+  if (!b) return nullptr;
+  b->search = std::move(search), b->last_error = std::move(last_error), b->device = device;
+  b->max_batch = max_batch, b->max_wait_us = max_wait_us;
   // staging: room for max_batch recordings of 8 s at 8 kHz (4 s at 16 kHz) each, at least 4 M samples; a recording
   // that does not fit an empty buffer is searched directly by its caller
-  cudaSetDevice(ctx->cfg.device);
+  cudaSetDevice(device);
   const uint64_t cap = std::max<uint64_t>((uint64_t)max_batch * 65536ull, 4ull << 20);
   for (Slot &s : b->slot) {
     if (cudaMallocHost((void **)&s.h_pcm, cap * sizeof(int16_t)) != cudaSuccess) {
       tir_batcher_destroy(b);
-      return tir_fail(ctx, TIR_ERR_NOMEM, "cudaMallocHost(%llu) for the batch staging buffers failed",
-                      (unsigned long long)(cap * sizeof(int16_t)));
+      return nullptr;
     }
     s.cap = cap;
     s.members.reserve(max_batch);
   }
   b->slot[0].open = true;
   b->worker = std::thread([b] {
-    cudaSetDevice(b->ctx->cfg.device);
+    cudaSetDevice(b->device);
     b->run();
   });
+  return b;
+}
+
+// one caller's recording through the dispatcher; rc of the batch it rode in (message in *err)
+int tir_batcher_submit(TirBatcher *b, const int16_t *pcm, uint64_t n_samples, int coefs, double tolerance, int freq_ignore_low,
+                       int freq_ignore_high, tir_hit *hit, std::string *err) {
+  Params p;
+  p.coefs = coefs, p.tol = tolerance, p.ign_lo = freq_ignore_low, p.ign_hi = freq_ignore_high;
+  Request r;
+  r.n = n_samples, r.hit = hit;
+  std::unique_lock<std::mutex> lk(b->mu);
+  Slot *s = nullptr;
+  for (;;) {
+    if (b->stop) {
+      if (err) *err = "batcher is stopping";
+      return TIR_ERR_STATE;
+    }
+    s = &b->slot[b->fill];
+    if (s->open && (s->members.empty() || s->params == p) && s->members.size() < b->max_batch && s->used + n_samples <= s->cap) break;
+    if (s->open && !s->members.empty()) { // cannot join this batch: send it off now, take the next one
+      s->sealed = true;
+      b->cv_work.notify_all();
+    }
+    b->cv_space.wait(lk);
+  }
+  if (s->members.empty()) s->params = p, s->t_first = std::chrono::steady_clock::now();
+  r.off = s->used, s->used += n_samples;
+  s->members.push_back(&r);
+  s->copying++;
+  if (s->members.size() == 1 || s->members.size() >= b->max_batch) b->cv_work.notify_all();
+  int16_t *dst = s->h_pcm + r.off;
+  lk.unlock();
+  if (n_samples) std::memcpy(dst, pcm, n_samples * sizeof(int16_t)); // in parallel with the other callers
+  lk.lock();
+  if (--s->copying == 0) b->cv_work.notify_all();
+  b->cv_done.wait(lk, [&] { return r.done; });
+  if (r.rc != TIR_OK && err) *err = b->last_err;
+  return r.rc;
+}
+
+bool tir_batcher_fits(TirBatcher *b, uint64_t n_samples) { return n_samples <= b->slot[0].cap; }
+void tir_batcher_enter(TirBatcher *b) { b->callers++; }
+void tir_batcher_leave(TirBatcher *b) { b->callers--; }
+void tir_batcher_counters(TirBatcher *b, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen) {
+  std::lock_guard<std::mutex> lk(b->mu);
+  *n_requests = b->n_requests, *n_batches = b->n_batches, *max_batch_seen = b->max_seen;
+}
+
+extern "C" {
+
+int tir_batcher_start(tir_ctx *ctx, uint32_t max_batch, uint32_t max_wait_us) {
+  if (!ctx || max_batch == 0) return tir_fail(ctx, TIR_ERR_ARG, "bad batcher arguments");
+  std::lock_guard<std::mutex> lk(ctx->batcher_mu);
+  if (ctx->batcher) return tir_fail(ctx, TIR_ERR_STATE, "batcher already running");
+  TirBatcher *b = tir_batcher_create(
+      ctx->cfg.device, max_batch, max_wait_us,
+      [ctx](const int16_t *pcm, const uint64_t *off, uint32_t n, int coefs, double tol, int lo, int hi, tir_hit *hits) {
+        return tir_search(ctx, pcm, off, n, coefs, tol, lo, hi, hits);
+      },
+      [ctx] { return std::string(tir_last_error(ctx)); });
+  if (!b) return tir_fail(ctx, TIR_ERR_NOMEM, "could not start the batcher (pinned staging buffers)");
   ctx->batcher = b;
   return TIR_OK;
 }
@@ -186,34 +252,9 @@ int tir_search_one(tir_ctx *ctx, const int16_t *pcm, uint64_t n_samples, int coe
   const uint64_t direct_off[2] = {0, n_samples};
   if (!b || n_samples > b->slot[0].cap) // no dispatcher (or an oversized recording): a batch of one
     return tir_search(ctx, pcm, direct_off, 1, coefs, tolerance, freq_ignore_low, freq_ignore_high, hit);
-  Params p;
-  p.coefs = coefs, p.tol = tolerance, p.ign_lo = freq_ignore_low, p.ign_hi = freq_ignore_high;
-  Request r;
-  r.n = n_samples, r.hit = hit;
-  std::unique_lock<std::mutex> lk(b->mu);
-  Slot *s = nullptr;
-  for (;;) {
-    if (b->stop) return tir_fail(ctx, TIR_ERR_STATE, "batcher is stopping");
-    s = &b->slot[b->fill];
-    if (s->open && (s->members.empty() || s->params == p) && s->members.size() < b->max_batch && s->used + n_samples <= s->cap) break;
-    if (s->open && !s->members.empty()) { // cannot join this batch: send it off now, take the next one
-      s->sealed = true;
-      b->cv_work.notify_all();
-    }
-    b->cv_space.wait(lk);
-  }
-  if (s->members.empty()) s->params = p, s->t_first = std::chrono::steady_clock::now();
-  r.off = s->used, s->used += n_samples;
-  s->members.push_back(&r);
-  s->copying++;
-  if (s->members.size() == 1 || s->members.size() >= b->max_batch) b->cv_work.notify_all();
-  int16_t *dst = s->h_pcm + r.off;
-  lk.unlock();
-  if (n_samples) std::memcpy(dst, pcm, n_samples * sizeof(int16_t)); // in parallel with the other callers
-  lk.lock();
-  if (--s->copying == 0) b->cv_work.notify_all();
-  b->cv_done.wait(lk, [&] { return r.done; });
-  if (r.rc != TIR_OK) return tir_fail(ctx, r.rc, "%s", b->last_err.c_str());
+  std::string err;
+  const int rc = tir_batcher_submit(b, pcm, n_samples, coefs, tolerance, freq_ignore_low, freq_ignore_high, hit, &err);
+  if (rc != TIR_OK) return tir_fail(ctx, rc, "%s", err.c_str());
   return TIR_OK;
 }
 

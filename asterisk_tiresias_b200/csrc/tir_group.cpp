@@ -1,14 +1,18 @@
 // tir_group.cpp -- several GPUs inside ONE process.
 //
-// bench.py scales with one process per GPU and NCCL (torch.distributed), but an Asterisk module is a
-// single process: to use the 8 GPUs of a box it needs the same scheme without a launcher.  A
-// tir_group owns one tir_ctx per device; table audio_fingerprint is sharded by uuid
-// (tir_shard_of) over the contexts; a search extracts the query recordings on the first device,
-// hands the coefficients to every device over NVLink (cudaMemcpyPeerAsync), lets every device match
-// against its shard concurrently, pulls the per-shard winners (24 bytes per query and shard) back
-// and folds them with tir_merge_hits_dev -- the same data flow as the NCCL path: only the per-query
-// top-1 of every shard crosses the links.  Results equal those of one context holding the whole
-// table (tests/test_gpu_group.py).
+// bench.py scales with one process per GPU (torch.distributed), but an Asterisk module is a single
+// process: to use the 8 GPUs of a box it needs the same scheme without a launcher.  A tir_group owns one
+// tir_ctx per device; table audio_fingerprint is sharded by uuid (tir_shard_of) over the contexts.
+// A search is the sharded search of tir_p2p_search driven from this one process (regions connected
+// with tir_p2p_connect_local): the batch's clips are cut into one slice per device, every device uploads
+// and extracts its slice, the coefficients cross NVLink inside the extraction kernel, every device matches
+// all queries against its shard and the winners are exchanged and folded inside the match kernels.  One
+// host thread enqueues all devices, so every buffer is sized BEFORE the first enqueue (tir_p2p_reserve).
+// Devices without peer access (or a batch beyond the exchange buffers) take the copy-based path: extract
+// on the first device, cudaMemcpyPeerAsync of coefficients and winners, tir_merge_hits_dev.
+// tir_group_batcher_start / tir_group_search_one: the concurrent front-end of config[4] (1 000 dialplan
+// channels) on top of the group.  Results equal those of one context holding the whole table
+// (tests/test_gpu_group.py).
 #include <cstring>
 #include <new>
 
@@ -27,6 +31,16 @@ struct tir_group {
   cudaEvent_t ev_coef = nullptr;  // device 0: coefficients ready
   std::mutex mu;
   std::string err;
+  // fused path
+  std::vector<tir_p2p *> p2p;
+  bool p2p_tried = false;
+  uint32_t p2p_queries = 0;
+  uint64_t p2p_frames = 0, p2p_samples = 0;
+  std::vector<tir_hit *> d_final; // per device
+  std::vector<size_t> final_cap;
+  uint64_t n_fused = 0, n_copy = 0;
+  TirBatcher *batcher = nullptr;
+  std::mutex batcher_mu;
 };
 
 static int gfail(tir_group *g, int code, const char *msg) {
@@ -54,9 +68,19 @@ static int grow(tir_group *g, void **p, size_t *cap, size_t bytes, int device) {
 
 extern "C" {
 
+static void group_drop_p2p(tir_group *g) {
+  for (size_t i = 0; i < g->ctx.size(); i++)
+    if (g->ctx[i]) cudaSetDevice(g->ctx[i]->cfg.device), cudaDeviceSynchronize();
+  for (tir_p2p *p : g->p2p) tir_p2p_destroy(p);
+  g->p2p.clear();
+}
+
 void tir_group_close(tir_group *g) {
   if (!g) return;
+  if (g->batcher) tir_batcher_destroy(g->batcher), g->batcher = nullptr;
+  group_drop_p2p(g);
   for (size_t i = 0; i < g->ctx.size(); i++) {
+    if (g->ctx[i] && i < g->d_final.size() && g->d_final[i]) cudaSetDevice(g->ctx[i]->cfg.device), cudaFree(g->d_final[i]);
     if (g->ctx[i]) cudaSetDevice(g->ctx[i]->cfg.device), cudaDeviceSynchronize();
     if (i < g->d_coef.size() && g->d_coef[i]) cudaFree(g->d_coef[i]);
     if (i < g->d_hits.size() && g->d_hits[i]) cudaFree(g->d_hits[i]);
@@ -81,6 +105,7 @@ int tir_group_open(const tir_cfg *cfg, const int *devices, int n_devices, tir_gr
   g->d_coef.assign(n_devices, nullptr), g->coef_cap.assign(n_devices, 0);
   g->d_hits.assign(n_devices, nullptr), g->hits_cap.assign(n_devices, 0);
   g->ev.assign(n_devices, nullptr);
+  g->d_final.assign(n_devices, nullptr), g->final_cap.assign(n_devices, 0);
   for (int i = 0; i < n_devices; i++) {
     tir_cfg c = *cfg;
     c.device = devices[i], c.stream = nullptr; // every context runs on a stream of its own
@@ -165,12 +190,103 @@ int tir_group_db_stats(tir_group *g, uint64_t *n_audio, uint64_t *n_rows) {
   return TIR_OK;
 }
 
+// (re)create the exchange objects for batches of up to n_queries / n_frames / n_samples; false: no peer access
+static bool group_ensure_p2p(tir_group *g, uint32_t n_queries, uint64_t n_frames, uint64_t n_samples) {
+  const int S = (int)g->ctx.size();
+  if (S < 2) return false;
+  // Kernels of different shards wait for one another (flags over peer memory): that needs one DEVICE per shard.
+  // Several shards on one device (tests; a box with fewer GPUs than configured) would rely on the streams of one
+  // device running concurrently, which nothing guarantees (shared hardware queues): they take the copy path.
+  for (int a = 0; a < S; a++)
+    for (int b = a + 1; b < S; b++)
+      if (g->ctx[a]->cfg.device == g->ctx[b]->cfg.device) return false;
+  if (!g->p2p.empty() && n_queries <= g->p2p_queries && n_frames <= g->p2p_frames && n_samples <= g->p2p_samples) return true;
+  if (g->p2p_tried && g->p2p.empty()) return false; // tried before: these devices cannot reach each other
+  g->p2p_tried = true;
+  group_drop_p2p(g);
+  const uint32_t q = std::max<uint32_t>(4096, n_queries * 2);
+  const uint64_t f = std::max<uint64_t>(1u << 20, n_frames * 2), smp = std::max<uint64_t>(64u << 20, n_samples * 2);
+  std::vector<tir_p2p *> ps(S, nullptr);
+  bool ok = true;
+  for (int s = 0; s < S && ok; s++) ok = tir_p2p_create2(g->ctx[s], s, S, q, f, &ps[s]) == TIR_OK;
+  for (int s = 0; s < S && ok; s++) ok = tir_p2p_connect_local(ps[s], ps.data()) == TIR_OK;
+  for (int s = 0; s < S && ok; s++) ok = tir_p2p_reserve(ps[s], smp) == TIR_OK;
+  if (!ok) {
+    for (tir_p2p *p : ps) tir_p2p_destroy(p);
+    return false;
+  }
+  g->p2p = ps, g->p2p_queries = q, g->p2p_frames = f, g->p2p_samples = smp;
+  return true;
+}
+
+static int group_search_copy_path(tir_group *g, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
+                                  double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits);
+
 int tir_group_search(tir_group *g, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
                      double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits) {
   if (!g || !clip_off || !hits || (!pcm && n_clips && clip_off[n_clips] > clip_off[0])) return gfail(g, TIR_ERR_ARG, "null argument");
   if (coefs < 1 || coefs > TIR_N_COEFS) return gfail(g, TIR_ERR_ARG, "Wrong coefs count."); // src/fp_handler.c:247
   if (n_clips == 0) return TIR_OK;
   std::lock_guard<std::mutex> lk(g->mu);
+  const int S = (int)g->ctx.size();
+  const int hop = g->ctx[0]->cfg.hop;
+  std::vector<uint64_t> foff((size_t)n_clips + 1, 0);
+  for (uint32_t c = 0; c < n_clips; c++) {
+    if (clip_off[c + 1] < clip_off[c]) return gfail(g, TIR_ERR_ARG, "clip_off must be non-decreasing");
+    foff[c + 1] = foff[c] + tir_n_frames(clip_off[c + 1] - clip_off[c], hop);
+  }
+  const uint64_t total = clip_off[n_clips] - clip_off[0];
+  if (!group_ensure_p2p(g, n_clips, foff[n_clips], total)) {
+    g->n_copy++;
+    return group_search_copy_path(g, pcm, clip_off, n_clips, coefs, tolerance, freq_ignore_low, freq_ignore_high, hits);
+  }
+  // ---- fused path: one slice of the clips per device (balanced by samples), all devices enqueued by this thread
+  std::vector<uint32_t> cut((size_t)S + 1, n_clips);
+  cut[0] = 0;
+  for (int s = 1; s < S; s++) {
+    const uint64_t want = clip_off[0] + total * (uint64_t)s / (uint64_t)S;
+    uint32_t c = cut[s - 1];
+    while (c < n_clips && clip_off[c] < want) c++;
+    cut[s] = c;
+  }
+  int rc;
+  const size_t hit_bytes = (size_t)n_clips * sizeof(tir_hit);
+  for (int s = 0; s < S; s++) {
+    if ((rc = grow(g, (void **)&g->d_final[s], &g->final_cap[s], hit_bytes, g->ctx[s]->cfg.device))) return rc;
+    if (tir_db_ensure_index_public(g->ctx[s]) != TIR_OK) return gfail(g, TIR_ERR_CUDA, tir_last_error(g->ctx[s])); // no sort between the enqueues
+  }
+  for (int s = 0; s < S; s++) {
+    const uint32_t a = cut[s], b = cut[s + 1];
+    rc = tir_p2p_search(g->p2p[s], pcm, clip_off + a, b - a, a, foff.data(), n_clips, coefs, tolerance, freq_ignore_low, freq_ignore_high,
+                        nullptr, g->d_final[s]);
+    if (rc != TIR_OK) { // (the ranks already enqueued complete through the time-out of their waits)
+      gfail(g, rc, tir_last_error(g->ctx[s]));
+      group_drop_p2p(g), g->p2p_tried = false;
+      return rc;
+    }
+  }
+  tir_ctx *c0 = g->ctx[0];
+  TIRG_CUDA(g, cudaSetDevice(c0->cfg.device));
+  TIRG_CUDA(g, cudaMemcpyAsync(hits, g->d_final[0], hit_bytes, cudaMemcpyDeviceToHost, c0->stream));
+  TIRG_CUDA(g, cudaStreamSynchronize(c0->stream));
+  uint32_t bad = 0;
+  tir_p2p_error(g->p2p[0], &bad);
+  if (bad) {
+    if (getenv("TIR_DEBUG")) {
+      for (int s = 0; s < S; s++) {
+        uint32_t e = 0;
+        tir_p2p_error(g->p2p[s], &e);
+        fprintf(stderr, "[tir_group] rank %d: clips [%u, %u), error word %u\n", s, cut[s], cut[s + 1], e);
+      }
+    }
+    return gfail(g, TIR_ERR_CUDA, "a device did not answer in time (tir_p2p_error)");
+  }
+  g->n_fused++;
+  return TIR_OK;
+}
+
+static int group_search_copy_path(tir_group *g, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
+                                  double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits) {
   const int S = (int)g->ctx.size();
   tir_ctx *c0 = g->ctx[0];
   const int dev0 = c0->cfg.device;
@@ -223,6 +339,72 @@ int tir_group_search(tir_group *g, const int16_t *pcm, const uint64_t *clip_off,
   TIRG_CUDA(g, cudaMemcpyAsync(hits, g->d_out, hit_bytes, cudaMemcpyDeviceToHost, c0->stream));
   TIRG_CUDA(g, cudaStreamSynchronize(c0->stream));
   for (uint32_t q = 0; q < n_clips; q++) hits[q].frame_count = (int32_t)(foff[q + 1] - foff[q]); // also when no shard had a row
+  return TIR_OK;
+}
+
+int tir_group_stats(tir_group *g, uint64_t *n_fused, uint64_t *n_copy_path) {
+  if (!g) return TIR_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g->mu);
+  if (n_fused) *n_fused = g->n_fused;
+  if (n_copy_path) *n_copy_path = g->n_copy;
+  return TIR_OK;
+}
+
+int tir_group_batcher_start(tir_group *g, uint32_t max_batch, uint32_t max_wait_us) {
+  if (!g || max_batch == 0) return gfail(g, TIR_ERR_ARG, "bad batcher arguments");
+  std::lock_guard<std::mutex> lk(g->batcher_mu);
+  if (g->batcher) return gfail(g, TIR_ERR_STATE, "batcher already running");
+  g->batcher = tir_batcher_create(
+      g->ctx[0]->cfg.device, max_batch, max_wait_us,
+      [g](const int16_t *pcm, const uint64_t *off, uint32_t n, int coefs, double tol, int lo, int hi, tir_hit *hits) {
+        return tir_group_search(g, pcm, off, n, coefs, tol, lo, hi, hits);
+      },
+      [g] { return std::string(tir_group_last_error(g)); });
+  return g->batcher ? TIR_OK : gfail(g, TIR_ERR_NOMEM, "could not start the batcher");
+}
+
+int tir_group_batcher_stop(tir_group *g) {
+  if (!g) return TIR_ERR_ARG;
+  TirBatcher *b;
+  {
+    std::lock_guard<std::mutex> lk(g->batcher_mu);
+    b = g->batcher, g->batcher = nullptr;
+  }
+  tir_batcher_destroy(b);
+  return TIR_OK;
+}
+
+int tir_group_search_one(tir_group *g, const int16_t *pcm, uint64_t n_samples, int coefs, double tolerance, int freq_ignore_low,
+                         int freq_ignore_high, tir_hit *hit) {
+  if (!g || !hit || (!pcm && n_samples)) return gfail(g, TIR_ERR_ARG, "null argument");
+  if (coefs < 1 || coefs > TIR_N_COEFS) return gfail(g, TIR_ERR_ARG, "Wrong coefs count."); // src/fp_handler.c:247
+  TirBatcher *b;
+  {
+    std::lock_guard<std::mutex> lk(g->batcher_mu);
+    b = g->batcher;
+    if (b) tir_batcher_enter(b);
+  }
+  const uint64_t off[2] = {0, n_samples};
+  if (!b || !tir_batcher_fits(b, n_samples)) {
+    if (b) tir_batcher_leave(b);
+    return tir_group_search(g, pcm, off, 1, coefs, tolerance, freq_ignore_low, freq_ignore_high, hit);
+  }
+  std::string err;
+  const int rc = tir_batcher_submit(b, pcm, n_samples, coefs, tolerance, freq_ignore_low, freq_ignore_high, hit, &err);
+  tir_batcher_leave(b);
+  return rc == TIR_OK ? rc : gfail(g, rc, err.c_str());
+}
+
+int tir_group_batcher_stats(tir_group *g, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen) {
+  if (!g) return TIR_ERR_ARG;
+  uint64_t r = 0, n = 0, m = 0;
+  {
+    std::lock_guard<std::mutex> lk(g->batcher_mu);
+    if (g->batcher) tir_batcher_counters(g->batcher, &r, &n, &m);
+  }
+  if (n_requests) *n_requests = r;
+  if (n_batches) *n_batches = n;
+  if (max_batch_seen) *max_batch_seen = m;
   return TIR_OK;
 }
 

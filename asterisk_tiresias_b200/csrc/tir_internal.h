@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -118,9 +119,20 @@ int tir_p2p_merge_launch(tir_ctx *ctx, const TirP2PArgs &a, uint32_t n_queries);
 // tir_match.cu: pre-size the scratch of a search (no allocation / free inside the calls afterwards) and
 // rebuild a dirty index now rather than inside the next match
 int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_samples);
-int tir_db_ensure_index(tir_ctx *ctx);
+int tir_db_ensure_index(tir_ctx *ctx);        // caller holds ctx->mu
+int tir_db_ensure_index_public(tir_ctx *ctx); // takes it
 
-// tir_batcher.cpp
+// tir_batcher.cpp: the batching dispatcher, over any batched search function (a context's tir_search, a group's
+// tir_group_search)
+TirBatcher *tir_batcher_create(int device, uint32_t max_batch, uint32_t max_wait_us,
+                               std::function<int(const int16_t *, const uint64_t *, uint32_t, int, double, int, int, tir_hit *)> search,
+                               std::function<std::string()> last_error);
+int tir_batcher_submit(TirBatcher *b, const int16_t *pcm, uint64_t n_samples, int coefs, double tolerance, int freq_ignore_low,
+                       int freq_ignore_high, tir_hit *hit, std::string *err);
+bool tir_batcher_fits(TirBatcher *b, uint64_t n_samples);
+void tir_batcher_enter(TirBatcher *b);
+void tir_batcher_leave(TirBatcher *b);
+void tir_batcher_counters(TirBatcher *b, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen);
 void tir_batcher_destroy(TirBatcher *b);
 // tir_stream.cu
 void tir_stream_hub_destroy(TirStreamHub *h);

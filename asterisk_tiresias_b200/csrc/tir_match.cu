@@ -1065,6 +1065,11 @@ int tir_db_ensure_index(tir_ctx *ctx) {
   if (!ctx->db) return TIR_OK;
   return db_refresh(ctx, ctx->db);
 }
+int tir_db_ensure_index_public(tir_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  return tir_db_ensure_index(ctx);
+}
 
 // the match chain of one index: qprep -> pattern_block -> resolve -> per-query kernel (PDL-chained), hits to d_hits
 static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, const double *d_y, const float *d_coef,

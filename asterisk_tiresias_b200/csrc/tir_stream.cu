@@ -136,8 +136,9 @@ int TirStreamHub::extract_batch(std::vector<tir_stream *> &streams) {
   // ---- collect (per-stream lock only)
   for (tir_stream *s : streams) {
     std::lock_guard<std::mutex> lk(s->mu);
-    if (s->failed) continue;
+    if (s->failed || s->flushed) continue; // (a flushed stream has handed in its last hop: only its match is left)
     const size_t hist = s->hops_taken ? (size_t)hop : 0;
+    if (s->pending.size() < hist) continue;
     const size_t avail = s->pending.size() - hist;
     size_t nh = avail / (size_t)hop, rem = avail % (size_t)hop;
     bool last = false;

@@ -928,14 +928,25 @@ def main():
             match = {"error": str(ex)[:300]}
 
     # ---- BASELINE config[4]: concurrent channels through the batcher (C++ client of the C ABI) ----
+    # one GPU: tir_search_one on one context (+ the streaming variant: 20 ms chunks through tir_stream_*);
+    # N GPUs: ONE process drives all N devices through tir_group_* (an Asterisk module is one process) against the
+    # 10 M-fingerprint table -- rank 0 runs it while the other ranks, their work done, wait at the barrier
     concurrent = None
     tool = os.path.join(ROOT, "tools", "tir_concurrent_bench.bin")
-    if rank == 0 and world == 1 and not args.no_match and os.path.exists(tool):
+    ctx.close()
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and not args.no_match and os.path.exists(tool):
+        def run_tool(extra):
+            r = subprocess.run([tool, "--threads", str(args.channels), "--rounds", "20", "--wait-us", "1000", *extra], capture_output=True, text=True, timeout=900)
+            return json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
         try:
-            torch.cuda.empty_cache()
-            r = subprocess.run([tool, "--threads", str(args.channels), "--rounds", "20", "--wait-us", "1000", "--db-fps", str(args.channels_db_fps),
-                                "--device", str(local_rank)], capture_output=True, text=True, timeout=600)
-            concurrent = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+            if world == 1:
+                concurrent = run_tool(["--db-fps", str(args.channels_db_fps), "--device", str(local_rank)])
+                concurrent["streaming"] = run_tool(["--db-fps", str(args.channels_db_fps), "--device", str(local_rank), "--stream", "1"])
+            else:
+                concurrent = run_tool(["--db-fps", str(args.match_fps if args.match_fps > 0 else 10_000_000), "--devices", str(world)])
         except Exception as ex:  # noqa: BLE001
             concurrent = {"error": str(ex)[:300]}
 
@@ -964,7 +975,6 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
     return 0
 
 

@@ -260,10 +260,11 @@ int tir_p2p_search(tir_p2p *p, const int16_t *pcm, const uint64_t *clip_off, uin
 void tir_p2p_destroy(tir_p2p *p);
 
 /* The same inside ONE process (an Asterisk module cannot be launched one process per GPU): a group
- * owns one context per device, shards the table by uuid over them, and a search extracts on the
- * first device, hands the coefficients to the others over NVLink (cudaMemcpyPeerAsync), matches on
- * all devices concurrently and folds the per-shard winners -- only 24 bytes per query and shard cross
- * the links.  Results equal those of one context holding the whole table. */
+ * owns one context per device and shards the table by uuid over them.  A search is tir_p2p_search driven
+ * from this process: the batch's clips are cut into one slice per device, every device uploads and extracts
+ * its slice, coefficients and winners cross NVLink inside the kernels (peer stores + flags).  Devices that
+ * cannot reach each other take a copy-based path (extraction on the first device, cudaMemcpyPeerAsync).
+ * Results equal those of one context holding the whole table. */
 typedef struct tir_group tir_group;
 int tir_group_open(const tir_cfg *cfg, const int *devices, int n_devices, tir_group **out); /* cfg->device/stream ignored */
 void tir_group_close(tir_group *g);
@@ -277,6 +278,16 @@ int tir_group_db_remove(tir_group *g, const uint8_t uuid[16]);
 int tir_group_db_stats(tir_group *g, uint64_t *n_audio, uint64_t *n_rows);
 int tir_group_search(tir_group *g, const int16_t *pcm, const uint64_t *clip_off, uint32_t n_clips, int coefs,
                      double tolerance, int freq_ignore_low, int freq_ignore_high, tir_hit *hits);
+
+/* how many searches took the fused NVLink path / the copy path (no peer access between the devices) */
+int tir_group_stats(tir_group *g, uint64_t *n_fused, uint64_t *n_copy_path);
+/* the concurrent front-end on a group (BASELINE config[4]: 1 000 dialplan channels, 8 GPUs): like
+ * tir_batcher_start / tir_search_one, every sealed batch is one tir_group_search */
+int tir_group_batcher_start(tir_group *g, uint32_t max_batch, uint32_t max_wait_us);
+int tir_group_batcher_stop(tir_group *g);
+int tir_group_search_one(tir_group *g, const int16_t *pcm, uint64_t n_samples, int coefs, double tolerance,
+                         int freq_ignore_low, int freq_ignore_high, tir_hit *hit);
+int tir_group_batcher_stats(tir_group *g, uint64_t *n_requests, uint64_t *n_batches, uint64_t *max_batch_seen);
 
 /* which shard (0..n_shards-1) owns a uuid */
 uint32_t tir_shard_of(const uint8_t uuid[16], uint32_t n_shards);

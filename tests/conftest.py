@@ -4,6 +4,11 @@ import sys
 
 import pytest
 
+# The p2p tests run several ranks of the NVLink exchange as contexts of ONE process; on a single-GPU box they share
+# the device, and their kernels wait for one another.  More hardware queues than the default 8 keep the ranks'
+# streams from being serialised behind each other (must be set before CUDA initialises).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -50,6 +50,32 @@ def test_group_search_equals_single_context(layout):
         assert _same(grp.search(q2, q2off, 1, 0.05), ref.search(q2, q2off, 1, 0.05))
         with pytest.raises(capi.TirError):
             grp.search(qpcm, qoff, 3, 0.001)
+        st = grp.stats()
+        if layout == "all-devices":
+            assert st["fused"] >= 4 and st["copy_path"] == 0   # one device per shard: coefficients + winners cross NVLink inside the kernels
+        else:
+            assert st["copy_path"] >= 4 and st["fused"] == 0   # shards sharing a device never wait for one another: copy path
+        # config[4] on a group: concurrent channels through the group's batcher equal lone searches
+        import threading
+        want = ref.search(qpcm, qoff, 1, 0.05)
+        grp.batcher_start(max_batch=32, max_wait_us=2000)
+        got, errs = [None] * len(q_clips), []
+
+        def channel(i):
+            try:
+                got[i] = grp.search_one(q_clips[i], 1, 0.05)
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+        th = [threading.Thread(target=channel, args=(i,)) for i in range(len(q_clips))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for i, g_ in enumerate(got):
+            assert g_["match_count"] == want[i]["match_count"] and g_["frame_count"] == want[i]["frame_count"]
+            assert g_["match_count"] == 0 or bytes(g_["uuid"]) == bytes(want[i]["uuid"])
+        n_req, n_b, mx = grp.batcher_stats()
+        assert n_req == len(q_clips) and n_b < n_req
+        grp.batcher_stop()
     finally:
         grp.close()
         ref.close()
