@@ -60,7 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     host_src = os.path.join(HERE, "host", "fp_handler_gpu.cpp")
     if os.path.exists(host_src):
         r = subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", host_src, "-o", HOST_LIB, "-L" + HERE,
-                            "-ltiresias_gpu", "-lcrypto", "-ldl", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+                            "-ltiresias_gpu", "-lcrypto", "-ldl", "-Wl,-rpath,$ORIGIN",
+                            "-Wl,-Bsymbolic"],  # (the drop-in module of the tests exports the same fp_* names)
+                           capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("building libtiresias_host.so failed")

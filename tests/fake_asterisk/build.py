@@ -48,7 +48,8 @@ def build(force: bool = False) -> str | None:
            "-I" + os.path.join(HERE, "include"), "-I" + REF, "-I" + os.path.join(ROOT, "include"),
            *[os.path.join(REF, f) for f in UNCHANGED], *OURS, "-o", OUT,
            "-L" + libdir, "-ltiresias_gpu", "-l:libjansson.so.4", "-l:libsqlite3.so.0", "-l:libuuid.so.1", "-lcrypto", "-lm",
-           "-Wl,-rpath,$ORIGIN/../../asterisk_tiresias_b200"]
+           "-Wl,-rpath,$ORIGIN/../../asterisk_tiresias_b200",
+           "-Wl,-Bsymbolic"]     # libtiresias_host.so exports the same fp_* names: no interposition between the two in one process
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

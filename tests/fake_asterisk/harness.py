@@ -22,7 +22,7 @@ class FakeAsterisk:
         os.environ["TIRESIAS_BACKUP_DATABASE"] = backup_db or os.path.join(root, "var", "lib", "asterisk", "third-party", "tiresias", "audio_recongition.db")
         os.environ["TIRESIAS_GPU_DEVICE"] = str(device)
         self.root = root
-        L = self.L = C.CDLL(so, mode=C.RTLD_GLOBAL)
+        L = self.L = C.CDLL(so)
         L.fake_module_load.restype = C.c_int
         L.fake_module_unload.restype = C.c_int
         L.fake_module_reload.restype = C.c_int
