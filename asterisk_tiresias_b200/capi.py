@@ -102,6 +102,7 @@ def lib():
             L.tir_group_batcher_stats.argtypes = [vp, vp, vp, vp]
             L.tir_p2p_reserve.argtypes = [vp, C.c_uint64]
             L.tir_db_index_stats.argtypes = [vp, vp, vp, vp, vp]
+            L.tir_match_graph_stats.argtypes = [vp, vp, vp]
             L.tir_p2p_handle.argtypes = [vp, vp]
             L.tir_p2p_connect.argtypes = [vp, vp]
             L.tir_p2p_connect_local.argtypes = [vp, vp]
@@ -275,6 +276,12 @@ class Context:
         v = [C.c_uint64() for _ in range(4)]
         self._chk(lib().tir_db_index_stats(self._h, *[C.byref(x) for x in v]))
         return dict(zip(("full_builds", "tail_builds", "tail_audios", "tombstones"), (int(x.value) for x in v)))
+
+    def match_graph_stats(self):
+        """-> dict(graph_launches, graphs_built): batches replayed as one CUDA graph launch, graphs captured"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(lib().tir_match_graph_stats(self._h, C.byref(a), C.byref(b)))
+        return {"graph_launches": int(a.value), "graphs_built": int(b.value)}
 
     # ---- match ------------------------------------------------------------------------------
     def match(self, y, frame_off=None, coefs=1, tolerance=0.001, freq_ignore_low=-1, freq_ignore_high=-1):

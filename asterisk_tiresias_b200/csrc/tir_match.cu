@@ -106,6 +106,16 @@ struct TirDb {
   bool tail_dirty = false; // the tail's audio range grew
   TirIndex main, tail;
   uint64_t n_full_builds = 0, n_tail_builds = 0;
+  // the match chain of a steady caller (same buffers, same batch shape, same parameters) is replayed as ONE
+  // CUDA graph launch instead of a copy, a memset and four kernel launches: one cached graph per staging slot
+  struct ChainGraph {
+    unsigned char key[256];   // what `exec` was captured with
+    unsigned char seen[256];  // the key of the slot's previous call: a graph is only captured for a key seen twice in a
+    bool have_seen = false;   // row (a caller whose batch shape changes every time keeps the plain launches)
+    cudaGraphExec_t exec = nullptr;
+  } cg[tir_ctx::kStageSlots];
+  bool graph_off = false; // capture failed once: plain launches from then on
+  uint64_t n_graph_launches = 0, n_graph_builds = 0;
 };
 
 static void index_free(TirIndex &x) {
@@ -119,6 +129,8 @@ void tir_db_destroy(TirDb *db) {
   for (DevBuf *b : {&db->uuids, &db->row_off, &db->v1, &db->v2, &db->alive})
     if (b->p) cudaFree(b->p);
   index_free(db->main), index_free(db->tail);
+  for (auto &g : db->cg)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   delete db;
 }
 
@@ -1088,8 +1100,18 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   int slot;
   if ((rc = tir_stage_acquire(ctx, ((size_t)n_queries + 1) * 8, &hp, &slot))) return rc;
   std::memcpy(hp, frame_off, ((size_t)n_queries + 1) * 8);
+  const bool indexed = idx.n_blocks && idx.n_indexed;
+  if (indexed && !ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
+    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
+    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
+    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(true)));
+    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(true)));
+    ctx->match_smem_attr_set = true;
+  }
+  bool in_graph = false; // (the profiling events cannot be recorded inside a capture)
+  // everything the chain enqueues, as one function: run directly, or captured once into a graph and replayed
+  auto enqueue = [&]() -> int {
   TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, hp, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
-  if ((rc = tir_stage_release(ctx, slot))) return rc;
   TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_plist - o_best, st)); // best, batch, max_rank1, pattern hash table
   const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
@@ -1102,15 +1124,14 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<true>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, (const double *)nullptr, d_coef, d_foff, mp, d_win, d_nw, d_batch));
   else
     TIR_CUDA(ctx, tir_launch_pdl(tir_qprep_kernel<false>, dim3(n_queries), dim3(TIR_QPREP_THREADS), st, d_y, (const float *)nullptr, d_foff, mp, d_win, d_nw, d_batch));
-  ctx->launches++;
-  if (idx.n_blocks && idx.n_indexed) {
+  if (indexed) {
     const int32_t *k1 = (const int32_t *)idx.key1.p, *k2 = (const int32_t *)idx.key2.p;
     const uint16_t *uid = (const uint16_t *)idx.uid.p;
     const uint64_t *bst = (const uint64_t *)idx.block_start.p;
     const uint32_t *order = (const uint32_t *)idx.order.p;
     const uint8_t *uuids = (const uint8_t *)db->uuids.p + (size_t)idx.a0 * 16; // `order` holds audio numbers relative to the range
     const uint8_t *dead = idx.n_dead ? (const uint8_t *)idx.dead.p : nullptr;
-    if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
+    if (ctx->profiling && !in_graph) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
     const dim3 pgrid(idx.n_blocks), pthr(TIR_MATCH_THREADS);
     if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
@@ -1121,26 +1142,77 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)idx.n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);
-    if (!ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(true)));
-      TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(true)));
-      ctx->match_smem_attr_set = true;
-    }
     auto gen = coefs >= 2 ? (wide ? tir_match_kernel<2, true> : tir_match_kernel<2, false>)
                           : (wide ? tir_match_kernel<1, true> : tir_match_kernel<1, false>);
     TIR_CUDA(ctx, tir_launch_pdl_smem(gen, dim3(ggrid), dim3(TIR_MATCH_THREADS), (size_t)TIR_GEN_SMEM_OF(wide), st, k1, uid, k2, bst,
                                       (const TirWindow *)d_win, (const uint32_t *)d_nw, d_foff, d_best, idx.n_blocks, n_queries, d_batch,
                                       order, uuids, d_hits, x, dead));
-    ctx->launches += 3;
-    if (ctx->profiling) {
+    if (ctx->profiling && !in_graph) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
       ctx->ev_valid[1] = true;
     }
   } else {
     TIR_CUDA(ctx, tir_launch_pdl(tir_no_hits_kernel, dim3((n_queries + 127) / 128), dim3(128), st, d_foff, n_queries, d_hits));
-    ctx->launches++;
+  }
+  return TIR_OK;
+  }; // enqueue
+
+  // ---- a steady caller: replay the cached graph of this staging slot (no exchange: its epoch changes every batch)
+  if (indexed && !x.peer && !db->graph_off) {
+    struct Key {
+      const void *scratch, *hp, *d_y, *d_coef, *d_hits, *k1, *uid, *k2, *bst, *order, *uuids, *dead;
+      uint64_t F;
+      uint32_t n_queries, n_blocks, num_sms, wide;
+      TirMatchParams mp; // (key comparison only: same bytes as the argument)
+    } key;
+    static_assert(sizeof(Key) <= sizeof(TirDb::ChainGraph::key), "graph key storage");
+    std::memset(&key, 0, sizeof key);
+    key.scratch = scratch.p, key.hp = hp, key.d_y = d_y, key.d_coef = d_coef, key.d_hits = d_hits;
+    key.k1 = idx.key1.p, key.uid = idx.uid.p, key.k2 = idx.key2.p, key.bst = idx.block_start.p, key.order = idx.order.p;
+    key.uuids = (const uint8_t *)db->uuids.p + (size_t)idx.a0 * 16, key.dead = idx.n_dead ? idx.dead.p : nullptr;
+    key.F = F, key.n_queries = n_queries, key.n_blocks = idx.n_blocks, key.num_sms = (uint32_t)ctx->num_sms, key.wide = wide;
+    std::memcpy(&key.mp, &mp, sizeof mp);
+    TirDb::ChainGraph &g = db->cg[slot];
+    const bool cached = g.exec && std::memcmp(g.key, &key, sizeof key) == 0;
+    const bool twice = g.have_seen && std::memcmp(g.seen, &key, sizeof key) == 0;
+    std::memcpy(g.seen, &key, sizeof key), g.have_seen = true;
+    if (!cached && g.exec) cudaGraphExecDestroy(g.exec), g.exec = nullptr;
+    if (!cached && twice) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        in_graph = true;
+        const int erc = enqueue();
+        in_graph = false;
+        const cudaError_t ee = cudaStreamEndCapture(st, &graph);
+        if (erc == TIR_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+          std::memcpy(g.key, &key, sizeof key);
+          db->n_graph_builds++;
+        } else {
+          g.exec = nullptr, db->graph_off = true;
+          (void)cudaGetLastError();
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        db->graph_off = true;
+        (void)cudaGetLastError();
+      }
+    }
+    if (g.exec) {
+      if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
+      TIR_CUDA(ctx, cudaGraphLaunch(g.exec, st));
+      if (ctx->profiling) {
+        TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
+        ctx->ev_valid[1] = true;
+      }
+      if ((rc = tir_stage_release(ctx, slot))) return rc;
+      ctx->launches += 4, db->n_graph_launches++;
+      return TIR_OK;
+    }
+  }
+  if ((rc = enqueue())) return rc;
+  if ((rc = tir_stage_release(ctx, slot))) return rc;
+  ctx->launches += indexed ? 4 : 2;
+  if (!indexed) {
     if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x))) return rc; // an empty shard still answers
     if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x, n_queries))) return rc;
   }
@@ -1168,6 +1240,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
     wide |= frame_off[q + 1] - frame_off[q] > 65535;
   }
   TirMatchParams mp;
+  std::memset(&mp, 0, sizeof mp); // (its bytes are part of the key of the cached chain graph: no stray padding)
   mp.coefs = coefs;
   mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
   mp.use_lo = ign_lo > 0, mp.use_hi = ign_hi > 0;
@@ -1337,6 +1410,14 @@ int tir_db_index_stats(tir_ctx *ctx, uint64_t *n_full_builds, uint64_t *n_tail_b
   if (n_tail_builds) *n_tail_builds = b;
   if (tail_audios) *tail_audios = c;
   if (tombstones) *tombstones = d;
+  return TIR_OK;
+}
+
+int tir_match_graph_stats(tir_ctx *ctx, uint64_t *n_graph_launches, uint64_t *n_graphs_built) {
+  if (!ctx) return TIR_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_graph_launches) *n_graph_launches = ctx->db ? ctx->db->n_graph_launches : 0;
+  if (n_graphs_built) *n_graphs_built = ctx->db ? ctx->db->n_graph_builds : 0;
   return TIR_OK;
 }
 

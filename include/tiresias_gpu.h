@@ -130,6 +130,11 @@ int tir_db_stats(tir_ctx *ctx, uint64_t *n_audio, uint64_t *n_rows);
  * table runs only after a load, or when the tail holds more than max(2^20, rows/16) rows or a quarter of the main
  * index is dead.  Counters: full sorts so far, tail sorts, audios in the tail, tombstones. */
 int tir_db_index_stats(tir_ctx *ctx, uint64_t *n_full_builds, uint64_t *n_tail_builds, uint64_t *tail_audios, uint64_t *tombstones);
+/* A caller that keeps searching with the same buffers, batch shape and parameters (the batcher, the stream pump, a
+ * benchmark loop) has its match chain -- the copy of the query offsets, the clearing of the scratch, the four kernels --
+ * captured once into a CUDA graph and replayed with ONE launch per batch; any change of an argument, of the index or of
+ * the table re-captures.  Counters: batches served by a graph launch, graphs captured so far. */
+int tir_match_graph_stats(tir_ctx *ctx, uint64_t *n_graph_launches, uint64_t *n_graphs_built);
 
 /* ---- SQLite <-> device table -----------------------------------------------------------------
  * SQLite stays the system of record (schema src/fp_handler.c:686-753).  `sqlite3_db` is the

@@ -421,3 +421,33 @@ def test_one_million_fingerprints_both_paths_and_brute_force(gpu_ctx):
     torch.cuda.synchronize()
     got = out.cpu().numpy().view(capi.HIT_DTYPE)
     assert np.array_equal(got["match_count"], want["match_count"]) and np.array_equal(got["uuid"], want["uuid"])
+
+
+def test_steady_caller_is_served_by_graph_replays(gpu_ctx, oracle):
+    """The match chain of a caller that repeats the same batch shape / buffers / parameters is captured into a CUDA
+    graph (after the key was seen twice on a staging slot) and replayed with one launch per batch; every replay, and
+    every call after a change of parameters or of the table, still equals SQLite."""
+    rng = np.random.default_rng(21)
+    db = synth_db.make_db(80, 20, 40, seed=17)
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    qa, qb = db[3][1], synth_db.random_y(rng, db[3][1].shape[0])
+    s0 = gpu_ctx.match_graph_stats()
+    for i in range(16):
+        y = qa if i % 2 == 0 else qb                                   # same shape, different content: same graph
+        assert gpu_result(gpu_ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01)), i
+    s1 = gpu_ctx.match_graph_stats()
+    assert s1["graph_launches"] - s0["graph_launches"] >= 8 and 1 <= s1["graphs_built"] - s0["graphs_built"] <= 4
+    for tol in (0.05, 0.01, 0.05):                                     # a parameter change: plain launches, then a new graph
+        for i in range(9):
+            assert gpu_result(gpu_ctx.match(qa, tolerance=tol)[0]) == sql_result(sq.search(qa, tolerance=tol))
+    u_new, y_new = synth_db.make_db(1, 25, 25, seed=99)[0]
+    v = synth_db.quantize_y(y_new)
+    gpu_ctx.db_add(capi.uuid_to_bytes(u_new), v[:, 0], v[:, 1]); sq.add_audio(u_new, y_new)
+    gpu_ctx.db_remove(capi.uuid_to_bytes(db[3][0])); sq.delete_audio(db[3][0])
+    for i in range(12):                                                # tail index + tombstone: two chains per call
+        for y in (qa, y_new):
+            assert gpu_result(gpu_ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01))
+    assert gpu_ctx.match_graph_stats()["graph_launches"] > s1["graph_launches"]
