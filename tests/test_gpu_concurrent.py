@@ -1,7 +1,6 @@
 """BASELINE config[4]: many dialplan channels searching at once.  Concurrent tir_search_one() callers
 (one host thread per channel, as the PBX does, src/application_handler.c:180) through the batcher
-must get exactly what a lone tir_search of the same recording returns, and the streaming entry
-points must equal the one-shot call."""
+and the streaming entry points must return what the ORACLE chain returns for the same recording."""
 import threading
 
 import numpy as np
@@ -12,30 +11,28 @@ from asterisk_tiresias_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-def _db_and_clips(ctx, n_db=200, n_q=96):
-    pcm, off = synth.make_corpus(n_db, 3.0, first_index=12000)
-    coef, vq = ctx.extract(pcm, off)
-    fo = np.concatenate([[0], np.cumsum((np.diff(off.astype(np.int64)) + 255) // 256)]).astype(np.uint64)
-    uu = np.stack([capi.uuid_to_bytes(synth.uuid_for(910000 + i)) for i in range(n_db)])
-    ctx.db_load(uu, fo, vq[:, 0], vq[:, 1])
-    clips = []
-    for i in range(n_q):
-        if i % 3 == 0:
-            clips.append(pcm[int(off[i]):int(off[i + 1])].copy())          # a stored recording
-        elif i % 3 == 1:
-            clips.append(synth.make_clip(50000 + i, 1.0 + (i % 5) * 0.7))    # unrelated, ragged lengths
-        else:
-            c = pcm[int(off[i]):int(off[i + 1])].astype(np.int32) + np.random.default_rng(i).integers(-3, 4, int(off[i + 1] - off[i]))
-            clips.append(np.clip(c, -32768, 32767).astype(np.int16))         # noisy copy
-    return clips
-
-
-def test_concurrent_callers_equal_single_searches():
+def test_concurrent_callers_equal_the_oracle_chain(oracle):
+    """96 simultaneous channels through the batcher, three waves: every answer equals the ORACLE chain (oracle
+    extraction of the recording + the reference's SQL on SQLite) -- not another GPU call."""
     ctx = capi.Context(device=0)
     try:
-        clips = _db_and_clips(ctx)
+        pcm, off, plan, sq = _oracle_db(oracle, ctx, n_db=120)
+        clips = []
+        for i in range(96):
+            if i % 3 == 0:
+                clips.append(pcm[int(off[i]):int(off[i + 1])].copy())          # a stored recording
+            elif i % 3 == 1:
+                clips.append(synth.make_clip(50000 + i, 1.0 + (i % 5) * 0.7))    # unrelated, ragged lengths
+            else:
+                c = pcm[int(off[i]):int(off[i + 1])].astype(np.int32) + np.random.default_rng(i).integers(-3, 4, int(off[i + 1] - off[i]))
+                clips.append(np.clip(c, -32768, 32767).astype(np.int16))         # noisy copy
         params = [(1, 0.001, -1, -1), (1, 0.05, -1, -1), (2, 0.5, -1, -1), (1, 0.05, 40, 70)]
-        want = [ctx.search(c, None, *params[i % len(params)])[0] for i, c in enumerate(clips)]
+        want = []
+        for i, c in enumerate(clips):
+            _, y, _ = plan.extract(c)
+            co, t, lo, hi = params[i % len(params)]
+            want.append(sq.search(y, co, t, lo, hi, has_y=np.isfinite(y)))
+        assert sum(w is not None for w in want) >= 30
         ctx.batcher_start(max_batch=64, max_wait_us=2000)
         got = [None] * len(clips)
         errs = []
@@ -51,16 +48,14 @@ def test_concurrent_callers_equal_single_searches():
             [t.start() for t in th]
             [t.join() for t in th]
             assert not errs, errs
-            for w, g in zip(want, got):
-                assert g["match_count"] == w["match_count"] and g["frame_count"] == w["frame_count"]
-                assert bytes(g["uuid"]) == bytes(w["uuid"])
+            for i, (w, g) in enumerate(zip(want, got)):
+                assert _same_as_oracle(g, w), i
         n_req, n_batches, max_seen = ctx.batcher_stats()
         assert n_req == 3 * len(clips) and n_batches < n_req and max_seen > 1     # requests really were batched
         with pytest.raises(capi.TirError):                   # argument rule of src/fp_handler.c:247 survives the queue
             ctx.search_one(clips[0], coefs=3)
         ctx.batcher_stop()
-        h = ctx.search_one(clips[0])                         # no batcher: a batch of one
-        assert h["match_count"] == want[0]["match_count"]
+        assert _same_as_oracle(ctx.search_one(clips[0]), sq.search(plan.extract(clips[0])[1], 1, 0.001))   # no batcher: a batch of one
     finally:
         ctx.close()
 
@@ -169,7 +164,10 @@ def test_streaming_finish_latency_does_not_depend_on_the_recording_length():
     import time
     ctx = capi.Context(device=0)
     try:
-        _db_and_clips(ctx, n_db=100, n_q=3)
+        pcm, off = synth.make_corpus(100, 3.0, first_index=12000)   # (timing only: the table comes from the GPU's own extraction)
+        _, vq = ctx.extract(pcm, off)
+        fo = np.concatenate([[0], np.cumsum((np.diff(off.astype(np.int64)) + 255) // 256)]).astype(np.uint64)
+        ctx.db_load(np.stack([capi.uuid_to_bytes(synth.uuid_for(910000 + i)) for i in range(100)]), fo, vq[:, 0], vq[:, 1])
 
         def finish_ms(seconds, reps=5):
             r = synth.make_clip(777, seconds)
