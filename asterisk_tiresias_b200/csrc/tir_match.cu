@@ -172,26 +172,41 @@ __global__ void tir_invert_kernel(const uint32_t *__restrict__ order, uint32_t n
   if (r < n) rank_of[order[r]] = r;
 }
 
-// one warp per audio: emit (block | biased v1) sort keys and (v2 | local uid) payloads for its rows.
+// rows of the audio with rank r (ranks = audios sorted by uuid bytes; 16 384 consecutive ranks = one index block)
+__global__ void tir_rank_rows_kernel(const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ order, uint32_t n,
+                                     uint64_t *__restrict__ cnt) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) cnt[r] = row_off[order[r] + 1] - row_off[order[r]];
+}
+// rank_row_off at the block boundaries (and at n) -> the host cuts the build into passes of whole blocks
+__global__ void tir_block_rows_kernel(const uint64_t *__restrict__ rank_row_off, uint32_t n, uint32_t n_blocks,
+                                      uint64_t *__restrict__ out) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= n_blocks) out[b] = rank_row_off[min((uint64_t)b * TIR_BLOCK_UUIDS, (uint64_t)n)];
+}
+
+// One pass of the build = the ranks [r_lo, r_hi) (whole index blocks).  One warp per rank: emit (block | biased v1)
+// sort keys and (v2 | local uid) payloads for the audio's rows, at the rank's position inside the pass.
 // NULL max1 rows and rows of deleted audios can never be selected by "max1 >= lo and max1 <= hi":
-// they get the all-ones key, sort to the end and are cut off.
+// they get the all-ones key, sort to the end of the pass and are cut off.
 __global__ void tir_row_keys_kernel(const uint64_t *__restrict__ row_off, const int32_t *__restrict__ v1,
                                     const int32_t *__restrict__ v2, const uint8_t *__restrict__ alive,
-                                    const uint32_t *__restrict__ rank_of, uint32_t n_audio, uint64_t r_begin,
-                                    uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
+                                    const uint32_t *__restrict__ order, const uint64_t *__restrict__ rank_row_off,
+                                    uint32_t r_lo, uint32_t r_hi, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
                                     unsigned long long *__restrict__ n_valid) {
-  const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (a >= n_audio) return;
+  const uint32_t rank = r_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (rank >= r_hi) return;
+  const uint32_t a = order[rank];
   const uint64_t r0 = row_off[a], r1 = row_off[a + 1];
-  const uint32_t rank = rank_of[a];
+  const uint64_t dst0 = rank_row_off[rank] - rank_row_off[r_lo];
   const uint64_t blk = rank / TIR_BLOCK_UUIDS, local = rank % TIR_BLOCK_UUIDS;
   const bool live = alive[a] != 0;
   unsigned long long cnt = 0;
   for (uint64_t r = r0 + lane; r < r1; r += 32) {
     const int32_t a1 = v1[r], a2 = v2[r];
     const bool ok = live && a1 != TIR_NULL_V;
-    keys[r - r_begin] = ok ? ((blk << 32) | (uint64_t)((uint32_t)a1 ^ 0x80000000u)) : ~0ull; // (key / value arrays start at the range's first row)
-    vals[r - r_begin] = ((uint64_t)(uint32_t)a2 << 32) | local;
+    keys[dst0 + (r - r0)] = ok ? ((blk << 32) | (uint64_t)((uint32_t)a1 ^ 0x80000000u)) : ~0ull;
+    vals[dst0 + (r - r0)] = ((uint64_t)(uint32_t)a2 << 32) | local;
     cnt += ok;
   }
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -208,17 +223,17 @@ __global__ void tir_split_rows_kernel(const uint64_t *__restrict__ keys, const u
   key2[i] = (int32_t)(uint32_t)(v >> 32);
 }
 
-// block_start[b] = first sorted row whose block id is >= b
-__global__ void tir_block_start_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t n_blocks,
+// block_start[b] = base + first sorted row of the pass whose block id is >= b, for the blocks [b_lo, b_hi) of the pass
+__global__ void tir_block_start_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t b_lo, uint32_t b_hi, uint64_t base,
                                        uint64_t *__restrict__ block_start) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_blocks) return;
+  const uint32_t b = b_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= b_hi) return;
   uint64_t lo = 0, hi = n;
   while (lo < hi) {
     const uint64_t mid = (lo + hi) >> 1;
     if ((keys[mid] >> 32) < (uint64_t)b) lo = mid + 1; else hi = mid;
   }
-  block_start[b] = lo;
+  block_start[b] = base + lo;
 }
 
 // device temporaries of a build, freed on every exit path
@@ -274,9 +289,7 @@ static int db_build_index(tir_ctx *ctx, TirDb *db, TirIndex &x, uint32_t a0, uin
   tir_uuid_keys_kernel<<<gb, 256, 0, st>>>(uu, n, hi, lo, idx_a);
   size_t tmp_bytes = 0, tmp2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lo, k_out, idx_a, idx_b, (int)n, 0, 64, st);
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint64_t *)nullptr,
-                                  (uint64_t *)nullptr, (long long)rows, 0, 64, st);
-  tmp_bytes = std::max(tmp_bytes, tmp2);
+  (void)tmp2;
   void *tmp = nullptr;
   TIR_CUDA(ctx, tmpbuf.get(&tmp, tmp_bytes));
   TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lo, k_out, idx_a, idx_b, (int)n, 0, 64, st));
@@ -284,31 +297,84 @@ static int db_build_index(tir_ctx *ctx, TirDb *db, TirIndex &x, uint32_t a0, uin
   TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, idx_b, (uint32_t *)x.order.p, (int)n, 0, 64, st));
   tir_invert_kernel<<<gb, 256, 0, st>>>((const uint32_t *)x.order.p, n, rank_of);
   ctx->launches += 5;
-  // ---- rows: (block, v1) keys -> radix sort -> SoA.  Row arrays are indexed from the range's first row.
+  // ---- rows: (block, v1) keys -> radix sort -> SoA, in PASSES of whole index blocks of at most ~pass_rows rows, so
+  // that the build needs 32 B of scratch per row of a pass instead of per row of the table (a 4.7 G-row shard of the
+  // 10 M x 938-frame table is built with 2 GB of scratch next to its 18 B per row of master copy + index)
+  uint64_t *cnt, *rank_row_off, *d_blk_rows;
+  TIR_CUDA(ctx, tmpbuf.get(&cnt, (size_t)n * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rank_row_off, ((size_t)n + 1) * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&d_blk_rows, ((size_t)x.n_blocks + 1) * 8));
+  tir_rank_rows_kernel<<<gb, 256, 0, st>>>(roff, (const uint32_t *)x.order.p, n, cnt);
+  {
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, rank_row_off, (int)n, st);
+    void *scan_tmp = tmp;
+    if (scan_bytes > tmp_bytes) TIR_CUDA(ctx, tmpbuf.get(&scan_tmp, scan_bytes));
+    TIR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cnt, rank_row_off, (int)n, st));
+    TIR_CUDA(ctx, cudaMemcpyAsync(rank_row_off + n, &rows, 8, cudaMemcpyHostToDevice, st)); // every row of the range belongs to one of its audios
+  }
+  tir_block_rows_kernel<<<(x.n_blocks + 1 + 255) / 256, 256, 0, st>>>(rank_row_off, n, x.n_blocks, d_blk_rows);
+  std::vector<uint64_t> blk_rows((size_t)x.n_blocks + 1);
+  TIR_CUDA(ctx, cudaMemcpyAsync(blk_rows.data(), d_blk_rows, blk_rows.size() * 8, cudaMemcpyDeviceToHost, st));
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->launches += 3;
+  uint64_t pass_rows = 1ull << 26;
+  if (const char *e = getenv("TIR_BUILD_PASS_ROWS")) pass_rows = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+  uint64_t max_pass = 0; // the largest pass: whole blocks, at least one
+  for (uint32_t b = 0; b < x.n_blocks;) {
+    uint32_t e = b + 1;
+    while (e < x.n_blocks && blk_rows[e + 1] - blk_rows[b] <= pass_rows) e++;
+    max_pass = std::max(max_pass, blk_rows[e] - blk_rows[b]);
+    b = e;
+  }
+  {
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (uint64_t *)nullptr, (long long)max_pass, 0, 64, st);
+    if (need > tmp_bytes) {
+      TIR_CUDA(ctx, tmpbuf.get(&tmp, need));
+      tmp_bytes = need;
+    }
+  }
   uint64_t *rk, *rv, *rk2, *rv2;
   unsigned long long *d_nvalid;
-  TIR_CUDA(ctx, tmpbuf.get(&rk, rows * 8));
-  TIR_CUDA(ctx, tmpbuf.get(&rv, rows * 8));
-  TIR_CUDA(ctx, tmpbuf.get(&rk2, rows * 8));
-  TIR_CUDA(ctx, tmpbuf.get(&rv2, rows * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rk, max_pass * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rv, max_pass * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rk2, max_pass * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&rv2, max_pass * 8));
   TIR_CUDA(ctx, tmpbuf.get(&d_nvalid, 8));
-  TIR_CUDA(ctx, cudaMemsetAsync(d_nvalid, 0, 8, st));
-  tir_row_keys_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, st>>>(
-      roff, (const int32_t *)db->v1.p, (const int32_t *)db->v2.p, alive, rank_of, n, r_begin, rk, rv, d_nvalid);
-  // block ids need ceil(log2(n_blocks)) bits above the 32 key bits; the all-ones tail sorts last anyway
-  TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rk, rk2, rv, rv2, (long long)rows, 0, 64, st));
-  unsigned long long nvalid = 0;
-  TIR_CUDA(ctx, cudaMemcpyAsync(&nvalid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
-  TIR_CUDA(ctx, cudaStreamSynchronize(st));
-  x.n_indexed = nvalid;
-  if ((rc = tir_reserve(ctx, x.key1, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
-  if ((rc = tir_reserve(ctx, x.uid, std::max<size_t>(nvalid, 1) * 2 + 64))) return rc;
-  if ((rc = tir_reserve(ctx, x.key2, std::max<size_t>(nvalid, 1) * 4 + 64))) return rc;
-  if (nvalid)
-    tir_split_rows_kernel<<<(uint32_t)((nvalid + 255) / 256), 256, 0, st>>>(rk2, rv2, nvalid, (int32_t *)x.key1.p,
-                                                                            (uint16_t *)x.uid.p, (int32_t *)x.key2.p);
-  tir_block_start_kernel<<<(x.n_blocks + 1 + 255) / 256, 256, 0, st>>>(rk2, nvalid, x.n_blocks, (uint64_t *)x.block_start.p);
-  ctx->launches += 4;
+  // the index arrays are sized for every row of the range (NULL / dead rows leave a little slack)
+  if ((rc = tir_reserve(ctx, x.key1, rows * 4 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, x.uid, rows * 2 + 64))) return rc;
+  if ((rc = tir_reserve(ctx, x.key2, rows * 4 + 64))) return rc;
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < x.n_blocks;) {
+    uint32_t e = b + 1;
+    while (e < x.n_blocks && blk_rows[e + 1] - blk_rows[b] <= pass_rows) e++;
+    const uint64_t prow = blk_rows[e] - blk_rows[b];
+    const uint32_t r_lo = b * TIR_BLOCK_UUIDS, r_hi = (uint32_t)std::min<uint64_t>((uint64_t)e * TIR_BLOCK_UUIDS, n);
+    unsigned long long nvalid = 0;
+    if (prow) {
+      TIR_CUDA(ctx, cudaMemsetAsync(d_nvalid, 0, 8, st));
+      tir_row_keys_kernel<<<(uint32_t)(((uint64_t)(r_hi - r_lo) * 32 + 255) / 256), 256, 0, st>>>(
+          roff, (const int32_t *)db->v1.p, (const int32_t *)db->v2.p, alive, (const uint32_t *)x.order.p, rank_row_off, r_lo, r_hi,
+          rk, rv, d_nvalid);
+      // block ids need ceil(log2(n_blocks)) bits above the 32 key bits; the all-ones tail sorts last anyway
+      TIR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rk, rk2, rv, rv2, (long long)prow, 0, 64, st));
+      TIR_CUDA(ctx, cudaMemcpyAsync(&nvalid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
+      TIR_CUDA(ctx, cudaStreamSynchronize(st));
+      if (nvalid)
+        tir_split_rows_kernel<<<(uint32_t)((nvalid + 255) / 256), 256, 0, st>>>(rk2, rv2, nvalid, (int32_t *)x.key1.p + total,
+                                                                                (uint16_t *)x.uid.p + total, (int32_t *)x.key2.p + total);
+      ctx->launches += 3;
+    }
+    tir_block_start_kernel<<<(e - b + 255) / 256, 256, 0, st>>>(rk2, nvalid, b, e, total, (uint64_t *)x.block_start.p);
+    ctx->launches++;
+    total += nvalid;
+    b = e;
+  }
+  TIR_CUDA(ctx, cudaMemcpyAsync((uint64_t *)x.block_start.p + x.n_blocks, &total, 8, cudaMemcpyHostToDevice, st));
+  x.n_indexed = total;
   TIR_CUDA(ctx, cudaStreamSynchronize(st));
   TIR_CUDA(ctx, cudaGetLastError());
   x.built = true;

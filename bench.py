@@ -486,9 +486,9 @@ def match_bench(ctx, args, rank, world, device, dist):
     del bf, uu, v1, v2
     torch.cuda.empty_cache()
     # BASELINE config[3]/[4]'s table: 10 M fingerprints x 938 frames (30 s of audio each; 9.38 G rows, 94 GB of index)
-    # -- only fits sharded: run where a rank's share and its build scratch fit (N >= 4)
+    # -- only fits sharded (the index is built in passes: 18 B per row of master copy + index, 2 GB of scratch): N >= 2
     res["db_938_frames"] = None
-    if world >= 4 and not args.no_db938:
+    if world >= 2 and not args.no_db938:
         try:
             F2 = 938
             uu, v1, v2, n_local, rows2, build2 = make_db(F2, 1991)
@@ -653,7 +653,7 @@ def main():
     ap.add_argument("--channels", type=int, default=1000, help="concurrent channel threads of the config[4] leg")
     ap.add_argument("--channels-db-fps", type=int, default=1_000_000)
     ap.add_argument("--no-match", action="store_true")
-    ap.add_argument("--no-db938", action="store_true", help="skip the 10 M x 938-frame table leg (runs at N >= 4 only)")
+    ap.add_argument("--no-db938", action="store_true", help="skip the 10 M x 938-frame table leg (runs at N >= 2 only)")
     ap.add_argument("--no-wideband", action="store_true", help="skip the config[3] extraction leg (1024/512 at 16 kHz)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

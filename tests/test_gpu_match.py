@@ -451,3 +451,44 @@ def test_steady_caller_is_served_by_graph_replays(gpu_ctx, oracle):
         for y in (qa, y_new):
             assert gpu_result(gpu_ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01))
     assert gpu_ctx.match_graph_stats()["graph_launches"] > s1["graph_launches"]
+
+
+def test_index_built_in_passes_equals_one_pass(monkeypatch):
+    """The index build sorts the rows in passes of whole index blocks (32 B of scratch per row of a PASS, not of the
+    table).  Forced to one block per pass, a 3-block table with NULLs, removed audios and empty audios must give the
+    same winners as the single-pass build, query by query, on both match paths."""
+    rng = np.random.default_rng(77)
+    n = 40000
+    nrows = rng.integers(0, 6, n)                                      # some audios have no rows at all
+    off = np.concatenate([[0], np.cumsum(nrows)]).astype(np.uint64)
+    y1 = rng.uniform(14.0, 19.0, int(off[-1]))
+    near = rng.random(y1.size) < 0.5
+    y1[near] = np.round(y1[near]) + rng.uniform(-0.012, 0.012, int(near.sum()))   # half of the rows lie next to an integer
+    y = np.stack([y1, rng.uniform(-5, 20, y1.size)], axis=1)
+    y[rng.random(y1.size) < 0.03, 0] = np.nan                           # NULL max1
+    v = synth_db.quantize_y(y)
+    ub = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    queries = [np.stack([rng.uniform(14, 19, 30), rng.uniform(-5, 20, 30)], axis=1) for _ in range(6)]
+    foff = np.arange(7, dtype=np.uint64) * 30
+    qy = np.concatenate(queries)
+
+    def run():
+        c = capi.Context(device=0)
+        try:
+            c.db_load(ub, off, v[:, 0], v[:, 1])
+            for a in (5, 17000, 39999):
+                try:
+                    c.db_remove(ub[a])
+                except capi.TirError:
+                    pass
+            out = [c.match(qy, foff, 1, 0.01), c.match(qy, foff, 2, 0.5), c.match(qy, foff, 1, 0.3)]
+            return [(o["match_count"].copy(), o["uuid"].copy()) for o in out]
+        finally:
+            c.close()
+
+    one = run()
+    monkeypatch.setenv("TIR_BUILD_PASS_ROWS", "1")
+    many = run()
+    assert any((m > 0).any() for m, _ in one)
+    for (m1, u1), (m2, u2) in zip(one, many):
+        assert np.array_equal(m1, m2) and np.array_equal(u1, u2)
