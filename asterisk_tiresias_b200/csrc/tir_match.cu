@@ -115,7 +115,7 @@ struct TirDb {
     cudaGraphExec_t exec = nullptr;
   } cg[tir_ctx::kStageSlots];
   bool graph_off = false; // capture failed once: plain launches from then on
-  uint64_t n_graph_launches = 0, n_graph_builds = 0;
+  uint64_t n_graph_launches = 0, n_graph_builds = 0, n_compactions = 0;
 };
 
 static void index_free(TirIndex &x) {
@@ -381,6 +381,79 @@ static int db_build_index(tir_ctx *ctx, TirDb *db, TirIndex &x, uint32_t a0, uin
   return TIR_OK;
 }
 
+// compaction of the master copy before a full rebuild: one warp per surviving audio copies its uuid and its rows to
+// their new places (map[a] = new audio number, or 0xffffffff for a removed audio)
+__global__ void tir_compact_kernel(const uint32_t *__restrict__ map, const uint64_t *__restrict__ row_off, const uint64_t *__restrict__ new_row_off,
+                                   const uint8_t *__restrict__ uuids, const int32_t *__restrict__ v1, const int32_t *__restrict__ v2, uint32_t n,
+                                   uint8_t *__restrict__ uuids2, int32_t *__restrict__ v1b, int32_t *__restrict__ v2b) {
+  const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (a >= n) return;
+  const uint32_t m = map[a];
+  if (m == 0xffffffffu) return;
+  if (lane < 16) uuids2[(size_t)m * 16 + lane] = uuids[(size_t)a * 16 + lane];
+  const uint64_t r0 = row_off[a], r1 = row_off[a + 1], d0 = new_row_off[m];
+  for (uint64_t r = r0 + lane; r < r1; r += 32) v1b[d0 + (r - r0)] = v1[r], v2b[d0 + (r - r0)] = v2[r];
+}
+
+// Drop the removed audios from the master copy (device arrays and host mirrors).  Called when a full rebuild is due
+// anyway: the table does not grow without bound under add / remove churn (fp_sync_directories, the CLI).
+static int db_compact(tir_ctx *ctx, TirDb *db) {
+  const uint32_t n = (uint32_t)db->n_audio;
+  if (db->n_alive == db->n_audio || n == 0) return TIR_OK;
+  cudaStream_t st = ctx->stream;
+  std::vector<uint32_t> map(n, 0xffffffffu);
+  std::vector<uint64_t> nro;
+  nro.reserve((size_t)db->n_alive + 1);
+  nro.push_back(0);
+  std::vector<uint8_t> nuu;
+  nuu.reserve((size_t)db->n_alive * 16);
+  uint32_t m = 0;
+  for (uint32_t a = 0; a < n; a++) {
+    if (!db->h_alive[a]) continue;
+    map[a] = m++;
+    nro.push_back(nro.back() + (db->h_row_off[a + 1] - db->h_row_off[a]));
+    nuu.insert(nuu.end(), db->h_uuids.begin() + (size_t)a * 16, db->h_uuids.begin() + (size_t)a * 16 + 16);
+  }
+  const uint64_t rows2 = nro.back();
+  TirTmp tmpbuf; // (frees what is still registered on an error path)
+  uint32_t *d_map;
+  uint64_t *d_nro;
+  uint8_t *uu2, *alive2;
+  int32_t *v1b, *v2b;
+  TIR_CUDA(ctx, tmpbuf.get(&d_map, (size_t)n * 4));
+  TIR_CUDA(ctx, tmpbuf.get(&d_nro, ((size_t)m + 1) * 8));
+  TIR_CUDA(ctx, tmpbuf.get(&uu2, (size_t)m * 16 + 16));
+  TIR_CUDA(ctx, tmpbuf.get(&alive2, (size_t)m + 1));
+  TIR_CUDA(ctx, tmpbuf.get(&v1b, rows2 * 4 + 4));
+  TIR_CUDA(ctx, tmpbuf.get(&v2b, rows2 * 4 + 4));
+  TIR_CUDA(ctx, cudaMemcpyAsync(d_map, map.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  TIR_CUDA(ctx, cudaMemcpyAsync(d_nro, nro.data(), ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, st));
+  TIR_CUDA(ctx, cudaMemsetAsync(alive2, 1, (size_t)m + 1, st));
+  tir_compact_kernel<<<(uint32_t)(((uint64_t)n * 32 + 255) / 256), 256, 0, st>>>(d_map, (const uint64_t *)db->row_off.p, d_nro, (const uint8_t *)db->uuids.p,
+                                                                                (const int32_t *)db->v1.p, (const int32_t *)db->v2.p, n, uu2, v1b, v2b);
+  TIR_CUDA(ctx, cudaGetLastError());
+  TIR_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->launches++;
+  // swap: the new arrays become the master copy, the old ones are freed with the temporaries
+  auto take = [&](DevBuf &b, void *np, size_t cap) {
+    for (void *&q : tmpbuf.p)
+      if (q == np) q = b.p; // the old buffer takes the new one's place in the to-free list
+    b.p = np, b.cap = cap;
+  };
+  take(db->uuids, uu2, (size_t)m * 16 + 16);
+  take(db->alive, alive2, (size_t)m + 1);
+  take(db->v1, v1b, rows2 * 4 + 4);
+  take(db->v2, v2b, rows2 * 4 + 4);
+  take(db->row_off, d_nro, ((size_t)m + 1) * 8);
+  db->h_uuids.swap(nuu);
+  db->h_row_off.swap(nro);
+  db->h_alive.assign(m, 1);
+  db->by_uuid.clear(), db->lookup_ready = false;
+  db->n_audio = m, db->n_rows = rows2, db->n_alive = m;
+  db->n_compactions++;
+  return TIR_OK;
+}
+
 // Bring the indices up to date.  A full rebuild (main over everything alive) happens after a load and when
 // the tail or the tombstones have outgrown their budget; otherwise only the small tail is re-indexed.
 static int db_refresh(tir_ctx *ctx, TirDb *db) {
@@ -391,6 +464,8 @@ static int db_refresh(tir_ctx *ctx, TirDb *db) {
     if (tail_rows > std::max<uint64_t>(1u << 20, main_rows / 16) || (uint64_t)db->main.n_dead * 4 > (uint64_t)(db->main.a1 - db->main.a0) + 64) db->dirty = true;
   }
   if (db->dirty || !db->main.built) {
+    if ((rc = db_compact(ctx, db))) return rc; // (audio numbers change: both indices are rebuilt / emptied below)
+    const uint32_t n = (uint32_t)db->n_audio;
     if ((rc = db_build_index(ctx, db, db->main, 0, n))) return rc;
     index_free(db->tail);
     db->tail.a0 = db->tail.a1 = n, db->tail.built = true;

@@ -128,7 +128,9 @@ int tir_db_stats(tir_ctx *ctx, uint64_t *n_audio, uint64_t *n_rows);
  * a millisecond by the next search; its winners are folded with the main index's like those of a second shard), a
  * removed audio gets a tombstone that the kernels consult where they pick a block's winners.  The full sort of the
  * table runs only after a load, or when the tail holds more than max(2^20, rows/16) rows or a quarter of the main
- * index is dead.  Counters: full sorts so far, tail sorts, audios in the tail, tombstones. */
+ * index is dead; it first drops the removed audios from the device copy of the table (no growth under churn) and sorts
+ * in passes of ~64 M rows (scratch: 2 GB whatever the table's size).  Counters: full sorts so far, tail sorts, audios
+ * in the tail, tombstones. */
 int tir_db_index_stats(tir_ctx *ctx, uint64_t *n_full_builds, uint64_t *n_tail_builds, uint64_t *tail_audios, uint64_t *tombstones);
 /* A caller that keeps searching with the same buffers, batch shape and parameters (the batcher, the stream pump, a
  * benchmark loop) has its match chain -- the copy of the query offsets, the clearing of the scratch, the four kernels --

@@ -492,3 +492,45 @@ def test_index_built_in_passes_equals_one_pass(monkeypatch):
     assert any((m > 0).any() for m, _ in one)
     for (m1, u1), (m2, u2) in zip(one, many):
         assert np.array_equal(m1, m2) and np.array_equal(u1, u2)
+
+
+def test_churn_compacts_the_table_and_still_follows_sqlite(gpu_ctx, oracle):
+    """add / remove churn: once a quarter of the main index is dead the next search rebuilds it, and the rebuild first
+    drops the removed audios from the master copy (the table does not grow without bound); every answer before,
+    across and after the compaction equals SQLite, adds and removes keep working on the renumbered table."""
+    rng = np.random.default_rng(33)
+    db = synth_db.make_db(300, 8, 20, seed=41)
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    queries = [db[i][1] for i in (1, 150, 299)] + [synth_db.random_y(rng, 30) for _ in range(3)]
+
+    def check():
+        for y in queries:
+            assert gpu_result(gpu_ctx.match(y, tolerance=0.01)[0]) == sql_result(sq.search(y, tolerance=0.01))
+
+    check()
+    b0 = gpu_ctx.db_index_stats()["full_builds"]
+    gone = list(range(0, 300, 2))                                       # half of the table: past the tombstone budget
+    for k, i in enumerate(gone):
+        gpu_ctx.db_remove(capi.uuid_to_bytes(db[i][0])); sq.delete_audio(db[i][0])
+        if k in (10, 60):
+            check()                                                     # tombstones only
+    check()                                                             # this search compacts and rebuilds
+    st = gpu_ctx.db_index_stats()
+    assert st["full_builds"] == b0 + 1 and st["tombstones"] == 0
+    assert gpu_ctx.db_stats() == (150, sq.count_rows())
+    extra = synth_db.make_db(40, 8, 20, seed=43)
+    for u, y in extra:                                                  # the renumbered table takes adds and removes
+        v = synth_db.quantize_y(y)
+        gpu_ctx.db_add(capi.uuid_to_bytes(u), v[:, 0], v[:, 1]); sq.add_audio(u, y)
+    queries.append(extra[7][1])
+    check()
+    for i in (1, 151, 299):
+        gpu_ctx.db_remove(capi.uuid_to_bytes(db[i][0])); sq.delete_audio(db[i][0])
+    gpu_ctx.db_remove(capi.uuid_to_bytes(extra[7][0])); sq.delete_audio(extra[7][0])
+    check()
+    with pytest.raises(capi.TirError):
+        gpu_ctx.db_remove(capi.uuid_to_bytes(db[0][0]))                 # compacted away long ago: unknown
+    assert gpu_ctx.db_stats() == (150 + 40 - 4, sq.count_rows())
