@@ -302,6 +302,21 @@ TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg,
 // over its bins in ascending order from 0.f; bins where a lane's weight is 0 add +0 (x is finite: a
 // magnitude).  Weights and run lists are read from shared memory (w2, run_*); the parameters of the
 // next run are fetched while the current one accumulates.  Writes the raw sums to lg.
+// `NP` pairs of bins starting `k` pairs before the end of the run: the addresses are run-end pointers plus
+// immediates, all loads of the block are issued before its sums (the sums themselves are one dependent chain).
+template <int NP>
+TIR_DEV TirP2 tir_mel_block(TirP2 acc, const float *me, const float4 *wp, int k, TirP2 nz) {
+  float4 wv[NP];
+  float ma[NP], mb[NP];
+#pragma unroll
+  for (int j = 0; j < NP; j++) wv[j] = wp[j - k], ma[j] = me[64 * (j - k)], mb[j] = me[64 * (j - k) + 32];
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    acc = tir_padd(acc, tir_pmulx(tir_pbc(ma[j]), tir_pmk(wv[j].x, wv[j].y), nz));
+    acc = tir_padd(acc, tir_pmulx(tir_pbc(mb[j]), tir_pmk(wv[j].z, wv[j].w), nz));
+  }
+  return acc;
+}
 TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp, const float2 *w2, const int *run_bins,
                            const int *run_emit, int seg, int f, TirP2 nz) {
   const int r0 = mp.seg_run0[seg], nr = mp.seg_nruns[seg];
@@ -313,15 +328,22 @@ TIR_DEV void tir_mel_sweep(const float *norm, float *lg, const TirMelParams &mp,
   for (int r = 0; r < nr; r++) {
     const int n_next = run_bins[r0 + r + 1], fe_next = run_emit[r0 + r + 1]; // the list ends with a sentinel
     // bins in pairs; an odd run's last pair holds a zero-weight record (tir_tables.cpp) and sweeps the
-    // next bin with it: acc + (+-0) is exact, and the magnitude buffer is finite everywhere
-    const int np = (n + 1) >> 1;
-#pragma unroll 2
-    for (int p = 0; p < np; p++) {
-      const float4 wv = wp[p];
-      acc = tir_padd(acc, tir_pmulx(tir_pbc(m[64 * p]), tir_pmk(wv.x, wv.y), nz));
-      acc = tir_padd(acc, tir_pmulx(tir_pbc(m[64 * p + 32]), tir_pmk(wv.z, wv.w), nz));
+    // next bin with it: acc + (+-0) is exact, and the magnitude buffer is finite everywhere.
+    // Runs are short (a mel triangle's rising or falling edge: 2..30 pairs), so a counted loop spends as many
+    // instructions on its compare / branch / address updates as on the sums.  The pairs are addressed from the
+    // run's END: first the k mod 4 leading pairs, then blocks of four pairs (ascending bins -- the very order of
+    // the loop this replaces), every block with immediate addresses and its loads in flight together.  The code
+    // is the same for every warp: per-warp straight-line code lost to the instruction cache.
+    int k = (n + 1) >> 1;
+    const float *me = m + 64 * k; // end of the run's pairs (one bin past the run when n is odd)
+    m += 32 * n, wp += k;         // the next run starts at bin + n, after the k records
+    switch (k & 3) {
+      case 3: acc = tir_mel_block<3>(acc, me + 0, wp, k, nz); break;
+      case 2: acc = tir_mel_block<2>(acc, me + 0, wp, k, nz); break;
+      case 1: acc = tir_mel_block<1>(acc, me + 0, wp, k, nz); break;
+      default: break;
     }
-    m += 32 * n, wp += np;
+    for (k &= ~3; k > 0; k -= 4) acc = tir_mel_block<4>(acc, me, wp, k, nz);
     if (fe & 1) lg[fe * 32 + f] = acc.hi, acc.hi = 0.f;
     else lg[fe * 32 + f] = acc.lo, acc.lo = 0.f;
     n = n_next, fe = fe_next;

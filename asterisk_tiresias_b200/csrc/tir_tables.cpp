@@ -186,7 +186,7 @@ bool tir_build_tables(int win, int hop, int n_filters, int n_coefs, int samplera
   // of the previous tile (clock64 trace: worth about 270 slots), so their segments are smaller
   const int n_sweep = NW;
   auto seg_cost = [&](int ia, int ib) { // live[ia..ib)
-    return ia >= ib ? 0 : 21 * (last[live[ib - 1]] - first[live[ia]] + 1) / 4 + 26 * (ib - ia) + 20;
+    return ia >= ib ? 0 : 16 * (last[live[ib - 1]] - first[live[ia]] + 1) / 4 + 24 * (ib - ia) + 20;
   };
   const int dct_cost = 270;
   const int nl = (int)live.size();
