@@ -19,6 +19,11 @@
 #include <new>
 #include <thread>
 
+#include <climits>
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "tir_internal.h"
 
 namespace {
@@ -27,8 +32,20 @@ struct Request {
   uint64_t n = 0, off = 0;
   tir_hit *hit = nullptr;
   int rc = TIR_OK;
-  bool done = false;
 };
+
+// Completion of a batch is announced through a per-slot generation word that the members sleep on with futex(2):
+// a thousand callers woken by one condition variable would re-acquire the dispatcher's mutex one after the other
+// (and contend with the callers joining the next batch) -- the tail of the latency distribution.  The members'
+// results are written before the release-increment, read after the acquire-load: no lock on the way out.
+static void gen_wait(std::atomic<uint32_t> &g, uint32_t seen) {
+  while (g.load(std::memory_order_acquire) == seen)
+    syscall(SYS_futex, reinterpret_cast<uint32_t *>(&g), FUTEX_WAIT_PRIVATE, seen, nullptr, nullptr, 0);
+}
+static void gen_bump(std::atomic<uint32_t> &g) {
+  g.fetch_add(1, std::memory_order_release);
+  syscall(SYS_futex, reinterpret_cast<uint32_t *>(&g), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+}
 
 struct Params {
   int coefs = 1, ign_lo = -1, ign_hi = -1;
@@ -49,6 +66,7 @@ struct Slot {
   bool open = false;    // accepts members
   bool sealed = false;  // somebody could not join: dispatch without waiting for max_wait
   std::chrono::steady_clock::time_point t_first;
+  std::atomic<uint32_t> done_gen{0}; // + 1 per finished batch of this slot (its members sleep on it)
 };
 
 } // namespace
@@ -106,11 +124,11 @@ void TirBatcher::run() {
     if (nb > max_seen) max_seen = nb;
     for (size_t i = 0; i < nb; i++) {
       if (rc == TIR_OK) *s.members[i]->hit = hits[i];
-      s.members[i]->rc = rc, s.members[i]->done = true;
+      s.members[i]->rc = rc;
     }
-    s.members.clear(), s.used = 0, s.sealed = false;
+    s.members.clear(), s.used = 0, s.sealed = false; // (the Requests live on their callers' stacks: not touched after the bump)
     (void)cur;
-    cv_done.notify_all();
+    gen_bump(s.done_gen);
   }
 }
 
@@ -187,14 +205,19 @@ int tir_batcher_submit(TirBatcher *b, const int16_t *pcm, uint64_t n_samples, in
   r.off = s->used, s->used += n_samples;
   s->members.push_back(&r);
   s->copying++;
+  const uint32_t gen0 = s->done_gen.load(std::memory_order_relaxed); // this slot's batches finished so far
   if (s->members.size() == 1 || s->members.size() >= b->max_batch) b->cv_work.notify_all();
   int16_t *dst = s->h_pcm + r.off;
   lk.unlock();
   if (n_samples) std::memcpy(dst, pcm, n_samples * sizeof(int16_t)); // in parallel with the other callers
   lk.lock();
   if (--s->copying == 0) b->cv_work.notify_all();
-  b->cv_done.wait(lk, [&] { return r.done; });
-  if (r.rc != TIR_OK && err) *err = b->last_err;
+  lk.unlock();
+  gen_wait(s->done_gen, gen0); // the batch this request rode in has been served
+  if (r.rc != TIR_OK && err) {
+    lk.lock();
+    *err = b->last_err;
+  }
   return r.rc;
 }
 

@@ -26,6 +26,11 @@
 #include <new>
 #include <thread>
 
+#include <climits>
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "tir_internal.h"
 
 namespace {
@@ -83,8 +88,20 @@ struct tir_stream {
   Params params;
   tir_hit hit{};
   int rc = TIR_OK;
-  bool done = false, closing = false, busy = false;
+  bool closing = false, busy = false;
+  // set (release) after rc / hit are in place; tir_stream_finish sleeps on it with futex(2) -- a thousand finishing
+  // callers woken through one condition variable would queue up on the hub's mutex
+  std::atomic<uint32_t> done{0};
 };
+
+static void stream_mark_done(tir_stream *s) {
+  s->done.store(1, std::memory_order_release);
+  syscall(SYS_futex, reinterpret_cast<uint32_t *>(&s->done), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+}
+static void stream_wait_done(tir_stream *s) {
+  while (s->done.load(std::memory_order_acquire) == 0)
+    syscall(SYS_futex, reinterpret_cast<uint32_t *>(&s->done), FUTEX_WAIT_PRIVATE, 0, nullptr, nullptr, 0);
+}
 
 struct TirStreamHub {
   tir_ctx *ctx = nullptr;
@@ -104,6 +121,28 @@ struct TirStreamHub {
   tir_hit *h_hits = nullptr;
   size_t hits_cap = 0;
   uint64_t n_batches = 0, n_hops = 0, n_match_batches = 0;
+  // coefficient arrays of closed streams, reused by the next ones: a cudaMalloc per new stream and a device-wide
+  // synchronising cudaFree per closed one were most of the front-end's latency at a thousand channels.  Everything
+  // that touches these arrays is ordered on the context's stream, so a reused array needs no synchronisation.
+  std::mutex pool_mu;
+  std::vector<std::pair<float *, uint64_t>> pool; // (array, capacity in frames)
+  float *pool_take(uint64_t cap_frames, uint64_t *got_cap) {
+    std::lock_guard<std::mutex> lk(pool_mu);
+    for (size_t i = 0; i < pool.size(); i++)
+      if (pool[i].second >= cap_frames) {
+        float *p = pool[i].first;
+        *got_cap = pool[i].second;
+        pool[i] = pool.back(), pool.pop_back();
+        return p;
+      }
+    return nullptr;
+  }
+  bool pool_give(float *p, uint64_t cap_frames) { // false: the pool is full, the caller frees
+    std::lock_guard<std::mutex> lk(pool_mu);
+    if (pool.size() >= 8192) return false;
+    pool.emplace_back(p, cap_frames);
+    return true;
+  }
 
   void run();
   int extract_batch(std::vector<tir_stream *> &streams);
@@ -185,10 +224,10 @@ int TirStreamHub::extract_batch(std::vector<tir_stream *> &streams) {
     if (s->frames + add > s->cap_frames) { // grow the stream's coefficient array (4096 frames = 131 s at 8 kHz / hop 256 to start with)
       uint64_t cap = std::max<uint64_t>(4096, s->cap_frames * 2);
       while (cap < s->frames + add) cap *= 2;
-      float *np = nullptr;
-      TIR_CUDA(ctx, cudaMalloc(&np, cap * TIR_N_COEFS * sizeof(float)));
+      float *np = pool_take(cap, &cap);
+      if (!np) TIR_CUDA(ctx, cudaMalloc(&np, cap * TIR_N_COEFS * sizeof(float)));
       if (s->frames) TIR_CUDA(ctx, cudaMemcpyAsync(np, s->d_coef, s->frames * TIR_N_COEFS * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-      if (s->d_coef) {
+      if (s->d_coef && !pool_give(s->d_coef, s->cap_frames)) {
         TIR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(s->d_coef);
       }
@@ -267,9 +306,8 @@ void TirStreamHub::match_batch(std::vector<tir_stream *> &group) {
   for (uint32_t i = 0; i < Q; i++) {
     group[i]->rc = rc;
     if (rc == TIR_OK) group[i]->hit = h_hits[i];
-    group[i]->done = true;
+    stream_mark_done(group[i]);
   }
-  cv_done.notify_all();
 }
 
 void TirStreamHub::run() {
@@ -298,7 +336,7 @@ void TirStreamHub::run() {
       if (s->finishing && (s->flushed || s->failed)) fin.push_back(s);
     }
     lk.lock();
-    fin.erase(std::remove_if(fin.begin(), fin.end(), [](tir_stream *s) { return s->done; }), fin.end());
+    fin.erase(std::remove_if(fin.begin(), fin.end(), [](tir_stream *s) { return s->done.load(std::memory_order_acquire) != 0; }), fin.end());
     lk.unlock();
     while (!fin.empty()) {
       std::vector<tir_stream *> group, rest;
@@ -310,8 +348,8 @@ void TirStreamHub::run() {
         }
         if (failed) {
           std::lock_guard<std::mutex> l3(mu);
-          s->rc = TIR_ERR_CUDA, s->done = true;
-          cv_done.notify_all();
+          s->rc = TIR_ERR_CUDA;
+          stream_mark_done(s);
         } else if (group.empty() || s->params == group[0]->params) {
           group.push_back(s);
         } else {
@@ -347,7 +385,10 @@ void tir_stream_hub_destroy(TirStreamHub *h) {
     std::lock_guard<std::mutex> lk(h->mu);
     h->stop = true;
     for (tir_stream *s : h->live) // callers blocked in finish: released with an error
-      if (s->finishing && !s->done) s->rc = TIR_ERR_STATE, s->done = true;
+      if (s->finishing && !s->done.load()) {
+        s->rc = TIR_ERR_STATE;
+        stream_mark_done(s);
+      }
   }
   h->cv_pump.notify_all();
   h->cv_done.notify_all();
@@ -358,6 +399,7 @@ void tir_stream_hub_destroy(TirStreamHub *h) {
   if (h->h_hits) cudaFreeHost(h->h_hits);
   for (DevBuf *b : {&h->d_pcm, &h->d_tmp, &h->d_seg, &h->d_qcoef, &h->d_qhits})
     if (b->p) cudaFree(b->p);
+  for (auto &e : h->pool) cudaFree(e.first);
   for (tir_stream *s : h->live) s->hub = nullptr; // the owners still close them
   delete h;
 }
@@ -424,11 +466,16 @@ int tir_stream_finish(tir_stream *s, int coefs, double tolerance, int freq_ignor
     s->params.coefs = coefs, s->params.tol = tolerance, s->params.ign_lo = freq_ignore_low, s->params.ign_hi = freq_ignore_high;
     s->finishing = true;
   }
-  std::unique_lock<std::mutex> lk(h->mu);
-  h->kick = true;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->kick = true;
+  }
   h->cv_pump.notify_all(); // do not wait for the period
-  h->cv_done.wait(lk, [&] { return s->done; });
-  if (s->rc != TIR_OK) return tir_fail(ctx, s->rc, "tir_stream_finish: %s", h->last_err.c_str());
+  stream_wait_done(s);
+  if (s->rc != TIR_OK) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    return tir_fail(ctx, s->rc, "tir_stream_finish: %s", h->last_err.c_str());
+  }
   *hit = s->hit;
   return TIR_OK;
 }
@@ -441,7 +488,7 @@ void tir_stream_close(tir_stream *s) {
     h->cv_done.wait(lk, [&] { return !s->busy; }); // the pump may be in the middle of a batch that holds this stream
     h->live.erase(std::remove(h->live.begin(), h->live.end(), s), h->live.end());
   }
-  if (s->d_coef) {
+  if (s->d_coef && !(s->hub && s->hub->pool_give(s->d_coef, s->cap_frames))) {
     std::lock_guard<std::mutex> lk(s->ctx->mu);
     cudaSetDevice(s->ctx->cfg.device);
     cudaStreamSynchronize(s->ctx->stream);
