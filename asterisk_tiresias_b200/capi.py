@@ -58,6 +58,7 @@ def lib():
         L.tir_extract.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_selftest.argtypes = [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.tir_extract_ulaw.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
+        L.tir_extract_interleaved.argtypes = [vp, vp, C.c_int, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_extract_dev.argtypes = [vp, vp, u64p, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.tir_get_tables.argtypes = [vp, vp, vp, vp]
         L.tir_launch_count.restype = C.c_uint64
@@ -225,6 +226,20 @@ class Context:
         vq = np.empty((F, 2), np.int32)
         nf = C.c_uint64()
         self._chk(lib().tir_extract_ulaw(self._h, _p(ulaw), _p(clip_off), clip_off.size - 1, _p(coef), _p(vq), C.byref(nf)))
+        assert nf.value == F
+        return coef, vq
+
+    def extract_interleaved(self, pcm, channels, clip_off=None):
+        """pcm[sample frame, channel] int16 (interleaved); clip_off in sample frames."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        if clip_off is None:
+            clip_off = np.array([0, pcm.size // channels], np.uint64)
+        clip_off = np.ascontiguousarray(clip_off, dtype=np.uint64)
+        F = self.n_frames(clip_off)
+        coef = np.empty((F, 2), np.float32)
+        vq = np.empty((F, 2), np.int32)
+        nf = C.c_uint64()
+        self._chk(lib().tir_extract_interleaved(self._h, _p(pcm), channels, _p(clip_off), clip_off.size - 1, _p(coef), _p(vq), C.byref(nf)))
         assert nf.value == F
         return coef, vq
 

@@ -147,7 +147,7 @@ void tir_close(tir_ctx *ctx) {
   if (ctx->db) tir_db_destroy(ctx->db);
   cudaFree(ctx->d_win4), cudaFree(ctx->d_twp4), cudaFree(ctx->d_twu4);
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
-  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_qmeta2), free_dev(ctx->d_hits), free_dev(ctx->d_hits2), free_dev(ctx->d_y), free_dev(ctx->d_counter), free_dev(ctx->d_ulaw);
+  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_qmeta2), free_dev(ctx->d_hits), free_dev(ctx->d_hits2), free_dev(ctx->d_y), free_dev(ctx->d_counter), free_dev(ctx->d_ulaw), free_dev(ctx->d_mix);
   for (int k = 0; k < tir_ctx::kStageSlots; k++) {
     if (ctx->h_stage[k].p) cudaFreeHost(ctx->h_stage[k].p);
     if (ctx->h_stage_ev[k]) cudaEventDestroy(ctx->h_stage_ev[k]);
@@ -320,6 +320,49 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
 int tir_extract_ulaw(tir_ctx *ctx, const uint8_t *ulaw, const uint64_t *clip_off, uint32_t n_clips, float *coef, int32_t *vq,
                      uint64_t *n_frames) {
   return extract_host(ctx, ulaw, true, clip_off, n_clips, coef, vq, n_frames);
+}
+
+// Multi-channel files are an ingest-time case (a directory scan, the CLI): one copy in, the down-mix, one launch, one
+// copy out -- no chunk pipeline.
+int tir_extract_interleaved(tir_ctx *ctx, const int16_t *pcm, int channels, const uint64_t *clip_off, uint32_t n_clips,
+                            float *coef, int32_t *vq, uint64_t *n_frames) {
+  if (channels == 1) return tir_extract(ctx, pcm, clip_off, n_clips, coef, vq, n_frames);
+  if (!ctx || !clip_off || (!pcm && n_clips && clip_off[n_clips] > clip_off[0])) return tir_fail(ctx, TIR_ERR_ARG, "null argument");
+  if (channels < 1 || channels > 64) return tir_fail(ctx, TIR_ERR_ARG, "channels must be 1..64");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+  const uint64_t base = clip_off[0], total = clip_off[n_clips] - base;
+  uint64_t F = 0;
+  std::vector<uint64_t> rel((size_t)n_clips + 1, 0);
+  for (uint32_t c = 0; c < n_clips; c++) {
+    if (clip_off[c + 1] < clip_off[c]) return tir_fail(ctx, TIR_ERR_ARG, "clip_off must be non-decreasing");
+    F += tir_n_frames(clip_off[c + 1] - clip_off[c], ctx->cfg.hop);
+    rel[c + 1] = clip_off[c + 1] - base;
+  }
+  if (n_frames) *n_frames = F;
+  if (F == 0) return TIR_OK;
+  int rc;
+  if ((rc = tir_reserve(ctx, ctx->d_pcm, total * (uint64_t)channels * sizeof(int16_t) + 16))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_mix, total * sizeof(float) + 16))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_coef, F * TIR_N_COEFS * sizeof(float)))) return rc;
+  if ((rc = tir_reserve(ctx, ctx->d_vq, F * TIR_N_COEFS * sizeof(int32_t)))) return rc;
+  int16_t *d_in = (int16_t *)ctx->d_pcm.p;
+  float *d_mix = (float *)ctx->d_mix.p;
+  TIR_CUDA(ctx, cudaMemcpyAsync(d_in, pcm + base * (uint64_t)channels, total * (uint64_t)channels * sizeof(int16_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = tir_downmix_launch(ctx, d_in, total, channels, d_mix))) return rc;
+  if ((rc = tir_extract_launch_f32(ctx, d_mix, rel.data(), n_clips, (float *)ctx->d_coef.p, (int32_t *)ctx->d_vq.p, nullptr))) {
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+  }
+  const size_t n = (size_t)F * TIR_N_COEFS;
+  cudaError_t e = cudaSuccess;
+  if (coef) e = cudaMemcpyAsync(coef, ctx->d_coef.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (vq && e == cudaSuccess) e = cudaMemcpyAsync(vq, ctx->d_vq.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = e2;
+  if (e != cudaSuccess) return tir_fail(ctx, TIR_ERR_CUDA, "tir_extract_interleaved: %s", cudaGetErrorString(e));
+  return TIR_OK;
 }
 
 } // extern "C"

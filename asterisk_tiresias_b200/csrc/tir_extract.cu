@@ -23,13 +23,13 @@ struct __align__(16) TirTile {
 };
 
 struct TirExtractArgs {
-  const int16_t *pcm;
+  const void *pcm;        // int16_t samples, or float samples (F32IN kernels: the down-mixed multi-channel input * 2^15)
   const TirTile *tiles; // [n_tiles]
   const float4 *win4, *twp4, *twu4;
   float *coef;
   int32_t *vq;
   uint32_t n_tiles;
-  uint32_t pcm_aligned8; // base pointer is 8-byte aligned
+  uint32_t pcm_aligned8; // base pointer is aligned to one 4-sample unit (8 bytes of s16, 16 bytes of float)
   float2 neg_zero;       // (-0, -0): see tir_pmulx
   uint32_t *tile_counter; // zeroed before the launch: tiles beyond the first two of every CTA are claimed dynamically
   TirCoefX cx;            // sharded search: coefficients also go to every rank's buffer (cx.peer == nullptr: off)
@@ -103,56 +103,72 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_unit(uint2 *dst, const int16_t *src) { cp_async8(dst, src); }
+__device__ __forceinline__ void cp_async_unit(float4 *dst, const float *src) { cp_async16(dst, src); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// four samples s .. s+3 of a clip, zeros outside it, as one unit of the tile
+__device__ __forceinline__ uint2 tir_edge_unit(const int16_t *clip, int64_t s, int64_t nsamp, uint2) {
+  uint32_t h[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int64_t i = s + e;
+    h[e] = (i >= 0 && i < nsamp) ? (uint32_t)(uint16_t)__ldg(clip + i) : 0u;
+  }
+  return make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+}
+__device__ __forceinline__ float4 tir_edge_unit(const float *clip, int64_t s, int64_t nsamp, float4) {
+  float h[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int64_t i = s + e;
+    h[e] = (i >= 0 && i < nsamp) ? __ldg(clip + i) : 0.f;
+  }
+  return make_float4(h[0], h[1], h[2], h[3]);
+}
 
-// P0: (T+1) hops of the clip -> buf, 8 bytes (4 samples) per copy, asynchronously where the four
-// samples lie inside the clip and are 8-byte aligned; samples outside the clip are zeros (the first
+// P0: (T+1) hops of the clip -> buf, one unit (4 samples) per copy, asynchronously where the four
+// samples lie inside the clip and the unit is aligned; samples outside the clip are zeros (the first
 // hop of a clip sees the all-zero pvoc history, the last hop is zero padded: new_aubio_pvoc /
 // aubio_source_do).  Hop chunk c of the tile lands at buf[c * PCH ...]: lane = frame reads of P1
-// then have a stride of PCH 8-byte units = 2 banks (mod 32), conflict free.
+// then have a stride of PCH units (odd), conflict free.
 // Thread tid copies unit p = tid % UPC of chunks tid / UPC, + NT / UPC, ...
-template <int WIN>
-__device__ __forceinline__ void tir_issue_tile_load(uint2 *buf, const int16_t *__restrict__ pcm, const TirTile &td,
+template <int WIN, class U, class S>
+__device__ __forceinline__ void tir_issue_tile_load(U *buf, const S *__restrict__ pcm, const TirTile &td,
                                                     bool base_aligned, int tid) {
   using C = TirCfg<WIN>;
-  constexpr int UPC = C::HOP / 4;       // 8-byte units per hop chunk
+  constexpr int UPC = C::HOP / 4;       // units per hop chunk
   constexpr int CSTEP = C::NT / UPC;    // chunks advanced per iteration (4)
   static_assert(C::NT % UPC == 0, "thread <-> unit mapping");
-  const int16_t *clip = pcm + td.c0;
+  const S *clip = pcm + td.c0;
   const bool aligned = base_aligned && ((td.c0 & 3) == 0);
   const int64_t nsamp = td.nsamp;
   const int p = tid % UPC;
   int chunk = tid / UPC;
   int64_t s = ((int64_t)td.f0 - 1 + chunk) * C::HOP + 4 * p;
-  uint2 *dst = buf + chunk * C::PCH + p;
+  U *dst = buf + chunk * C::PCH + p;
   const bool interior = aligned && td.f0 >= 1 && ((int64_t)td.f0 + C::T) * C::HOP <= nsamp; // CTA-uniform
   if (interior) {
 #pragma unroll
     for (int i = 0; i < (C::T + 1 + CSTEP - 1) / CSTEP; i++) {
-      if (chunk + i * CSTEP <= C::T) cp_async8(dst + i * CSTEP * C::PCH, clip + s + (int64_t)i * CSTEP * C::HOP);
+      if (chunk + i * CSTEP <= C::T) cp_async_unit(dst + i * CSTEP * C::PCH, clip + s + (int64_t)i * CSTEP * C::HOP);
     }
   } else {
 #pragma unroll 1
     for (; chunk <= C::T; chunk += CSTEP, s += (int64_t)CSTEP * C::HOP, dst += CSTEP * C::PCH) {
-      if (aligned && s >= 0 && s + 4 <= nsamp) {
-        cp_async8(dst, clip + s);
-      } else {
-        uint32_t h[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int64_t i = s + e;
-          h[e] = (i >= 0 && i < nsamp) ? (uint32_t)(uint16_t)__ldg(clip + i) : 0u;
-        }
-        *dst = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
-      }
+      if (aligned && s >= 0 && s + 4 <= nsamp) cp_async_unit(dst, clip + s);
+      else *dst = tir_edge_unit(clip, s, nsamp, U{});
     }
   }
   cp_async_commit();
 }
 
-template <int WIN>
-__device__ __forceinline__ void tir_pass1(TirSmem<WIN> &sm, const uint2 *pcm, int role, int lane, TirP2 nz) {
+template <int WIN, class SM, class U>
+__device__ __forceinline__ void tir_pass1(SM &sm, const U *pcm, int role, int lane, TirP2 nz) {
   if constexpr (WIN == 512) tir_pass1_512(sm, pcm, role, lane, nz);
   else tir_pass1_1024(sm, pcm, role, lane, nz);
 }
@@ -176,12 +192,16 @@ __device__ __forceinline__ void tir_emit_coefs(const float *lg, const TirMelPara
 
 // Per tile: P1 | sync | P2 load | sync | P2 compute | sync | P3a sweep (coefficient warps: P4 of the
 // previous tile first) + wait for the next tile's PCM | sync | P3b logs -- no barrier before the next P1.
-template <int WIN>
-__global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
+// F32IN: float samples in (the down-mixed multi-channel path, tir_extract_interleaved): twice the PCM tile, one CTA per SM
+template <int WIN, bool F32IN>
+__global__ void __launch_bounds__(TirCfg<WIN>::NT, F32IN ? 1 : TirCfg<WIN>::CTAS_PER_SM)
     tir_extract_kernel(const __grid_constant__ TirExtractArgs a, const __grid_constant__ TirMelParams mp) {
   using C = TirCfg<WIN>;
+  using SM = TirSmem<WIN, F32IN>;
+  using S = typename std::conditional<F32IN, float, int16_t>::type;
+  const S *const a_pcm = static_cast<const S *>(a.pcm);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TirSmem<WIN> &sm = *reinterpret_cast<TirSmem<WIN> *>(smem_raw);
+  SM &sm = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler
   const bool base_aligned = a.pcm_aligned8 != 0;
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   // the last quarter of its tiles alone on the SM.  Every CTA starts with tiles bid and bid + grid.
   __shared__ uint32_t s_claim;
   TirTile cur = tir_load_tile_desc(a.tiles + blockIdx.x); // grid <= n_tiles
-  tir_issue_tile_load<WIN>(sm.pcm, a.pcm, cur, base_aligned, tid);
+  tir_issue_tile_load<WIN>(sm.pcm, a_pcm, cur, base_aligned, tid);
   bool have_nxt = blockIdx.x + gridDim.x < a.n_tiles;
   TirTile nxt = cur, prev = cur;
   if (have_nxt) nxt = tir_load_tile_desc(a.tiles + blockIdx.x + gridDim.x);
@@ -204,7 +224,7 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
   for (int i = tid; i < TIR_MAX_W2; i += C::NT) sm.w2[i] = mp.w2[i];
   for (int i = tid; i < TIR_MAX_RUNS; i += C::NT) sm.run_bins[i] = mp.run_bins[i], sm.run_emit[i] = mp.run_emit[i];
   // bins 0 and M of the magnitude buffer are never written; keep the whole buffer finite
-  for (int i = tid; i < TirSmem<WIN>::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
+  for (int i = tid; i < SM::XCH_WORDS; i += C::NT) sm.xch[i] = 0.f;
   // filters without weights: log10f(clamp) once, nothing overwrites it
   for (int i = tid; i < 2 * TIR_MAX_FILTERS * 32; i += C::NT) {
     const int fidx = (i / 32) % TIR_MAX_FILTERS;
@@ -227,7 +247,7 @@ __global__ void __launch_bounds__(TirCfg<WIN>::NT, TirCfg<WIN>::CTAS_PER_SM)
     TirTile nn = nxt;
     bool have_nn = false;
     if (have_nxt) {
-      tir_issue_tile_load<WIN>(sm.pcm, a.pcm, nxt, base_aligned, tid); // streams in under P2..P3a
+      tir_issue_tile_load<WIN>(sm.pcm, a_pcm, nxt, base_aligned, tid); // streams in under P2..P3a
       const uint32_t t2 = s_claim;
       have_nn = t2 < a.n_tiles;
       if (have_nn) nn = tir_load_tile_desc(a.tiles + t2); // needed one tile from now
@@ -354,8 +374,28 @@ size_t tir_extract_smem_bytes(int win) {
   return win == 512 ? sizeof(TirSmem<512>) : win == 1024 ? sizeof(TirSmem<1024>) : 0;
 }
 
-template <int WIN>
-static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,
+// aubio_source_*_do for a multi-channel file (source_wavread.c / source_sndfile.c): every channel's sample / 32768 in
+// float, summed in channel order from 0.f, divided by the channel count.  The result is kept * 2^15 (exact), so that
+// the kernel's window product rn(v * w * 2^-15) is aubio's rn(mono * w).
+__global__ void tir_downmix_kernel(const int16_t *__restrict__ in, uint64_t n_frames, int channels, float *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames) return;
+  const int16_t *p = in + i * (uint64_t)channels;
+  float acc = 0.f;
+  for (int c = 0; c < channels; c++) acc = __fadd_rn(acc, __fdiv_rn((float)p[c], 32768.f));
+  out[i] = __fmul_rn(__fdiv_rn(acc, (float)channels), 32768.f);
+}
+
+int tir_downmix_launch(tir_ctx *ctx, const int16_t *d_in, uint64_t n_frames, int channels, float *d_out) {
+  if (n_frames == 0) return TIR_OK;
+  tir_downmix_kernel<<<(uint32_t)((n_frames + 255) / 256), 256, 0, ctx->stream>>>(d_in, n_frames, channels, d_out);
+  TIR_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return TIR_OK;
+}
+
+template <int WIN, bool F32IN>
+static int tir_extract_launch_t(tir_ctx *ctx, const void *d_pcm, const uint64_t *clip_off, uint32_t n_clips,
                                 float *d_coef, int32_t *d_vq, uint64_t *n_frames, const TirCoefX *cx) {
   using C = TirCfg<WIN>;
   // ---- host-side tile bookkeeping (metadata only) -> one pinned staging buffer -> device
@@ -403,22 +443,22 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
   a.win4 = ctx->d_win4, a.twp4 = ctx->d_twp4, a.twu4 = ctx->d_twu4;
   a.coef = d_coef, a.vq = d_vq;
   a.n_tiles = n_tiles;
-  a.pcm_aligned8 = (((uintptr_t)d_pcm) & 7) == 0;
+  a.pcm_aligned8 = (((uintptr_t)d_pcm) & (F32IN ? 15 : 7)) == 0;
   a.neg_zero = make_float2(-0.0f, -0.0f);
   if ((rc = tir_reserve(ctx, ctx->d_counter, 256))) return rc;
   TIR_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(uint32_t), ctx->stream));
   a.tile_counter = (uint32_t *)ctx->d_counter.p;
   a.cx = cx ? *cx : TirCoefX{nullptr, 0, 0, 1, 0, nullptr, 0};
 
-  const size_t smem = sizeof(TirSmem<WIN>);
-  if (!ctx->smem_attr_set) { // per context: the attribute belongs to the device the context is on
-    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_extract_kernel<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->smem_attr_set = true;
+  const size_t smem = sizeof(TirSmem<WIN, F32IN>);
+  if (F32IN || !ctx->smem_attr_set) { // per context: the attribute belongs to the device the context is on
+    TIR_CUDA(ctx, cudaFuncSetAttribute(tir_extract_kernel<WIN, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!F32IN) ctx->smem_attr_set = true;
   }
-  const uint32_t resident = (uint32_t)ctx->num_sms * (uint32_t)C::CTAS_PER_SM;
+  const uint32_t resident = (uint32_t)ctx->num_sms * (uint32_t)(F32IN ? 1 : C::CTAS_PER_SM);
   const uint32_t grid = n_tiles < resident ? n_tiles : resident;
   if (ctx->profiling) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], ctx->stream));
-  tir_extract_kernel<WIN><<<grid, C::NT, smem, ctx->stream>>>(a, ctx->tab.mel);
+  tir_extract_kernel<WIN, F32IN><<<grid, C::NT, smem, ctx->stream>>>(a, ctx->tab.mel);
   TIR_CUDA(ctx, cudaGetLastError());
   if (ctx->profiling) {
     TIR_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], ctx->stream));
@@ -445,7 +485,15 @@ static int tir_extract_launch_t(tir_ctx *ctx, const int16_t *d_pcm, const uint64
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
                        uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames, const TirCoefX *cx) {
   (void)total_samples;
-  if (ctx->cfg.win == 512) return tir_extract_launch_t<512>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, cx);
-  if (ctx->cfg.win == 1024) return tir_extract_launch_t<1024>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, cx);
+  if (ctx->cfg.win == 512) return tir_extract_launch_t<512, false>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, cx);
+  if (ctx->cfg.win == 1024) return tir_extract_launch_t<1024, false>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, cx);
+  return tir_fail(ctx, TIR_ERR_ARG, "extraction kernels exist for win 512 / hop 256 and win 1024 / hop 512");
+}
+
+// the same from float samples (down-mixed multi-channel input * 2^15, tir_downmix_launch)
+int tir_extract_launch_f32(tir_ctx *ctx, const float *d_pcm, const uint64_t *clip_off, uint32_t n_clips, float *d_coef,
+                           int32_t *d_vq, uint64_t *n_frames) {
+  if (ctx->cfg.win == 512) return tir_extract_launch_t<512, true>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, nullptr);
+  if (ctx->cfg.win == 1024) return tir_extract_launch_t<1024, true>(ctx, d_pcm, clip_off, n_clips, d_coef, d_vq, n_frames, nullptr);
   return tir_fail(ctx, TIR_ERR_ARG, "extraction kernels exist for win 512 / hop 256 and win 1024 / hop 512");
 }

@@ -26,6 +26,8 @@
 // The float32 FFT is "TIR-FFT" (operation order documented in DESIGN.md, and restated
 // independently by the CPU oracle).
 #pragma once
+#include <type_traits>
+
 #include "tir_fp.cuh"
 
 #define TIR_MAX_FILTERS 40
@@ -81,13 +83,15 @@ struct TirCfg {
   static constexpr int CTAS_PER_SM = WIN_ == 512 ? 2 : 1;
 };
 
-template <int WIN>
+// F32IN: the PCM tile holds float samples (the down-mixed multi-channel input, already scaled by 2^15) instead of s16
+template <int WIN, bool F32IN = false>
 struct TirSmem {
   using C = TirCfg<WIN>;
+  using PcmUnit = typename std::conditional<F32IN, float4, uint2>::type; // four samples
   static constexpr int PCM_UNITS = (C::T + 1) * C::PCH;
   static constexpr int XCH_WORDS = 2 * C::N1 * 16 * 32; // [plane re/im][k1][n2][frame]
   static_assert((C::M + 1 + 16) * 32 <= XCH_WORDS, "magnitudes (+ padded mel reads) alias the exchange buffer");
-  uint2 pcm[PCM_UNITS];      // P1 is its only reader: the next tile streams in (cp.async) under P2..P3a
+  PcmUnit pcm[PCM_UNITS];    // P1 is its only reader: the next tile streams in (cp.async) under P2..P3a
   float xch[XCH_WORDS];
   float lg[2][TIR_MAX_FILTERS * 32]; // log-mel values of this and of the previous tile (P4 lags by one)
   float4 win4[16 * C::NW];   // window pairs of the two lanes, pre-scaled by 2^-15
@@ -151,15 +155,26 @@ TIR_DEV float tir_s16hi(uint32_t w) { return (float)(int16_t)(w >> 16); }
 // role w = columns n2 = 2w (lane lo) and 2w+1 (lane hi); lane f = frame of the tile.
 // z[n], n = 16*n1 + n2, is the complex point (x[2n], x[2n+1]) of the windowed, fvec_shift'ed frame:
 // sample index (2n + WIN/2) mod WIN, i.e. hop chunk f + 1 - (n1 >> 3), 32-bit word 16*(n1 & 7) + n2.
-TIR_DEV void tir_pass1_512(TirSmem<512> &sm, const uint2 *pcm, int w, int f, TirP2 nz) {
+// the four samples of unit (chunk, 8*(n1&7)+w) as (re lo, re hi, im lo, im hi) = (s0, s2, s1, s3)
+TIR_DEV void tir_unit4(const uint2 *pcm, int idx, TirP2 &re, TirP2 &im) {
+  const uint2 u = pcm[idx];
+  re = tir_pmk(tir_s16lo(u.x), tir_s16lo(u.y)), im = tir_pmk(tir_s16hi(u.x), tir_s16hi(u.y));
+}
+TIR_DEV void tir_unit4(const float4 *pcm, int idx, TirP2 &re, TirP2 &im) {
+  const float4 u = pcm[idx];
+  re = tir_pmk(u.x, u.z), im = tir_pmk(u.y, u.w);
+}
+template <class SM, class U>
+TIR_DEV void tir_pass1_512(SM &sm, const U *pcm, int w, int f, TirP2 nz) {
   using C = TirCfg<512>;
   TirC2 x[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; n1++) {
-    const uint2 u = pcm[(f + 1 - (n1 >> 3)) * C::PCH + 8 * (n1 & 7) + w];
+    TirP2 re, im;
+    tir_unit4(pcm, (f + 1 - (n1 >> 3)) * C::PCH + 8 * (n1 & 7) + w, re, im);
     const float4 wv = sm.win4[n1 * C::NW + w];
-    x[n1].r = tir_pmulx(tir_pmk(tir_s16lo(u.x), tir_s16lo(u.y)), tir_pmk(wv.x, wv.y), nz);
-    x[n1].i = tir_pmulx(tir_pmk(tir_s16hi(u.x), tir_s16hi(u.y)), tir_pmk(wv.z, wv.w), nz);
+    x[n1].r = tir_pmulx(re, tir_pmk(wv.x, wv.y), nz);
+    x[n1].i = tir_pmulx(im, tir_pmk(wv.z, wv.w), nz);
   }
   tir_dft16(x, nz);
   float *xr = sm.xch + TIR_XI(C::N1, 0, 0, 2 * w, f), *xi = sm.xch + TIR_XI(C::N1, 1, 0, 2 * w, f);
@@ -190,17 +205,28 @@ TIR_DEV void tir_pass1_512(TirSmem<512> &sm, const uint2 *pcm, int w, int f, Tir
    : (k) == 9 ? -0x1.f6297cp-1f : (k) == 10 ? -0x1.d906bcp-1f : (k) == 11 ? -0x1.a9b662p-1f                        \
    : (k) == 12 ? -0x1.6a09e6p-1f : (k) == 13 ? -0x1.1c73b4p-1f : (k) == 14 ? -0x1.87de2ap-2f : -0x1.8f8b84p-3f)
 
-TIR_DEV void tir_pass1_1024(TirSmem<1024> &sm, const uint2 *pcm, int c, int f, TirP2 nz) {
+// the two sample pairs (words idx and idx + 16 of the tile: an even and an odd n1) as (re lo, re hi), (im lo, im hi)
+TIR_DEV void tir_pair2(const uint2 *pcm, int idx, TirP2 &re, TirP2 &im) {
+  const uint32_t *p = reinterpret_cast<const uint32_t *>(pcm) + idx;
+  const uint32_t ue = p[0], uo = p[16];
+  re = tir_pmk(tir_s16lo(ue), tir_s16lo(uo)), im = tir_pmk(tir_s16hi(ue), tir_s16hi(uo));
+}
+TIR_DEV void tir_pair2(const float4 *pcm, int idx, TirP2 &re, TirP2 &im) {
+  const float2 *p = reinterpret_cast<const float2 *>(pcm) + idx;
+  const float2 ue = p[0], uo = p[16];
+  re = tir_pmk(ue.x, uo.x), im = tir_pmk(ue.y, uo.y);
+}
+template <class SM, class U>
+TIR_DEV void tir_pass1_1024(SM &sm, const U *pcm, int c, int f, TirP2 nz) {
   using C = TirCfg<1024>;
-  const uint32_t *pcm32 = reinterpret_cast<const uint32_t *>(pcm);
   TirC2 x[16];
 #pragma unroll
   for (int m = 0; m < 16; m++) {
-    const uint32_t *p = pcm32 + (f + 1 - (m >> 3)) * (2 * C::PCH) + 32 * (m & 7) + c;
-    const uint32_t ue = p[0], uo = p[16];
+    TirP2 re, im;
+    tir_pair2(pcm, (f + 1 - (m >> 3)) * (2 * C::PCH) + 32 * (m & 7) + c, re, im);
     const float4 wv = sm.win4[m * C::NW + c];
-    x[m].r = tir_pmulx(tir_pmk(tir_s16lo(ue), tir_s16lo(uo)), tir_pmk(wv.x, wv.y), nz);
-    x[m].i = tir_pmulx(tir_pmk(tir_s16hi(ue), tir_s16hi(uo)), tir_pmk(wv.z, wv.w), nz);
+    x[m].r = tir_pmulx(re, tir_pmk(wv.x, wv.y), nz);
+    x[m].i = tir_pmulx(im, tir_pmk(wv.z, wv.w), nz);
   }
   tir_dft16(x, nz); // lane lo: E[k], lane hi: O[k]
   float *xr = sm.xch + TIR_XI(C::N1, 0, 0, c, f), *xi = sm.xch + TIR_XI(C::N1, 1, 0, c, f);
@@ -233,8 +259,8 @@ struct TirPass2Regs {
   TirC2 X[16];
 };
 
-template <int WIN>
-TIR_DEV void tir_pass2_load(const TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg) {
+template <int WIN, class SM>
+TIR_DEV void tir_pass2_load(const SM &sm, int t, int f, TirPass2Regs &rg) {
   using C = TirCfg<WIN>;
   const int kA = t, kB = t ? C::N1 - t : C::N1 / 2;
   const float *ar = sm.xch + TIR_XI(C::N1, 0, kA, 0, f), *ai = sm.xch + TIR_XI(C::N1, 1, kA, 0, f);
@@ -270,8 +296,8 @@ TIR_DEV void tir_untangle_mag2(TirC2 U, TirC2 V, float4 w, TirP2 nz, TirP2 &mk, 
 //                              lane hi  k = N1/2 + N1 s      U = B[s]    V = B[15-s]   (row N1/2)
 //   (role 0, s = 7, lane lo is k = M/2 paired with itself; bins 0 and M are never produced: no mel
 //   filter has weight there)
-template <int WIN, bool T0>
-TIR_DEV void tir_pass2_compute(TirSmem<WIN> &sm, int t, int f, TirPass2Regs &rg, TirP2 nz) {
+template <int WIN, bool T0, class SM>
+TIR_DEV void tir_pass2_compute(SM &sm, int t, int f, TirPass2Regs &rg, TirP2 nz) {
   using C = TirCfg<WIN>;
   tir_dft16(rg.X, nz); // lane lo: Z[kA + N1 k2], lane hi: Z[kB + N1 k2]
   float *mags = sm.xch + f;

@@ -40,7 +40,7 @@ struct tir_ctx {
   // device copies of the kernel-layout tables
   float4 *d_win4 = nullptr, *d_twp4 = nullptr, *d_twu4 = nullptr;
   // reusable device scratch
-  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_qmeta2, d_hits, d_hits2, d_y, d_counter, d_ulaw;
+  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_qmeta2, d_hits, d_hits2, d_y, d_counter, d_ulaw, d_mix;
   // pinned staging for small metadata: a ring, so that a call does not have to wait for the previous
   // call's copy (each slot is guarded by an event recorded after the copy that reads it)
   static constexpr int kStageSlots = 4;
@@ -85,6 +85,10 @@ struct TirCoefX {
 };
 int tir_extract_launch(tir_ctx *ctx, const int16_t *d_pcm, uint64_t total_samples, const uint64_t *clip_off,
                        uint32_t n_clips, float *d_coef, int32_t *d_vq, uint64_t *n_frames, const TirCoefX *cx = nullptr);
+// multi-channel input: interleaved PCM16 -> the float mean aubio's source makes of it (* 2^15), then the same kernel on floats
+int tir_downmix_launch(tir_ctx *ctx, const int16_t *d_in, uint64_t n_frames, int channels, float *d_out);
+int tir_extract_launch_f32(tir_ctx *ctx, const float *d_pcm, const uint64_t *clip_off, uint32_t n_clips, float *d_coef,
+                           int32_t *d_vq, uint64_t *n_frames);
 size_t tir_extract_smem_bytes(int win);
 int tir_selftest_launch(tir_ctx *ctx, uint64_t *sqrt_mismatches, uint32_t first, uint32_t step, uint32_t count, float *log10f_out);
 int tir_ulaw_decode_launch(tir_ctx *ctx, const uint8_t *d_in, int16_t *d_out, uint64_t n);

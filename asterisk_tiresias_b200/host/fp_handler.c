@@ -221,7 +221,8 @@ static int16_t *read_wav_pcm16(const char *filename, uint64_t *frames, int *chan
 
 /* The hop loop of create_audio_fingerprints() (src/fp_handler.c:577-671) for one file: mfcc coefficients and the
  * "%f" micro-unit values of every frame, computed on the GPU.  Caller frees *vq.  -1 on error. */
-static int64_t fingerprint_file(const char *filename, int32_t **vq, int16_t **pcm_out, uint64_t *n_out, tir_ctx **plan_out) {
+static int64_t fingerprint_file(const char *filename, int32_t **vq, int16_t **pcm_out, uint64_t *n_out, tir_ctx **plan_out,
+                                int *channels_out) {
   uint64_t frames = 0;
   int channels = 0, rate = 0;
   int16_t *pcm = read_wav_pcm16(filename, &frames, &channels, &rate);
@@ -232,12 +233,9 @@ static int64_t fingerprint_file(const char *filename, int32_t **vq, int16_t **pc
     return -1;
   }
   if (plan_out) *plan_out = plan;
-  if (channels != 1) {
-    /* aubio averages the channels in float; tir_downmix does exactly that on the way to the device */
-    ast_log(LOG_ERROR, "Only mono PCM16 WAV files are fingerprinted. filename[%s], channels[%d]\n", filename, channels);
-    release(pcm);
-    return -1;
-  }
+  /* more than one channel: aubio's source hands the hop loop the float mean of the channels; tir_extract_interleaved
+   * computes exactly that on the device */
+  if (channels_out) *channels_out = channels;
   if (!vq) { /* the caller only wants the samples (search: extraction happens inside the batched tir_search) */
     *pcm_out = pcm, *n_out = frames;
     return (int64_t)tir_n_frames(frames, DEF_AUBIO_HOPSIZE);
@@ -246,7 +244,7 @@ static int64_t fingerprint_file(const char *filename, int32_t **vq, int16_t **pc
   const uint64_t nf = tir_n_frames(frames, DEF_AUBIO_HOPSIZE);
   *vq = ast_calloc(nf * DEF_AUBIO_COEFS + 1, sizeof(int32_t));
   uint64_t got = 0;
-  const int rc = *vq ? tir_extract(plan, pcm, off, 1, NULL, *vq, &got) : TIR_ERR_NOMEM;
+  const int rc = *vq ? tir_extract_interleaved(plan, pcm, channels, off, 1, NULL, *vq, &got) : TIR_ERR_NOMEM;
   release(pcm);
   if (rc != TIR_OK || got != nf) {
     ast_log(LOG_ERROR, "GPU extraction failed. filename[%s], err[%d:%s]\n", filename, rc, tir_last_error(plan));
@@ -437,7 +435,7 @@ bool fp_craete_audio_list_info(const char *context, const char *filename) {
    * INSERTs store, src/fp_handler.c:538-575 + src/db_ctx_handler.c:480) and into the device mirror */
   int32_t *vq = NULL;
   tir_ctx *plan = NULL;
-  const int64_t nf = fingerprint_file(filename, &vq, NULL, NULL, &plan);
+  const int64_t nf = fingerprint_file(filename, &vq, NULL, NULL, &plan, NULL);
   bool ok = nf >= 0;
   uint8_t raw[16];
   if (ok) {
@@ -484,7 +482,8 @@ struct ast_json *fp_search_fingerprint_info(const char *context, const char *fil
   int16_t *pcm = NULL;
   uint64_t n = 0;
   tir_ctx *plan = NULL;
-  if (fingerprint_file(filename, NULL, &pcm, &n, &plan) < 0) {
+  int channels = 1;
+  if (fingerprint_file(filename, NULL, &pcm, &n, &plan, &channels) < 0) {
     ast_log(LOG_ERROR, "Could not create fingerprint info.\n");
     return NULL;
   }
@@ -492,15 +491,15 @@ struct ast_json *fp_search_fingerprint_info(const char *context, const char *fil
    * (src/fp_handler.c:308-314): every context's audios compete, here too. */
   tir_hit hit;
   int rc;
-  if (plan == main_plan()) {
+  if (plan == main_plan() && channels == 1) {
     rc = tir_search_one(plan, pcm, n, coefs, tole, freq_ignore_low, freq_ignore_high, &hit); /* batched with concurrent callers */
-  } else { /* a recording at another sample rate: its own filterbank, the one table */
+  } else { /* a recording at another sample rate (its own filterbank, the one table), or one with several channels */
     const uint64_t off[2] = {0, n};
     const uint64_t nf = tir_n_frames(n, DEF_AUBIO_HOPSIZE);
     float *coef = ast_calloc(nf * DEF_AUBIO_COEFS + 1, sizeof(float));
     double *y = ast_calloc(nf * DEF_AUBIO_COEFS + 1, sizeof(double));
     uint64_t got = 0;
-    rc = (coef && y) ? tir_extract(plan, pcm, off, 1, coef, NULL, &got) : TIR_ERR_NOMEM;
+    rc = (coef && y) ? tir_extract_interleaved(plan, pcm, channels, off, 1, coef, NULL, &got) : TIR_ERR_NOMEM;
     for (uint64_t i = 0; rc == TIR_OK && i < nf * DEF_AUBIO_COEFS; i++) y[i] = 10 * log10(fabs((double)coef[i])); /* :651 */
     const uint64_t foff[2] = {0, nf};
     if (rc == TIR_OK) rc = tir_match(main_plan(), y, foff, 1, coefs, tole, freq_ignore_low, freq_ignore_high, &hit), plan = main_plan();

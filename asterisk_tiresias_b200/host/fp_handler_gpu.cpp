@@ -114,9 +114,9 @@ void unparse_uuid16(const uint8_t u[16], char out[37]) {
 }
 
 // What aubio_source delivers for the files this module sees (ast_writefile(..., "wav") recordings and
-// WAV directories): RIFF/WAVE, PCM, 16 bit.  Mono only: aubio averages channels in float, which a
-// PCM16 input cannot express -- such a file is refused rather than fingerprinted differently.
-bool read_wav_pcm16_mono(const char *filename, std::vector<int16_t> &pcm, int &rate) {
+// WAV directories): RIFF/WAVE, PCM, 16 bit.  `pcm` keeps the channels interleaved as they lie in the file: aubio's
+// source averages them in float, which tir_extract_interleaved reproduces on the device.
+bool read_wav_pcm16(const char *filename, std::vector<int16_t> &pcm, int &rate, int &channels) {
   FILE *f = fopen(filename, "rb");
   if (!f) {
     ast_log_(LOG_WARNING_, "Could not open file. filename[%s]\n", filename);
@@ -124,8 +124,8 @@ bool read_wav_pcm16_mono(const char *filename, std::vector<int16_t> &pcm, int &r
   }
   unsigned char h[12];
   bool ok = fread(h, 1, 12, f) == 12 && !memcmp(h, "RIFF", 4) && !memcmp(h + 8, "WAVE", 4);
-  int channels = 0, bits = 0, format = 0;
-  rate = 0;
+  int bits = 0, format = 0;
+  rate = 0, channels = 0;
   bool have_fmt = false, have_data = false;
   while (ok && !have_data) {
     unsigned char ch[8];
@@ -153,10 +153,11 @@ bool read_wav_pcm16_mono(const char *filename, std::vector<int16_t> &pcm, int &r
     }
   }
   fclose(f);
-  if (!ok || !have_data || format != 1 || bits != 16 || channels != 1 || rate <= 0) {
-    ast_log_(LOG_ERROR_, "Could not read the file as mono PCM16 WAV. filename[%s]\n", filename);
+  if (!ok || !have_data || format != 1 || bits != 16 || channels < 1 || channels > 64 || rate <= 0) {
+    ast_log_(LOG_ERROR_, "Could not read the file as PCM16 WAV. filename[%s]\n", filename);
     return false;
   }
+  pcm.resize(pcm.size() / (size_t)channels * (size_t)channels); // whole sample frames only
   return true;
 }
 
@@ -179,14 +180,14 @@ tir_ctx *plan_for_rate(int rate) {
 // create_audio_fingerprints(): file -> per-frame coefficients and "%f" micro-units (:577-671)
 bool create_audio_fingerprints(const char *filename, std::vector<float> &coef, std::vector<int32_t> &vq) {
   std::vector<int16_t> pcm;
-  int rate;
-  if (!read_wav_pcm16_mono(filename, pcm, rate)) return false;
+  int rate, channels;
+  if (!read_wav_pcm16(filename, pcm, rate, channels)) return false;
   tir_ctx *ctx = plan_for_rate(rate);
   if (!ctx) return false;
-  const uint64_t off[2] = {0, pcm.size()};
-  uint64_t frames = tir_n_frames(pcm.size(), 256);
+  const uint64_t off[2] = {0, pcm.size() / (size_t)channels};
+  uint64_t frames = tir_n_frames(off[1], 256);
   coef.assign(frames * 2, 0.f), vq.assign(frames * 2, 0);
-  if (tir_extract(ctx, pcm.data(), off, 1, coef.data(), vq.data(), &frames) != TIR_OK) {
+  if (tir_extract_interleaved(ctx, pcm.data(), channels, off, 1, coef.data(), vq.data(), &frames) != TIR_OK) {
     ast_log_(LOG_ERROR_, "Could not create fingerprint data. err[%s]\n", tir_last_error(ctx));
     return false;
   }
@@ -555,7 +556,7 @@ static int sync_context_locked(const fp_context_info &c) {
   struct NewAudio {
     std::string path, hash, uuid;
     std::vector<int16_t> pcm;
-    int rate;
+    int rate, channels;
   };
   std::vector<NewAudio> fresh;
   for (size_t i = 0; i < files.size(); i++) {
@@ -574,25 +575,26 @@ static int sync_context_locked(const fp_context_info &c) {
     if (!exec(fmt("insert into audio_list(uuid, name, context, hash) values ('%s', '%s', '%s', '%s');", f.uuid.c_str(),
                   basename(&tmp[0]), c.name, f.hash.c_str()).c_str()))
       continue;
-    if (!read_wav_pcm16_mono(f.path.c_str(), f.pcm, f.rate)) continue;
+    if (!read_wav_pcm16(f.path.c_str(), f.pcm, f.rate, f.channels)) continue;
     fresh.push_back(std::move(f));
   }
   int added = 0;
-  std::map<int, std::vector<size_t>> by_rate;
-  for (size_t i = 0; i < fresh.size(); i++) by_rate[fresh[i].rate].push_back(i);
+  std::map<std::pair<int, int>, std::vector<size_t>> by_rate; // one batched extraction per (rate, channel count)
+  for (size_t i = 0; i < fresh.size(); i++) by_rate[{fresh[i].rate, fresh[i].channels}].push_back(i);
   for (auto &kv : by_rate) {
-    tir_ctx *ctx = plan_for_rate(kv.first);
+    tir_ctx *ctx = plan_for_rate(kv.first.first);
     if (!ctx) continue;
+    const int channels = kv.first.second;
     std::vector<int16_t> pcm;
-    std::vector<uint64_t> off(1, 0);
+    std::vector<uint64_t> off(1, 0); // in sample frames
     for (size_t i : kv.second) {
       pcm.insert(pcm.end(), fresh[i].pcm.begin(), fresh[i].pcm.end());
-      off.push_back(pcm.size());
+      off.push_back(pcm.size() / (size_t)channels);
     }
     uint64_t frames = 0;
     for (size_t k = 0; k + 1 < off.size(); k++) frames += tir_n_frames(off[k + 1] - off[k], 256);
     std::vector<int32_t> vq(frames * 2);
-    if (tir_extract(ctx, pcm.data(), off.data(), (uint32_t)kv.second.size(), nullptr, vq.data(), &frames) != TIR_OK) {
+    if (tir_extract_interleaved(ctx, pcm.data(), channels, off.data(), (uint32_t)kv.second.size(), nullptr, vq.data(), &frames) != TIR_OK) {
       ast_log_(LOG_ERROR_, "Could not create fingerprint data. err[%s]\n", tir_last_error(ctx));
       continue;
     }

@@ -90,6 +90,15 @@ int tir_extract(tir_ctx *ctx, const int16_t *pcm, const uint64_t *clip_off, uint
 int tir_extract_ulaw(tir_ctx *ctx, const uint8_t *ulaw, const uint64_t *clip_off, uint32_t n_clips, float *coef,
                      int32_t *vq, uint64_t *n_frames);
 
+/* Same for clips with `channels` interleaved PCM16 channels (a stereo WAV's data chunk as it lies in the file):
+ * aubio_source_do (src/fp_handler.c:604,612,633) hands the module the float mean of the channels -- every
+ * sample / 32768 in float, summed in channel order from 0.f, divided by the channel count (aubio source_wavread.c /
+ * source_sndfile.c) -- reproduced on the device rounding for rounding; the hop loop then runs on those floats.
+ *   pcm       [sample frame][channel]; clip c = sample frames clip_off[c] .. clip_off[c+1]
+ * channels == 1 is tir_extract. */
+int tir_extract_interleaved(tir_ctx *ctx, const int16_t *pcm, int channels, const uint64_t *clip_off, uint32_t n_clips,
+                            float *coef, int32_t *vq, uint64_t *n_frames);
+
 /* Same with DEVICE buffers (d_pcm, d_coef, d_vq); clip_off stays a host array.  Asynchronous on
  * ctx's stream. */
 int tir_extract_dev(tir_ctx *ctx, const int16_t *d_pcm, const uint64_t *clip_off, uint32_t n_clips,

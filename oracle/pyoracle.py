@@ -53,6 +53,8 @@ def lib():
         L.tiro_quantize.argtypes = [C.c_double]
         L.tiro_extract.restype = C.c_size_t
         L.tiro_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.tiro_extract_interleaved.restype = C.c_size_t
+        L.tiro_extract_interleaved.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tiro_extract_batch.restype = C.c_size_t
         L.tiro_extract_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_int]
@@ -147,6 +149,17 @@ class Plan:
         y = np.empty((F, self.n_coefs), np.float64)
         vq = np.empty((F, self.n_coefs), np.int32)
         lib().tiro_extract(self._h, _p(pcm), pcm.size, _p(coef), _p(y), _p(vq))
+        return coef, y, vq
+
+    def extract_interleaved(self, pcm, channels):
+        """pcm[sample frame, channel] (or flat, interleaved) -> the same triple, from the channels' float mean."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        n = pcm.size // channels
+        F = self.n_frames(n)
+        coef = np.empty((F, self.n_coefs), np.float32)
+        y = np.empty((F, self.n_coefs), np.float64)
+        vq = np.empty((F, self.n_coefs), np.int32)
+        lib().tiro_extract_interleaved(self._h, _p(pcm), n, channels, _p(coef), _p(y), _p(vq))
         return coef, y, vq
 
     def extract_batch(self, pcm, clip_off, n_threads=1, want_y=True):

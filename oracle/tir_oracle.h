@@ -70,6 +70,11 @@ int32_t tiro_quantize(double y);
 size_t tiro_extract(const tiro_plan *p, const int16_t *pcm, size_t n_samples, float *coef,
                     double *y, int32_t *vq);
 
+/* the same for `channels` interleaved channels (pcm[sample frame][channel], n_samples sample frames): the hop loop
+ * runs on the float mean of the channels, as aubio's source computes it (aubio source_wavread.c) */
+size_t tiro_extract_interleaved(const tiro_plan *p, const int16_t *pcm, size_t n_samples, int channels, float *coef,
+                                double *y, int32_t *vq);
+
 /* batch over concatenated clips, clip c = pcm[clip_off[c] .. clip_off[c+1]); frames are
  * written back to back in clip order.  n_threads>1 uses pthreads (one clip per task). */
 size_t tiro_extract_batch(const tiro_plan *p, const int16_t *pcm, const uint64_t *clip_off,

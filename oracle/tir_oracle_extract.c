@@ -478,9 +478,14 @@ int32_t tiro_quantize(double y) {
   return (int32_t)v;
 }
 
-/* src/fp_handler.c:632-661 : the hop loop */
-size_t tiro_extract(const tiro_plan *p, const int16_t *pcm, size_t n_samples, float *coef,
-                    double *y, int32_t *vq) {
+/* src/fp_handler.c:632-661 : the hop loop.
+ * `channels` interleaved PCM16 channels (pcm[sample frame][channel], n_samples sample frames): aubio_source_do
+ * delivers their mean -- aubio 0.4.x source_wavread.c aubio_source_wavread_do (and source_sndfile.c
+ * aubio_source_sndfile_do the same way): each channel's sample is scaled to float first (value * 1/32768,
+ * aubio_source_wavread_readframe), the output sample starts at 0, the channels are added in order, the sum is divided
+ * by (smpl_t)input_channels. */
+size_t tiro_extract_interleaved(const tiro_plan *p, const int16_t *pcm, size_t n_samples, int channels, float *coef,
+                                double *y, int32_t *vq) {
   const int win = p->win, hop = p->hop, end = win - hop, nc = p->n_coefs;
   float data[1024], dataold[1024], hopbuf[1024], norm[513], c[40];
   memset(dataold, 0, sizeof(dataold)); /* new_aubio_pvoc: dataold = zeros */
@@ -490,7 +495,15 @@ size_t tiro_extract(const tiro_plan *p, const int16_t *pcm, size_t n_samples, fl
     size_t base = t * (size_t)hop;
     for (int i = 0; i < hop; i++) {
       size_t s = base + (size_t)i;
-      hopbuf[i] = s < n_samples ? (float)pcm[s] / 32768.f : 0.f;
+      if (s >= n_samples) {
+        hopbuf[i] = 0.f;
+      } else if (channels == 1) {
+        hopbuf[i] = (float)pcm[s] / 32768.f;
+      } else {
+        float acc = 0.f;
+        for (int ch = 0; ch < channels; ch++) acc += (float)pcm[s * (size_t)channels + (size_t)ch] / 32768.f;
+        hopbuf[i] = acc / (float)channels;
+      }
     }
     /* aubio_pvoc_swapbuffers */
     for (int i = 0; i < end; i++) data[i] = dataold[i];
@@ -506,6 +519,11 @@ size_t tiro_extract(const tiro_plan *p, const int16_t *pcm, size_t n_samples, fl
     }
   }
   return F;
+}
+
+size_t tiro_extract(const tiro_plan *p, const int16_t *pcm, size_t n_samples, float *coef,
+                    double *y, int32_t *vq) {
+  return tiro_extract_interleaved(p, pcm, n_samples, 1, coef, y, vq);
 }
 
 typedef struct {

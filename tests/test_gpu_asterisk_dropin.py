@@ -35,6 +35,9 @@ def parse_table(text, widths):
     return rows
 
 
+STEREO_TWIN = 63001
+
+
 @pytest.fixture(scope="module")
 def world(tmp_path_factory, oracle):
     from fake_asterisk.harness import FakeAsterisk
@@ -51,8 +54,19 @@ def world(tmp_path_factory, oracle):
             name = f"{ctx}_{i:02d}.wav"
             write_wav(os.path.join(d, name), pcm)
             files[(ctx, name)] = pcm
+    # two-channel files (aubio's source averages the channels in float): one with different channels, one whose channels
+    # are both the clip STEREO_TWIN -- its mean is that clip, so a mono recording of it must find this file
+    d = os.path.join(root, "audio", "st")
+    os.makedirs(d)
+    rng = np.random.default_rng(9)
+    a = synth.make_clip(63000, 5.0, SR).astype(np.int32)
+    twin = synth.make_clip(STEREO_TWIN, 4.0, SR)
+    for name, st in (("st_00.wav", np.stack([a, np.clip(a // 3 + rng.integers(-1500, 1500, a.size), -32768, 32767)], axis=1).astype(np.int16)),
+                     ("st_01.wav", np.repeat(twin[:, None], 2, axis=1))):
+        write_wav(os.path.join(d, name), st.reshape(-1), channels=2)
+        files[("st", name)] = st
     fa = FakeAsterisk(root)
-    fa.write_conf(f"[global]\ntolerance=0.01\n\n[music]\ndirectory={root}/audio/music\n\n[ivr]\ndirectory = {root}/audio/ivr ; the announcements\n")
+    fa.write_conf(f"[global]\ntolerance=0.01\n\n[music]\ndirectory={root}/audio/music\n\n[ivr]\ndirectory = {root}/audio/ivr ; the announcements\n\n[st]\ndirectory={root}/audio/st\n")
     assert fa.load() == 0, fa.log()      # AST_MODULE_LOAD_SUCCESS: fp_init + directory scan + cli_init + application_init
     return {"fa": fa, "root": root, "files": files, "oracle": oracle}
 
@@ -63,7 +77,8 @@ def oracle_db(world, listing):
     plan = po.Plan(512, 256, 40, 2, SR)
     sq = po.SqliteDB()
     for uuid, name, ctx, _ in listing:
-        _, y, _ = plan.extract(world["files"][(ctx, name)])
+        x = world["files"][(ctx, name)]
+        _, y, _ = plan.extract(x) if x.ndim == 1 else plan.extract_interleaved(x, x.shape[1])
         sq.add_audio(uuid, y, context=ctx, name=name)
     return plan, sq
 
@@ -83,8 +98,8 @@ def test_module_load_fingerprints_the_directories_and_cli_lists_them(world):
     lines = out.splitlines()
     assert lines[0] == "%-36.36s %-70.70s" % ("Name", "Directory")                # src/cli_handler.c:78
     got = sorted(tuple(r) for r in parse_table(out, (36, 70)))
-    assert got == sorted([("music", f"{world['root']}/audio/music"[:70]), ("ivr", f"{world['root']}/audio/ivr"[:70])])
-    for ctx, n in (("music", 7), ("ivr", 5)):
+    assert got == sorted([("music", f"{world['root']}/audio/music"[:70]), ("ivr", f"{world['root']}/audio/ivr"[:70]), ("st", f"{world['root']}/audio/st"[:70])])
+    for ctx, n in (("music", 7), ("ivr", 5), ("st", 2)):
         rows = listing_of(fa, ctx)
         assert len(rows) == n
         for uuid, name, c, h in rows:
@@ -96,10 +111,11 @@ def test_module_load_fingerprints_the_directories_and_cli_lists_them(world):
 
 def test_tiresias_application_sets_the_channel_variables_like_the_oracle_chain(world):
     fa = world["fa"]
-    listing = listing_of(fa, "music") + listing_of(fa, "ivr")
+    listing = listing_of(fa, "music") + listing_of(fa, "ivr") + listing_of(fa, "st")
     plan, sq = oracle_db(world, listing)
     by_uuid = {u: (n, c, h) for u, n, c, h in listing}
     cases = [
+        ("st,3000,0.3", synth.make_clip(STEREO_TWIN, 4.0, SR), 3000, 0.3, -1, -1),                 # the mean of st_01.wav's channels
         ("music,3000", world["files"][("music", "music_03.wav")], 3000, 0.01, -1, -1),            # [global] tolerance applies
         ("ivr,2000,0.05", world["files"][("ivr", "ivr_01.wav")][4000:], 2000, 0.05, -1, -1),      # argument overrides it
         ("music,1500,0.5,1,5000", synth.make_clip(424242, 3.0, SR), 1500, 0.5, 1, 5000),          # unrelated audio, wide windows, freq_ignore_*
@@ -132,7 +148,7 @@ def test_tiresias_application_sets_the_channel_variables_like_the_oracle_chain(w
 
 def test_cli_remove_and_module_reload_follow_the_oracle_chain(world):
     fa = world["fa"]
-    listing = listing_of(fa, "music") + listing_of(fa, "ivr")
+    listing = listing_of(fa, "music") + listing_of(fa, "ivr") + listing_of(fa, "st")
     plan, sq = oracle_db(world, listing)
     audio = world["files"][("music", "music_03.wav")]
     _, y, _ = plan.extract(audio[:24000])
@@ -173,8 +189,8 @@ def test_cli_remove_and_module_reload_follow_the_oracle_chain(world):
     after = listing_of(fa, "music")
     assert sorted((n, c, h) for u, n, c, h in after if (n, c) != (removed_name, removed_ctx)) == before
     assert len(after) == 7 and len(listing_of(fa, "ivr")) == 5, fa.log()[-3000:]
-    assert any((n, c) == (removed_name, removed_ctx) for u, n, c, h in after + listing_of(fa, "ivr"))
-    plan, sq = oracle_db(world, listing_of(fa, "music") + listing_of(fa, "ivr"))
+    assert any((n, c) == (removed_name, removed_ctx) for u, n, c, h in after + listing_of(fa, "ivr") + listing_of(fa, "st"))
+    plan, sq = oracle_db(world, listing_of(fa, "music") + listing_of(fa, "ivr") + listing_of(fa, "st"))
     exp = sq.search(y, 1, 0.01, has_y=np.isfinite(y))
     rc, var, _ = fa.exec_app("music,3000", audio)
     assert exp is not None and var["TIRSTATUS"] == "FOUND" and var["TIRFILEUUID"] == exp["uuid"] and var["TIRMATCHCOUNT"] == str(exp["match_count"])

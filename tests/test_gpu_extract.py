@@ -210,3 +210,43 @@ def test_bad_arguments_are_errors_not_crashes():
         capi.Context(device=0, win=300, hop=150)
     with pytest.raises(capi.TirError):
         capi.Context(device=99)
+
+
+@pytest.mark.parametrize("win,sr", [(512, 8000), (1024, 16000)])
+def test_multichannel_files_take_aubios_float_mean(oracle, win, sr):
+    """aubio_source_do hands the module the float mean of a file's channels (src/fp_handler.c:604,612,633; aubio
+    source_wavread.c): tir_extract_interleaved against the oracle's restatement of it, 2 / 3 / 5 / 8 channels, ragged and
+    empty clips, clip starts that are not multiples of four sample frames (the synchronous edge path of the loader)."""
+    from asterisk_tiresias_b200 import capi
+    ctx = capi.Context(device=0, win=win, hop=win // 2, samplerate=sr)
+    try:
+        plan = oracle.Plan(win=win, hop=win // 2, samplerate=sr)
+        rng = np.random.default_rng(win)
+        for ch in (2, 3, 5, 8):
+            lens = [sr * 2, 0, 1, win // 2 + 1, 33 * (win // 2) + 7, 40001, 3, sr + 5]
+            clips = []
+            for i, n in enumerate(lens):
+                base = synth.make_clip(900 + 10 * ch + i, max(n, 1) / sr + 0.01, samplerate=sr)[:n].astype(np.int32)
+                x = np.stack([np.clip(base // (c + 1) + rng.integers(-3000, 3000, n), -32768, 32767) for c in range(ch)], axis=1)
+                clips.append(x.astype(np.int16))
+            clips[4][100:5000] = 0                                   # silence inside a clip
+            clips[5][:, 0] = 32767; clips[5][:, 1:] = -32768         # the channels nearly cancel
+            off = np.zeros(len(lens) + 1, np.uint64); off[1:] = np.cumsum(lens)
+            pcm = np.concatenate(clips, axis=0)
+            coef, vq = ctx.extract_interleaved(pcm, ch, off)
+            oc = [], []
+            for c in clips:
+                a, _, v = plan.extract_interleaved(c, ch)
+                oc[0].append(a), oc[1].append(v)
+            check(coef, vq, np.concatenate(oc[0]), np.concatenate(oc[1]))
+        # identical channels: (x + x) / 2 is exact, so the mean is the mono file
+        mono, moff = synth.make_corpus(5, 2.0, samplerate=sr, first_index=40, ragged=True)
+        c1, v1 = ctx.extract(mono, moff)
+        c2, v2 = ctx.extract_interleaved(np.repeat(mono[:, None], 2, axis=1), 2, moff)
+        assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(v1, v2)
+        c3, v3 = ctx.extract_interleaved(mono, 1, moff)                # one channel is tir_extract
+        assert np.array_equal(c1.view(np.uint32), c3.view(np.uint32)) and np.array_equal(v1, v3)
+        with pytest.raises(capi.TirError):
+            ctx.extract_interleaved(mono[:10], 0, np.array([0, 10], np.uint64))
+    finally:
+        ctx.close()

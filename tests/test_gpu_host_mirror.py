@@ -143,13 +143,41 @@ def test_directory_sync_batches_new_files_and_drops_removed_ones(oracle, tmp_pat
         fp.fp_term()
 
 
-def test_non_mono_or_non_pcm16_files_are_refused(tmp_path):
+def test_stereo_files_are_fingerprinted_from_the_channel_mean(oracle, tmp_path):
+    """A two-channel WAV (src/fp_handler.c:604: aubio opens whatever the file is and averages the channels in float):
+    fingerprinted, stored and searched like the oracle chain run on the float mean."""
+    plan = oracle.Plan()
     assert fp.fp_init(None, 0)
     try:
-        pcm = synth.make_clip(1, 1.0)
-        fp.write_wav(str(tmp_path / "stereo.wav"), np.repeat(pcm, 2), channels=2)
+        rng = np.random.default_rng(5)
+        sq, by_uuid, files = oracle.SqliteDB(), {}, {}
+        for i in range(6):
+            l = synth.make_clip(300 + i, 3.0).astype(np.int32)
+            r = np.clip(l // 2 + rng.integers(-2000, 2000, l.size), -32768, 32767)
+            st = np.stack([l, r], axis=1).astype(np.int16)
+            name = f"st-{i}.wav"
+            fp.write_wav(str(tmp_path / name), st.reshape(-1), channels=2)
+            files[name] = st
+            assert fp.fp_craete_audio_list_info("c", str(tmp_path / name))
+        for a in fp.fp_get_audio_lists_by_contextname("c"):
+            _, y, _ = plan.extract_interleaved(files[a["name"]], 2)
+            sq.add_audio(a["uuid"], y, context="c", name=a["name"])
+            by_uuid[a["uuid"]] = a["name"]
+        for name in ("st-0.wav", "st-4.wav"):
+            for coefs, tol in ((1, 0.001), (2, 0.5)):
+                _, y, _ = plan.extract_interleaved(files[name], 2)
+                h = sq.search(y, coefs, tol, -1, -1, has_y=np.isfinite(y))
+                want = None if h is None else (h["uuid"], by_uuid[h["uuid"]], h["match_count"], h["frame_count"])
+                assert got(fp.fp_search_fingerprint_info("c", str(tmp_path / name), coefs, tol)) == want
+    finally:
+        fp.fp_term()
+
+
+def test_non_pcm16_files_are_refused(tmp_path):
+    assert fp.fp_init(None, 0)
+    try:
         open(tmp_path / "junk.wav", "wb").write(b"not a wav file at all")
-        assert not fp.fp_craete_audio_list_info("c", str(tmp_path / "stereo.wav"))
+        assert not fp.fp_craete_audio_list_info("c", str(tmp_path / "junk.wav"))
         assert fp.fp_search_fingerprint_info("c", str(tmp_path / "junk.wav")) is None
         u = fp.fp_generate_uuid()
         assert len(u) == 36 and u[14] == "4" and u.count("-") == 4

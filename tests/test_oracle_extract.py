@@ -122,3 +122,31 @@ def test_batch_equals_single(oracle):
     parts = [p.extract(pcm[int(off[i]):int(off[i + 1])]) for i in range(6)]
     assert np.array_equal(cb, np.concatenate([x[0] for x in parts]))
     assert np.array_equal(vb, np.concatenate([x[2] for x in parts]))
+
+
+def test_interleaved_channels_are_averaged_in_float32_like_aubios_source(oracle):
+    """aubio source_wavread.c: every channel sample * (1/32768) in float, summed in channel order from 0, divided by the
+    channel count -- restated here in numpy float32 and fed to the mono oracle's stages; one channel is the mono path."""
+    p = oracle.Plan()
+    rng = np.random.default_rng(11)
+    for ch in (1, 2, 3, 6):
+        x = rng.integers(-32768, 32768, (3000 + ch, ch)).astype(np.int16)
+        coef, y, vq = p.extract_interleaved(x, ch)
+        acc = np.zeros(x.shape[0], np.float32)
+        for c in range(ch):
+            acc = (acc + x[:, c].astype(np.float32) / np.float32(32768)).astype(np.float32)
+        mono = (acc / np.float32(ch)).astype(np.float32)
+        data = np.zeros(512, np.float32)
+        for t in range(coef.shape[0]):
+            hop = np.zeros(256, np.float32)
+            seg = mono[t * 256:(t + 1) * 256]
+            hop[:seg.size] = seg
+            data = np.concatenate([data[256:], hop])
+            _, c2 = p.mfcc(p.pvoc_norm(data))
+            assert np.array_equal(c2.view(np.uint32), coef[t].view(np.uint32)), (ch, t)
+    mono16 = synth.make_clip(3, 1.0)
+    a = p.extract(mono16)
+    b = p.extract_interleaved(mono16, 1)
+    c = p.extract_interleaved(np.repeat(mono16[:, None], 2, axis=1), 2)    # (x + x) / 2 is exact
+    for u, v, w in zip(a, b, c):
+        assert np.array_equal(u, v, equal_nan=True) and np.array_equal(u, w, equal_nan=True)
