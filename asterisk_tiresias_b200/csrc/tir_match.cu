@@ -523,17 +523,20 @@ __device__ __forceinline__ bool tir_frame_window(double y1, double y2, const Tir
 //     match_count(q, uuid) = sum_k weight(q, k) * [bit k of pattern(uuid)]
 // -- the same votes, the same winner and tie rule as the per-query path, for a cost that is
 // independent of the number of queries.  "Greatest rank per pattern" lives in a direct table for up
-// to TIR_SHARED_DIRECT windows (2^11 patterns; synthetic audio and most telephone speech: max1 is
-// 10*log10|c0|, a handful of integers) and in a hash table for up to TIR_MAX_SHARED windows (a batch
-// of recordings of very different loudness): the patterns that OCCUR are few, whatever their width.
+// to TIR_DIRECT_K windows (2^8 patterns; synthetic audio: max1 is 10*log10|c0|, a handful of integers) and in a
+// hash table for up to TIR_MAX_SHARED = 64 windows (telephone speech with pauses, a batch of recordings of very
+// different loudness): the patterns that OCCUR are few, whatever their width.  Beyond 8 windows the direct table
+// loses: the resolve kernel would weigh all 2^K table entries for every query.
 // Batches with more distinct windows (coefs == 2: the max2 bounds are real numbers), or more
 // occurring patterns than the hash table holds, take the per-query kernel below; the choice is made
 // on the device (TirBatch::use_general), nothing is read back.
-#define TIR_SHARED_DIRECT 11
-#define TIR_MAX_SHARED 32
-#define TIR_PAT_HASH_CTA 1024     // slots of a CTA's table (8 KB, the size of the direct table)
+#define TIR_DIRECT_K 8
+#define TIR_SHARED_DIRECT 11      // log2 of the words of a CTA's table region (8 KB: direct table, or hash keys | values)
+#define TIR_MAX_SHARED 64
+#define TIR_PAT_HASH_CTA 1024     // slots of a CTA's table
 #define TIR_PAT_HASH_GLOBAL 16384 // slots of the batch's table
-#define TIR_WSET_SLOTS 64 // window set of the batch (open addressing; > TIR_MAX_SHARED so that probes stay short)
+#define TIR_WSET_SLOTS 128 // window set of the batch (open addressing; > TIR_MAX_SHARED so that probes stay short)
+typedef unsigned long long tir_pat64;
 struct TirBatch {
   uint32_t n_distinct, use_general; // published by the last qprep CTA (use_general also by an inserter that finds the set full)
   uint32_t n_patterns; // hashed mode: occupied slots of the batch's table (listed in pat_list)
@@ -562,7 +565,7 @@ __device__ __forceinline__ unsigned long long tir_window_key(const TirWindow &w)
 }
 __device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w, bool &claimed) {
   const unsigned long long key = tir_window_key(w);
-  uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 58); // 6 bits
+  uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 57); // 7 bits
   for (int probe = 0; probe < TIR_WSET_SLOTS; probe++, h = (h + 1) & (TIR_WSET_SLOTS - 1)) {
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&batch->wkey[h]);
     if (cur == 0) {
@@ -581,7 +584,15 @@ __device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWi
   return 0;
 }
 
-__device__ __forceinline__ uint32_t tir_pat_hash(uint32_t p) { return (p * 0x9e3779b1u) >> 7; }
+// Patterns are sparse bit sets -- one to three bits, often high ones -- so the hash must carry every input bit into the
+// low bits the tables index with (a multiply alone leaves them zero for multiples of 2^17: every pattern made of windows
+// 17 and up landed in slot 0 and probed its way through the table).
+__device__ __forceinline__ uint32_t tir_pat_hash(tir_pat64 p) {
+  p ^= p >> 33;
+  p *= 0xff51afd7ed558ccdull;
+  p ^= p >> 33;
+  return (uint32_t)p ^ (uint32_t)(p >> 17);
+}
 
 
 // One CTA per query: windows of all frames, identical windows folded into one with a weight
@@ -699,14 +710,19 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x < TIR_WSET_SLOTS) { // two warps
-    const int slot = threadIdx.x, lane = slot & 31;
+  static_assert(TIR_WSET_SLOTS == TIR_QPREP_THREADS, "one thread per slot of the window set");
+  {
+    const int slot = threadIdx.x, lane = slot & 31, wid = slot >> 5;
     const bool occ = *reinterpret_cast<volatile unsigned long long *>(&batch->wkey[slot]) != 0;
     const uint32_t m = __ballot_sync(0xffffffffu, occ);
-    if (lane == 0) s_warp[slot >> 5] = __popc(m);
-    asm volatile("bar.sync 1, 64;"); // the two warps only
-    const uint32_t bit = (slot >= 32 ? s_warp[0] : 0) + __popc(m & ((1u << lane) - 1u));
-    const uint32_t K = s_warp[0] + s_warp[1];
+    __syncthreads(); // (s_warp was last read by the compaction above)
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    uint32_t bit = __popc(m & ((1u << lane) - 1u)), K = 0;
+    for (int k = 0; k < TIR_QPREP_THREADS / 32; k++) {
+      if (k < wid) bit += s_warp[k];
+      K += s_warp[k];
+    }
     if (occ) {
       batch->wbit[slot] = bit;
       if (bit < TIR_MAX_SHARED) {
@@ -725,41 +741,50 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
 
 // ================================================================================ match kernel
 
-// 32-ary search by one warp: first index in [lo,hi) with key[idx] >= target (UPPER: > target)
-template <bool UPPER>
-__device__ __forceinline__ uint64_t tir_warp_bound(const int32_t *__restrict__ key, uint64_t lo, uint64_t hi, int32_t target,
-                                                   int lane) {
-  while (hi - lo > 32) {
-    const uint64_t step = (hi - lo + 32) / 33; // 32 probes split the range in 33 parts
-    const uint64_t p = lo + (uint64_t)(lane + 1) * step - 1;
+// (G+1)-ary search by a GROUP of G lanes (G = 2 .. 32, a power of two): first index in [lo, hi) with key[idx] >= target
+// (upper: > target).  The 32 / G groups of a warp search concurrently, each for its own target, so that the 2K bounds of a
+// batch with many distinct windows are ONE chain of dependent loads per CTA instead of one per round of eight searches
+// (K = 32: 8.8 levels instead of 8 x 4.1).  Every lane of the warp calls it; groups without a search pass active = false.
+__device__ __forceinline__ uint64_t tir_group_bound(const int32_t *__restrict__ key, uint64_t lo, uint64_t hi, int32_t target,
+                                                    bool upper, int G, int lane, bool active) {
+  const int sub = lane & (G - 1), sh = lane & ~(G - 1);
+  const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+  if (!active) lo = hi = 0;
+  while (__any_sync(0xffffffffu, hi - lo > (uint64_t)G)) {
+    const bool open = hi - lo > (uint64_t)G;
+    const uint64_t step = (hi - lo + (uint64_t)G) / (uint64_t)(G + 1); // G probes split the range in G + 1 parts
+    const uint64_t p = lo + (uint64_t)(sub + 1) * step - 1;
     bool below = false;
-    if (p < hi) {
+    if (open && p < hi) {
       const int32_t k = __ldg(key + p);
-      below = UPPER ? (k <= target) : (k < target);
+      below = upper ? (k <= target) : (k < target);
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, below);
-    const int nb = __popc(m); // probes are monotone: the first nb are below
-    const uint64_t nlo = nb ? lo + (uint64_t)nb * step : lo;
-    const uint64_t nhi = (nb < 32) ? min(hi, lo + (uint64_t)(nb + 1) * step - 1 + 1) : hi;
-    lo = nlo, hi = nhi;
+    const int nb = __popc((__ballot_sync(0xffffffffu, below) >> sh) & gmask); // probes are monotone: the first nb are below
+    if (open) {
+      const uint64_t nlo = lo + (uint64_t)nb * step;
+      const uint64_t nhi = nb < G ? min(hi, lo + (uint64_t)(nb + 1) * step) : hi;
+      lo = nlo, hi = nhi;
+    }
   }
   bool below = false;
-  if (lo + lane < hi) {
-    const int32_t k = __ldg(key + lo + lane);
-    below = UPPER ? (k <= target) : (k < target);
+  if (lo + sub < hi) {
+    const int32_t k = __ldg(key + lo + sub);
+    below = upper ? (k <= target) : (k < target);
   }
-  return lo + __popc(__ballot_sync(0xffffffffu, below));
+  return lo + __popc((__ballot_sync(0xffffffffu, below) >> sh) & gmask);
 }
 
 // ---- shared-window path: kernels (TirBatch and the window set are defined above tir_qprep_kernel) ----
 // A pattern new to a hash table claims a slot with atomicCAS (0 = empty: the zero pattern is never
-// inserted); the value is the greatest rank + 1 seen with that pattern.
-__device__ __forceinline__ bool tir_pat_insert(uint32_t *keys, uint32_t *vals, uint32_t mask, uint32_t p, uint32_t rank1,
+// inserted); the value is the greatest rank + 1 seen with that pattern.  KT: 32-bit keys (a CTA's table for up to 32
+// windows) or 64-bit keys (a CTA's table beyond, and the batch's table).
+template <typename KT>
+__device__ __forceinline__ bool tir_pat_insert(KT *keys, uint32_t *vals, uint32_t mask, KT p, uint32_t rank1,
                                                uint32_t *slot_out, bool *is_new) {
-  uint32_t h = tir_pat_hash(p) & mask;
+  uint32_t h = tir_pat_hash((tir_pat64)p) & mask;
   for (uint32_t probe = 0; probe <= mask; probe++, h = (h + 1) & mask) {
-    uint32_t cur = keys[h];
-    if (cur == 0) cur = atomicCAS(&keys[h], 0u, p);
+    KT cur = keys[h];
+    if (cur == 0) cur = atomicCAS(&keys[h], (KT)0, p);
     if (cur == 0 || cur == p) {
       atomicMax(&vals[h], rank1);
       if (slot_out) *slot_out = h;
@@ -807,55 +832,73 @@ __device__ __forceinline__ void tir_exchange_release(const TirP2PArgs &x) {
 }
 
 // One CTA per index block, everything in shared memory: (1) the 2K bound searches of the K distinct
-// windows (dependent global loads: the latency of this kernel) run concurrently, one warp each;
-// (2) the rows of every window OR bit k into the block's 16 384 patterns (64 KB) -- GROUP BY
-// audio_uuid is a bit, not a count; (3) the patterns are swept into "greatest rank (+1) per pattern"
-// -- a direct table up to TIR_SHARED_DIRECT windows, an open-addressing hash table beyond (same 16 KB);
-// (4) one global atomicMax per occupied pattern (hashed: insertion into the batch's table; a pattern
-// new to it is appended to pat_list).  No per-uuid state in HBM, no global atomics per row.
+// windows (dependent global loads: the latency of this kernel) run concurrently, one group of lanes each;
+// (2) the rows of every window OR bit k into the block's patterns -- GROUP BY audio_uuid is a bit, not a
+// count; (3) the patterns are swept into "greatest rank (+1) per pattern" -- a direct table up to
+// TIR_DIRECT_K windows, an open-addressing hash table beyond; (4) one global atomicMax per occupied
+// pattern (hashed: insertion into the batch's table; a pattern new to it is appended to pat_list).  No
+// per-uuid state in HBM, no global atomics per row.
 // A hash table that fills up raises TirBatch::overflow: the per-query kernel takes the batch.
-// The pattern array is 32 KB: 16 384 patterns of 16 bits for batches of up to 16 windows, or -- for
-// 17..32 windows -- 8 192 patterns of 32 bits, the block's uuids taken in two halves (the few rows
-// are read twice).  With the 8 KB table that is 40 KB per CTA: five CTAs per SM, so that the 611
-// blocks of a 10 M-fingerprint table are ONE wave of a kernel whose duration is a chain of latencies.
+// The pattern array is 32 KB: 16 384 patterns of 16 bits for batches of up to 16 windows; for 17..32
+// windows 8 192 patterns of 32 bits, the block's uuids taken in two halves; for 33..64 windows 2 048
+// patterns of 64 bits, the uuids in eight parts (the few rows are read again for every part), the other
+// half of the array holding the 64-bit keys of the CTA's table.  With the 8 KB table that is 40 KB per
+// CTA: five CTAs per SM, so that the 611 blocks of a 10 M-fingerprint table are ONE wave of a kernel whose
+// duration is a chain of latencies.
 #define TIR_PBLOCK_SMEM (TIR_BLOCK_UUIDS * 2 + (4 << TIR_SHARED_DIRECT))
+#define TIR_PBLOCK_U64_UUIDS 2048
 
 // rows of the K windows -> patterns of uuids [uid0, uid0 + n_uuid) -> table.  PW: pattern word.
-template <int COEFS, typename PW>
+template <int COEFS, typename PW, typename KT>
 __device__ __forceinline__ void tir_pblock_pass(const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
-                                                const TirBatch *__restrict__ batch, const uint64_t (*s_range)[2], uint32_t K,
-                                                uint32_t *s_pat, uint32_t *s_tab, uint32_t *s_full, bool hashed, uint32_t uid0,
-                                                uint32_t n_uuid, uint32_t rank0, int tid, const uint8_t *__restrict__ dead) {
-  uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
+                                                const TirBatch *__restrict__ batch, const uint64_t (*s_range)[2],
+                                                const uint32_t *s_pref, uint32_t K, uint32_t *s_pat, uint32_t *s_tab, KT *s_keys, uint32_t *s_vals, uint32_t *s_full,
+                                                bool hashed, uint32_t uid0, uint32_t n_uuid, uint32_t rank0, int tid,
+                                                const uint8_t *__restrict__ dead) {
   for (uint32_t i = tid; i < n_uuid * sizeof(PW) / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_pat)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (uint32_t k = 0; k < K; k++) {
-    const uint64_t r0 = s_range[k][0], r1 = s_range[k][1];
-    int32_t lo2 = 0, hi2 = 0;
-    if (COEFS >= 2) lo2 = batch->distinct[k].lo2, hi2 = batch->distinct[k].hi2;
-    // four independent row loads in flight per thread (a window holds ~4 rows per thread: without the
-    // unrolling their latencies add up)
-    for (uint64_t r = r0 + tid; r < r1; r += 4 * TIR_MATCH_THREADS) {
-      uint32_t u[4];
-      bool ok[4];
+  // The rows of all K windows as ONE index space (s_pref[k] = rows of the windows before k): with a loop per window
+  // every window costs a global-load latency of its own -- 64 windows x 8 parts were 0.35 ms of latencies for a few
+  // thousand rows.  Four independent row loads in flight per thread; a thread's window only moves forward (one compare
+  // while it stays inside a dense window, a binary search over the prefix when it leaves one).
+  const uint32_t total = s_pref[K];
+  uint32_t kw[4] = {0, 0, 0, 0};
+  for (uint32_t i = tid; i < total; i += 4 * TIR_MATCH_THREADS) {
+    uint32_t u[4], kk[4];
+    bool ok[4];
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const uint64_t re = r + (uint64_t)e * TIR_MATCH_THREADS;
-        ok[e] = re < r1;
-        u[e] = ok[e] ? (uint32_t)__ldg(uid + re) - uid0 : 0xffffffffu;
+    for (int e = 0; e < 4; e++) {
+      const uint32_t ie = i + (uint32_t)e * TIR_MATCH_THREADS;
+      ok[e] = ie < total;
+      u[e] = 0xffffffffu, kk[e] = 0;
+      if (ok[e]) {
+        uint32_t k = kw[e];
+        if (ie >= s_pref[k + 1]) { // largest k with s_pref[k] <= ie
+          uint32_t lo = k + 1, hi = K - 1;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (s_pref[mid] <= ie) lo = mid; else hi = mid - 1;
+          }
+          k = lo;
+        }
+        kw[e] = kk[e] = k;
+        const uint64_t re = s_range[k][0] + (ie - s_pref[k]);
+        u[e] = (uint32_t)__ldg(uid + re) - uid0;
         ok[e] = u[e] < n_uuid;
         if (COEFS >= 2 && ok[e]) {
           const int32_t k2 = __ldg(key2 + re);
-          ok[e] = k2 >= lo2 && k2 <= hi2;
+          ok[e] = k2 >= batch->distinct[k].lo2 && k2 <= batch->distinct[k].hi2;
         }
       }
-#pragma unroll
-      for (int e = 0; e < 4; e++)
-        if (ok[e]) {
-          if (sizeof(PW) == 2) atomicOr(&s_pat[u[e] >> 1], (1u << k) << ((u[e] & 1) * 16)); // 32-bit atomics on the holding word
-          else atomicOr(&s_pat[u[e]], 1u << k);
-        }
     }
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+      if (ok[e]) { // 32-bit atomics on the word that holds the bit
+        const uint32_t k = kk[e];
+        if (sizeof(PW) == 2) atomicOr(&s_pat[u[e] >> 1], (1u << k) << ((u[e] & 1) * 16));
+        else if (sizeof(PW) == 4) atomicOr(&s_pat[u[e]], 1u << k);
+        else atomicOr(&s_pat[2 * u[e] + (k >> 5)], 1u << (k & 31));
+      }
   }
   __syncthreads();
   constexpr uint32_t PER16 = 16 / (uint32_t)sizeof(PW); // patterns per 16-byte load
@@ -865,12 +908,15 @@ __device__ __forceinline__ void tir_pblock_pass(const uint16_t *__restrict__ uid
     const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
     for (uint32_t e = 0; e < PER16; e++) {
-      const uint32_t pv = sizeof(PW) == 2 ? (pw[e >> 1] >> ((e & 1) * 16)) & 0xffffu : pw[e & 3];
+      KT pv;
+      if constexpr (sizeof(PW) == 2) pv = (pw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+      else if constexpr (sizeof(PW) == 4) pv = pw[e & 3];
+      else pv = ((tir_pat64)pw[(2 * e + 1) & 3] << 32) | pw[(2 * e) & 3];
       if (!pv) continue;
       const uint32_t r1v = rank0 + uid0 + PER16 * i + e;
       if (dead && dead[r1v - 1]) continue; // removed since the index was built (tir_db_remove): never a winner
-      if (!hashed) atomicMax(&s_tab[pv], r1v);
-      else if (!tir_pat_insert(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, pv, r1v, nullptr, nullptr)) *s_full = 1;
+      if (!hashed) atomicMax(&s_tab[(uint32_t)pv], r1v);
+      else if (!tir_pat_insert<KT>(s_keys, s_vals, TIR_PAT_HASH_CTA - 1, pv, r1v, nullptr, nullptr)) *s_full = 1;
     }
   }
   __syncthreads();
@@ -880,40 +926,56 @@ template <int COEFS>
 __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_pattern_block_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
                              const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
-                             TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, uint32_t *__restrict__ g_keys,
+                             TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, tir_pat64 *__restrict__ g_keys,
                              uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list, const uint8_t *__restrict__ dead) {
   TIR_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint32_t s_dyn[];
-  uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: keys | values
+  uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: 32-bit keys | values (64-bit keys: values only)
   uint32_t *s_pat = s_dyn + (1 << TIR_SHARED_DIRECT);
   uint32_t *s_keys = s_tab, *s_vals = s_tab + TIR_PAT_HASH_CTA;
+  tir_pat64 *s_keys64 = reinterpret_cast<tir_pat64 *>(s_pat + TIR_PBLOCK_U64_UUIDS * 2); // behind the 2 048 64-bit patterns
   static_assert(2 * TIR_PAT_HASH_CTA == (1 << TIR_SHARED_DIRECT), "the two uses share one table");
+  static_assert(TIR_PBLOCK_U64_UUIDS * 8 + TIR_PAT_HASH_CTA * 8 <= TIR_BLOCK_UUIDS * 2, "64-bit patterns and keys share the pattern array");
+  static_assert((1 << TIR_DIRECT_K) <= (1 << TIR_SHARED_DIRECT), "direct table");
   __shared__ uint64_t s_range[TIR_MAX_SHARED][2];
+  __shared__ uint32_t s_pref[TIR_MAX_SHARED + 1];
   __shared__ uint32_t s_full;
   const uint32_t blk = blockIdx.x;
   const uint32_t K = batch->n_distinct;
   if (batch->use_general || K == 0) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const uint64_t bs = block_start[blk], be = block_start[blk + 1];
   if (bs == be) return;
-  const bool hashed = K > TIR_SHARED_DIRECT;
+  const bool hashed = K > TIR_DIRECT_K;
   for (int i = tid; i < (4 << TIR_SHARED_DIRECT) / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_tab)[i] = make_uint4(0, 0, 0, 0);
+  if (K > 32)
+    for (int i = tid; i < TIR_PAT_HASH_CTA * 8 / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_keys64)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) s_full = 0;
-  for (uint32_t j = warp; j < 2 * K; j += TIR_MATCH_THREADS / 32) {
-    const TirWindow w = batch->distinct[j >> 1];
-    const uint64_t r = (j & 1) ? tir_warp_bound<true>(key1, bs, be, w.hi1, lane) : tir_warp_bound<false>(key1, bs, be, w.lo1, lane);
-    if (lane == 0) s_range[j >> 1][j & 1] = r;
+  { // all 2K bounds at once: groups of G lanes, 256 / G >= 2K
+    const int G = K <= 4 ? 32 : K <= 8 ? 16 : K <= 16 ? 8 : K <= 32 ? 4 : 2;
+    const uint32_t j = (uint32_t)tid / (uint32_t)G;
+    const bool active = j < 2 * K;
+    const TirWindow w = batch->distinct[active ? (j >> 1) : 0];
+    const uint64_t r = tir_group_bound(key1, bs, be, (j & 1) ? w.hi1 : w.lo1, (j & 1) != 0, G, lane, active);
+    if (active && (tid & (G - 1)) == 0) s_range[j >> 1][j & 1] = r;
   }
   __syncthreads();
-  bool any = false;
-  for (uint32_t k = 0; k < K; k++) any |= s_range[k][1] > s_range[k][0];
-  if (!any) return; // (CTA-uniform) no row of this block lies in any window
+  if (tid == 0) { // (a block holds fewer than 2^32 rows: 16 384 audios)
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < K; k++) s_pref[k] = acc, acc += (uint32_t)(s_range[k][1] - s_range[k][0]);
+    s_pref[K] = acc;
+  }
+  __syncthreads();
+  if (s_pref[K] == 0) return; // (CTA-uniform) no row of this block lies in any window
   const uint32_t rank0 = blk * TIR_BLOCK_UUIDS + 1;
   if (K <= 16) {
-    tir_pblock_pass<COEFS, uint16_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid, dead);
+    tir_pblock_pass<COEFS, uint16_t, uint32_t>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys, s_vals, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid, dead);
+  } else if (K <= 32) {
+    for (uint32_t u0 = 0; u0 < TIR_BLOCK_UUIDS; u0 += TIR_BLOCK_UUIDS / 2)
+      tir_pblock_pass<COEFS, uint32_t, uint32_t>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys, s_vals, &s_full, hashed, u0, TIR_BLOCK_UUIDS / 2, rank0, tid, dead);
   } else {
-    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, 0, TIR_BLOCK_UUIDS / 2, rank0, tid, dead);
-    tir_pblock_pass<COEFS, uint32_t>(uid, key2, batch, s_range, K, s_pat, s_tab, &s_full, hashed, TIR_BLOCK_UUIDS / 2, TIR_BLOCK_UUIDS / 2, rank0, tid, dead);
+    for (uint32_t u0 = 0; u0 < TIR_BLOCK_UUIDS; u0 += TIR_PBLOCK_U64_UUIDS)
+      tir_pblock_pass<COEFS, tir_pat64, tir_pat64>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys64, s_tab, &s_full, hashed, u0, TIR_PBLOCK_U64_UUIDS, rank0, tid, dead);
   }
   if (!hashed) {
     const uint32_t np = 1u << K;
@@ -923,11 +985,11 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   }
   bool full = s_full != 0;
   for (uint32_t i = tid; i < TIR_PAT_HASH_CTA && !full; i += TIR_MATCH_THREADS) {
-    const uint32_t p = s_keys[i];
+    const tir_pat64 p = K > 32 ? s_keys64[i] : (tir_pat64)s_keys[i];
     if (!p) continue;
     uint32_t slot;
     bool is_new;
-    if (!tir_pat_insert(g_keys, g_vals, TIR_PAT_HASH_GLOBAL - 1, p, s_vals[i], &slot, &is_new)) full = true;
+    if (!tir_pat_insert<tir_pat64>(g_keys, g_vals, TIR_PAT_HASH_GLOBAL - 1, p, K > 32 ? s_tab[i] : s_vals[i], &slot, &is_new)) full = true;
     else if (is_new) {
       const uint32_t at = atomicAdd(&batch->n_patterns, 1u);
       if (at < TIR_PAT_HASH_GLOBAL / 2) pat_list[at] = slot;
@@ -937,62 +999,73 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   if (full) atomicExch(&batch->overflow, 1u); // the per-query kernel (launched after the resolve) takes the batch
 }
 
-// one warp per query: weigh the occupied patterns (direct: every table index; hashed: pat_list)
-__global__ void tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
-                                           const uint64_t *__restrict__ frame_off, uint32_t n_queries,
-                                           TirBatch *__restrict__ batch, const uint32_t *__restrict__ max_rank1,
-                                           const uint32_t *__restrict__ g_keys, const uint32_t *__restrict__ g_vals,
-                                           const uint32_t *__restrict__ pat_list, const uint32_t *__restrict__ order,
-                                           const uint8_t *__restrict__ uuids, tir_hit *__restrict__ hits, const TirP2PArgs x) {
+// one warp per query: weigh the occupied patterns (direct: every table index; hashed: pat_list).  The weights of the
+// query's windows sit in shared memory, indexed by pattern bit; a pattern's score is summed over its SET bits (one to
+// three, typically), not over all K.
+#define TIR_RESOLVE_THREADS 256
+__global__ void __launch_bounds__(TIR_RESOLVE_THREADS)
+    tir_pattern_resolve_kernel(const TirWindow *__restrict__ windows, const uint32_t *__restrict__ n_windows,
+                               const uint64_t *__restrict__ frame_off, uint32_t n_queries, TirBatch *__restrict__ batch,
+                               const uint32_t *__restrict__ max_rank1, const tir_pat64 *__restrict__ g_keys,
+                               const uint32_t *__restrict__ g_vals, const uint32_t *__restrict__ pat_list,
+                               const uint32_t *__restrict__ order, const uint8_t *__restrict__ uuids, tir_hit *__restrict__ hits,
+                               const TirP2PArgs x) {
   TIR_PDL_PROLOGUE();
   // (CTA-uniform decision: overflow can be raised while this kernel runs, and the CTA meets at a barrier below)
   __shared__ uint32_t s_general, s_last;
+  __shared__ uint32_t s_w[TIR_RESOLVE_THREADS / 32][TIR_MAX_SHARED];
   if (threadIdx.x == 0) s_general = batch->use_general | *reinterpret_cast<volatile uint32_t *>(&batch->overflow);
   __syncthreads();
   if (s_general) return; // the per-query kernel produces (and exchanges) the hits
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q < n_queries) {
   const uint32_t K = batch->n_distinct, nw = n_windows[q];
-  const bool hashed = K > TIR_SHARED_DIRECT;
+  const bool hashed = K > TIR_DIRECT_K;
   const TirWindow *wq = windows + frame_off[q];
+  uint32_t *wk = s_w[threadIdx.x >> 5]; // wk[k] = weight(q, k)
+  wk[lane] = 0, wk[lane + 32] = 0;
+  __syncwarp();
   // lane i takes window i (32 at a time): window -> slot -> bit -> the window that bit stands for are
   // three dependent loads, paid once per 32 windows instead of once per window
-  uint32_t wk = 0; // lane k holds weight(q, k)
   for (uint32_t i0 = 0; i0 < nw; i0 += 32) {
-    uint32_t bit = 0xffffffffu, weight = 0;
     if (i0 + lane < nw) {
       const TirWindow w = wq[i0 + lane];
-      bit = batch->wbit[w.pad]; // .pad: slot in the batch's window set
-      weight = w.weight;
-      const TirWindow d = batch->distinct[bit];
-      if (d.lo1 != w.lo1 || d.hi1 != w.hi1 || d.lo2 != w.lo2 || d.hi2 != w.hi2)
+      const uint32_t bit = batch->wbit[w.pad]; // .pad: slot in the batch's window set
+      const TirWindow d = batch->distinct[bit < TIR_MAX_SHARED ? bit : 0];
+      if (bit >= TIR_MAX_SHARED || d.lo1 != w.lo1 || d.hi1 != w.hi1 || d.lo2 != w.lo2 || d.hi2 != w.hi2)
         atomicExch(&batch->overflow, 1u); // two windows behind one 64-bit key
-    }
-    const uint32_t n = min(32u, nw - i0);
-    for (uint32_t i = 0; i < n; i++) {
-      const uint32_t b = __shfl_sync(0xffffffffu, bit, i), wg = __shfl_sync(0xffffffffu, weight, i);
-      if (b == lane) wk += wg;
+      else
+        atomicAdd(&wk[bit], w.weight);
     }
   }
+  __syncwarp();
   unsigned long long bestv = 0;
   const uint32_t np = hashed ? batch->n_patterns : (K ? (1u << K) : 0);
-  for (uint32_t p0 = 0; p0 < np; p0 += 32) {
-    const uint32_t i = p0 + lane;
-    uint32_t p = i, r1 = 0;
-    if (i < np) {
-      if (hashed) {
-        const uint32_t slot = __ldg(pat_list + i);
-        p = g_keys[slot], r1 = g_vals[slot];
-      } else {
-        r1 = __ldg(max_rank1 + i);
+  // four chunks of 32 patterns per iteration: the loads (list -> slot -> key, value: two dependent levels) of all four
+  // are in flight before the first score is summed
+  for (uint32_t p0 = 0; p0 < np; p0 += 128) {
+    tir_pat64 p[4];
+    uint32_t r1[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const uint32_t i = p0 + 32 * e + lane;
+      p[e] = i, r1[e] = 0;
+      if (i < np) {
+        if (hashed) {
+          const uint32_t slot = __ldg(pat_list + i);
+          p[e] = g_keys[slot], r1[e] = g_vals[slot];
+        } else {
+          r1[e] = __ldg(max_rank1 + i);
+        }
       }
     }
-    uint32_t score = 0;
-    for (uint32_t k = 0; k < K; k++) {
-      const uint32_t w = __shfl_sync(0xffffffffu, wk, k);
-      if ((p >> k) & 1u) score += w;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      uint32_t score = 0;
+      if (r1[e])
+        for (tir_pat64 b = p[e]; b; b &= b - 1) score += wk[__ffsll((long long)b) - 1];
+      if (r1[e] && score) bestv = max(bestv, ((unsigned long long)score << 32) | (unsigned long long)(r1[e] - 1));
     }
-    if (r1 && score) bestv = max(bestv, ((unsigned long long)score << 32) | (unsigned long long)(r1 - 1));
   }
   for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
   if (lane == 0) tir_write_hit(bestv, order, uuids, frame_off, q, hits, x); // (the per-query kernel rewrites it if it runs)
@@ -1185,7 +1258,7 @@ static TirMatchScratch match_scratch_layout(uint32_t n_queries, uint64_t F) {
   L.o_foff = 0, L.o_nw = L.o_foff + ((size_t)n_queries + 1) * 8, L.o_best = (L.o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
   L.o_batch = (L.o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
   L.o_maxr = (L.o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
-  L.o_gkeys = L.o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), L.o_gvals = L.o_gkeys + (size_t)4 * TIR_PAT_HASH_GLOBAL;
+  L.o_gkeys = L.o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), L.o_gvals = L.o_gkeys + (size_t)8 * TIR_PAT_HASH_GLOBAL;
   L.o_plist = L.o_gvals + (size_t)4 * TIR_PAT_HASH_GLOBAL; // (first bytes that need no clearing)
   L.o_win = L.o_plist + (size_t)4 * TIR_PAT_HASH_GLOBAL;
   L.bytes = L.o_win + std::max<uint64_t>(F, 1) * sizeof(TirWindow);
@@ -1258,7 +1331,8 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
   unsigned long long *d_best = (unsigned long long *)(d + o_best);
   TirBatch *d_batch = (TirBatch *)(d + o_batch);
-  uint32_t *d_maxr = (uint32_t *)(d + o_maxr), *d_gkeys = (uint32_t *)(d + o_gkeys), *d_gvals = (uint32_t *)(d + o_gvals);
+  uint32_t *d_maxr = (uint32_t *)(d + o_maxr), *d_gvals = (uint32_t *)(d + o_gvals);
+  tir_pat64 *d_gkeys = (tir_pat64 *)(d + o_gkeys);
   uint32_t *d_plist = (uint32_t *)(d + o_plist);
   TirWindow *d_win = (TirWindow *)(d + o_win);
   if (d_coef)
@@ -1277,9 +1351,9 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     const dim3 pgrid(idx.n_blocks), pthr(TIR_MATCH_THREADS);
     if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
     else TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
-    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + 255) / 256), dim3(256), st, (const TirWindow *)d_win,
+    TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + TIR_RESOLVE_THREADS - 1) / TIR_RESOLVE_THREADS), dim3(TIR_RESOLVE_THREADS), st, (const TirWindow *)d_win,
                                  (const uint32_t *)d_nw, d_foff, n_queries, d_batch, (const uint32_t *)d_maxr,
-                                 (const uint32_t *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, order, uuids, d_hits, x));
+                                 (const tir_pat64 *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, order, uuids, d_hits, x));
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)idx.n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);

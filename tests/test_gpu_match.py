@@ -88,16 +88,21 @@ def test_shared_window_and_per_query_paths_agree(gpu_ctx, oracle):
     ys.append(db[17][1].copy())
     ys.append(np.zeros((0, 2)))
     foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    ints = {int(v) for y in ys for v in np.trunc(y[:, 0])}
+    assert 33 <= len(ints) <= 64, len(ints)      # coefs = 1: the batch runs on 64-bit patterns, every single on the direct table
+    decoy = np.stack([np.arange(80) - 30 + 0.5, np.zeros(80)], axis=1)          # 80 more windows: the per-query kernel
+    foff_d = np.concatenate([foff, [foff[-1] + 80]]).astype(np.uint64)
     for coefs, tol in ((1, 0.001), (1, 0.02), (2, 1.5)):
         batch = gpu_ctx.match(np.concatenate(ys), foff, coefs, tol)
+        general = gpu_ctx.match(np.concatenate(ys + [decoy]), foff_d, coefs, tol)
         for qi, y in enumerate(ys):
             single = gpu_ctx.match(y, None, coefs, tol)[0] if y.shape[0] else batch[qi]
-            assert gpu_result(single) == gpu_result(batch[qi]), (coefs, tol, qi)
+            assert gpu_result(single) == gpu_result(batch[qi]) == gpu_result(general[qi]), (coefs, tol, qi)
             if qi % 3 == 0 and y.shape[0]:
                 assert gpu_result(batch[qi]) == sql_result(sq.search(y, coefs, tol, has_y=np.isfinite(y))), (coefs, tol, qi)
-    # the table boundaries: 11 distinct windows (direct pattern table), 12..16 (hashed, 16-bit patterns),
-    # 17..32 (hashed, 32-bit patterns), 33 (per-query)
-    for n_int in (11, 12, 16, 17, 32, 33):
+    # the table boundaries: 8 distinct windows (direct pattern table), 9..16 (hashed, 16-bit patterns),
+    # 17..32 (32-bit patterns, the block's uuids in halves), 33..64 (64-bit patterns, in eighths), 65 (per-query)
+    for n_int in (8, 9, 11, 12, 16, 17, 32, 33, 48, 64, 65, 70):
         y = np.stack([np.arange(n_int) - 5 + 0.2, np.zeros(n_int)], axis=1)
         h = gpu_ctx.match(y, None, 1, 0.3)[0]
         assert gpu_result(h) == sql_result(sq.search(y, 1, 0.3)), n_int
@@ -182,9 +187,10 @@ def test_very_long_queries_and_far_values(gpu_ctx, oracle):
         sq.add_audio(u, y)
     gpu_ctx.db_load(*synth_db.db_arrays(db))
     n_long = 70_000
-    y_long = np.stack([rng.integers(10, 60, n_long) + rng.uniform(0.0, 0.9, n_long), np.full(n_long, 3.0)], axis=1)   # 50 distinct windows: per-query path
+    y_long = np.stack([rng.integers(10, 60, n_long) + rng.uniform(0.0, 0.9, n_long), np.full(n_long, 3.0)], axis=1)   # 50 distinct windows
     y_far = np.array([[600.7, 0.0], [-700.2, 0.0], [15.5, 0.0], [600.1, 0.0], [2000.0, 0.0]])
-    ys = [y_long, y_far, db[2][1]]
+    y_wide = np.stack([np.arange(-20, 80) + 0.25, np.full(100, 3.0)], axis=1)   # 100 more: the batch takes the per-query kernel (u32 counters)
+    ys = [y_long, y_far, db[2][1], y_wide]
     foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
     for coefs, tol in ((1, 0.001), (2, 0.5)):
         hits = gpu_ctx.match(np.concatenate(ys), foff, coefs, tol)
@@ -365,7 +371,7 @@ def test_shard_merge_equals_unsharded(gpu_ctx, oracle):
 def test_one_million_fingerprints_both_paths_and_brute_force(gpu_ctx):
     """BASELINE config[2] at its full size (1 M fingerprints x 94 frames, generated on the device): the
     SQLite oracle cannot ingest that in a test, so (i) the shared-window path (one batched call) and the
-    per-query path (a batch widened past 12 distinct windows by a decoy query) must agree on every
+    per-query path (a batch widened past 64 distinct windows by a decoy query) must agree on every
     query, (ii) a brute-force restatement of the vote in torch confirms sampled queries, (iii) sharding
     the same table four ways and merging gives the same winners."""
     import torch
@@ -382,8 +388,8 @@ def test_one_million_fingerprints_both_paths_and_brute_force(gpu_ctx):
     y[:8, :, 0] = (v1.view(n, F)[:8].cpu().numpy() * 1e-6)                     # stored entries as queries
     foff = np.arange(Q + 1, dtype=np.uint64) * F
     shared = gpu_ctx.match(y.reshape(-1, 2), foff, 1, 0.001)
-    decoy = np.stack([np.arange(40) - 20.0, np.zeros(40)], axis=1)              # 40 more distinct windows -> per-query path
-    foff2 = np.concatenate([foff, [foff[-1] + 40]]).astype(np.uint64)
+    decoy = np.stack([np.arange(90) - 45.0, np.zeros(90)], axis=1)              # 89 more distinct windows -> per-query path
+    foff2 = np.concatenate([foff, [foff[-1] + 90]]).astype(np.uint64)
     general = gpu_ctx.match(np.concatenate([y.reshape(-1, 2), decoy]), foff2, 1, 0.001)[:Q]
     assert np.array_equal(shared["match_count"], general["match_count"]) and np.array_equal(shared["uuid"], general["uuid"])
     assert (shared["frame_count"] == F).all() and (shared["match_count"] > 0).all()
