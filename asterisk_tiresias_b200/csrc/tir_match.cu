@@ -854,51 +854,82 @@ __device__ __forceinline__ void tir_pblock_pass(const uint16_t *__restrict__ uid
                                                 const TirBatch *__restrict__ batch, const uint64_t (*s_range)[2],
                                                 const uint32_t *s_pref, uint32_t K, uint32_t *s_pat, uint32_t *s_tab, KT *s_keys, uint32_t *s_vals, uint32_t *s_full,
                                                 bool hashed, uint32_t uid0, uint32_t n_uuid, uint32_t rank0, int tid,
-                                                const uint8_t *__restrict__ dead) {
+                                                const uint8_t *__restrict__ dead, uint32_t flat_max) {
   for (uint32_t i = tid; i < n_uuid * sizeof(PW) / 16; i += TIR_MATCH_THREADS) reinterpret_cast<uint4 *>(s_pat)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  // The rows of all K windows as ONE index space (s_pref[k] = rows of the windows before k): with a loop per window
-  // every window costs a global-load latency of its own -- 64 windows x 8 parts were 0.35 ms of latencies for a few
-  // thousand rows.  Four independent row loads in flight per thread; a thread's window only moves forward (one compare
-  // while it stays inside a dense window, a binary search over the prefix when it leaves one).
+  auto set_bit = [&](uint32_t u, uint32_t k) { // 32-bit atomics on the word that holds the bit
+    if (sizeof(PW) == 2) atomicOr(&s_pat[u >> 1], (1u << k) << ((u & 1) * 16));
+    else if (sizeof(PW) == 4) atomicOr(&s_pat[u], 1u << k);
+    else atomicOr(&s_pat[2 * u + (k >> 5)], 1u << (k & 31));
+  };
   const uint32_t total = s_pref[K];
-  uint32_t kw[4] = {0, 0, 0, 0};
-  for (uint32_t i = tid; i < total; i += 4 * TIR_MATCH_THREADS) {
-    uint32_t u[4], kk[4];
-    bool ok[4];
+  constexpr int UF = 8; // row loads in flight per thread
+  if (total <= flat_max * K) {
+    // Few rows per window (many distinct windows at a narrow tolerance; measured: below ~512 rows per window and block):
+    // the rows of all K windows as ONE index space
+    // (s_pref[k] = rows of the windows before k).  With a loop per window every window costs a global-load latency of
+    // its own -- 64 windows x 8 parts were 0.35 ms of latencies for a few thousand rows.  A thread's window only moves
+    // forward (one compare while it stays inside a window, a binary search over the prefix when it leaves one).
+    uint32_t kw[UF];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const uint32_t ie = i + (uint32_t)e * TIR_MATCH_THREADS;
-      ok[e] = ie < total;
-      u[e] = 0xffffffffu, kk[e] = 0;
-      if (ok[e]) {
-        uint32_t k = kw[e];
-        if (ie >= s_pref[k + 1]) { // largest k with s_pref[k] <= ie
-          uint32_t lo = k + 1, hi = K - 1;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (s_pref[mid] <= ie) lo = mid; else hi = mid - 1;
+    for (int e = 0; e < UF; e++) kw[e] = 0;
+    for (uint32_t i = tid; i < total; i += UF * TIR_MATCH_THREADS) {
+      uint32_t u[UF];
+      bool ok[UF];
+#pragma unroll
+      for (int e = 0; e < UF; e++) {
+        const uint32_t ie = i + (uint32_t)e * TIR_MATCH_THREADS;
+        ok[e] = ie < total;
+        u[e] = 0xffffffffu;
+        if (ok[e]) {
+          uint32_t k = kw[e];
+          if (ie >= s_pref[k + 1]) { // largest k with s_pref[k] <= ie
+            uint32_t lo = k + 1, hi = K - 1;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi + 1) >> 1;
+              if (s_pref[mid] <= ie) lo = mid; else hi = mid - 1;
+            }
+            k = lo;
           }
-          k = lo;
+          kw[e] = k;
+          const uint64_t re = s_range[k][0] + (ie - s_pref[k]);
+          u[e] = (uint32_t)__ldg(uid + re) - uid0;
+          ok[e] = u[e] < n_uuid;
+          if (COEFS >= 2 && ok[e]) {
+            const int32_t k2 = __ldg(key2 + re);
+            ok[e] = k2 >= batch->distinct[k].lo2 && k2 <= batch->distinct[k].hi2;
+          }
         }
-        kw[e] = kk[e] = k;
-        const uint64_t re = s_range[k][0] + (ie - s_pref[k]);
-        u[e] = (uint32_t)__ldg(uid + re) - uid0;
-        ok[e] = u[e] < n_uuid;
-        if (COEFS >= 2 && ok[e]) {
-          const int32_t k2 = __ldg(key2 + re);
-          ok[e] = k2 >= batch->distinct[k].lo2 && k2 <= batch->distinct[k].hi2;
+      }
+#pragma unroll
+      for (int e = 0; e < UF; e++)
+        if (ok[e]) set_bit(u[e], kw[e]);
+    }
+  } else {
+    // dense windows (wide tolerances): a streaming loop per window, four row loads in flight per thread
+    for (uint32_t k = 0; k < K; k++) {
+      const uint64_t r0 = s_range[k][0], r1 = s_range[k][1];
+      int32_t lo2 = 0, hi2 = 0;
+      if (COEFS >= 2) lo2 = batch->distinct[k].lo2, hi2 = batch->distinct[k].hi2;
+      for (uint64_t r = r0 + tid; r < r1; r += 4 * TIR_MATCH_THREADS) {
+        uint32_t u[4];
+        bool ok[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const uint64_t re = r + (uint64_t)e * TIR_MATCH_THREADS;
+          ok[e] = re < r1;
+          u[e] = ok[e] ? (uint32_t)__ldg(uid + re) - uid0 : 0xffffffffu;
+          ok[e] = u[e] < n_uuid;
+          if (COEFS >= 2 && ok[e]) {
+            const int32_t k2 = __ldg(key2 + re);
+            ok[e] = k2 >= lo2 && k2 <= hi2;
+          }
         }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (ok[e]) set_bit(u[e], k);
       }
     }
-#pragma unroll
-    for (int e = 0; e < 4; e++)
-      if (ok[e]) { // 32-bit atomics on the word that holds the bit
-        const uint32_t k = kk[e];
-        if (sizeof(PW) == 2) atomicOr(&s_pat[u[e] >> 1], (1u << k) << ((u[e] & 1) * 16));
-        else if (sizeof(PW) == 4) atomicOr(&s_pat[u[e]], 1u << k);
-        else atomicOr(&s_pat[2 * u[e] + (k >> 5)], 1u << (k & 31));
-      }
   }
   __syncthreads();
   constexpr uint32_t PER16 = 16 / (uint32_t)sizeof(PW); // patterns per 16-byte load
@@ -927,7 +958,8 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
     tir_pattern_block_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid,
                              const int32_t *__restrict__ key2, const uint64_t *__restrict__ block_start,
                              TirBatch *__restrict__ batch, uint32_t *__restrict__ max_rank1, tir_pat64 *__restrict__ g_keys,
-                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list, const uint8_t *__restrict__ dead) {
+                             uint32_t *__restrict__ g_vals, uint32_t *__restrict__ pat_list, const uint8_t *__restrict__ dead,
+                             uint32_t flat_max) {
   TIR_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_tab = s_dyn; // direct: max rank by pattern; hashed: 32-bit keys | values (64-bit keys: values only)
@@ -969,13 +1001,13 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   if (s_pref[K] == 0) return; // (CTA-uniform) no row of this block lies in any window
   const uint32_t rank0 = blk * TIR_BLOCK_UUIDS + 1;
   if (K <= 16) {
-    tir_pblock_pass<COEFS, uint16_t, uint32_t>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys, s_vals, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid, dead);
+    tir_pblock_pass<COEFS, uint16_t, uint32_t>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys, s_vals, &s_full, hashed, 0, TIR_BLOCK_UUIDS, rank0, tid, dead, flat_max);
   } else if (K <= 32) {
     for (uint32_t u0 = 0; u0 < TIR_BLOCK_UUIDS; u0 += TIR_BLOCK_UUIDS / 2)
-      tir_pblock_pass<COEFS, uint32_t, uint32_t>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys, s_vals, &s_full, hashed, u0, TIR_BLOCK_UUIDS / 2, rank0, tid, dead);
+      tir_pblock_pass<COEFS, uint32_t, uint32_t>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys, s_vals, &s_full, hashed, u0, TIR_BLOCK_UUIDS / 2, rank0, tid, dead, flat_max);
   } else {
     for (uint32_t u0 = 0; u0 < TIR_BLOCK_UUIDS; u0 += TIR_PBLOCK_U64_UUIDS)
-      tir_pblock_pass<COEFS, tir_pat64, tir_pat64>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys64, s_tab, &s_full, hashed, u0, TIR_PBLOCK_U64_UUIDS, rank0, tid, dead);
+      tir_pblock_pass<COEFS, tir_pat64, tir_pat64>(uid, key2, batch, s_range, s_pref, K, s_pat, s_tab, s_keys64, s_tab, &s_full, hashed, u0, TIR_PBLOCK_U64_UUIDS, rank0, tid, dead, flat_max);
   }
   if (!hashed) {
     const uint32_t np = 1u << K;
@@ -1349,8 +1381,12 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     if (ctx->profiling && !in_graph) TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     // shared-window path (no-ops when the batch has too many distinct windows) ...
     const dim3 pgrid(idx.n_blocks), pthr(TIR_MATCH_THREADS);
-    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
-    else TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead));
+    static const uint32_t flat_max = [] { // rows per window of a block up to which the windows are swept as one index space
+      const char *e = getenv("TIR_PBLOCK_FLAT_ROWS"); // (tuning knob; 4 windows x 1 000 rows: 37.5 us per window, 49.9 us flat;
+      return e ? (uint32_t)strtoul(e, nullptr, 10) : 512u; //  64 windows x 50 rows: 473 us per window, 315 us flat)
+    }();
+    if (coefs >= 2) TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<2>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead, flat_max));
+    else TIR_CUDA(ctx, tir_launch_pdl_smem(tir_pattern_block_kernel<1>, pgrid, pthr, TIR_PBLOCK_SMEM, st, k1, uid, k2, bst, d_batch, d_maxr, d_gkeys, d_gvals, d_plist, dead, flat_max));
     TIR_CUDA(ctx, tir_launch_pdl(tir_pattern_resolve_kernel, dim3((n_queries * 32 + TIR_RESOLVE_THREADS - 1) / TIR_RESOLVE_THREADS), dim3(TIR_RESOLVE_THREADS), st, (const TirWindow *)d_win,
                                  (const uint32_t *)d_nw, d_foff, n_queries, d_batch, (const uint32_t *)d_maxr,
                                  (const tir_pat64 *)d_gkeys, (const uint32_t *)d_gvals, (const uint32_t *)d_plist, order, uuids, d_hits, x));

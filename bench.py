@@ -390,21 +390,22 @@ def match_bench(ctx, args, rank, world, device, dist):
             else:
                 exchange = "tir_p2p (NVLink peer stores + flags, folded in the last CTA of the match chain; no collective call)"
 
-    def step(coefs=1, nq=Q, use_p2p=True, tol=0.001):
+    def step(coefs=1, nq=Q, use_p2p=True, tol=0.001, cf=None):
+        cf = coef if cf is None else cf
         if p2p is not None and use_p2p:
-            p2p.match_dev(coef.data_ptr(), foff[: nq + 1], d_final.data_ptr(), coefs, tol)
+            p2p.match_dev(cf.data_ptr(), foff[: nq + 1], d_final.data_ptr(), coefs, tol)
             return
-        ctx.match_dev(coef.data_ptr(), foff[: nq + 1], d_hits.data_ptr(), coefs, tol)
+        ctx.match_dev(cf.data_ptr(), foff[: nq + 1], d_hits.data_ptr(), coefs, tol)
         if world > 1:
             dist.all_gather_into_tensor(d_gather[: world * nq * 24], d_hits[: nq * 24])
             ctx.merge_hits_dev(d_gather.data_ptr(), world, nq, d_final.data_ptr())
         # (one GPU: the shard's winners are the answer, nothing to merge)
 
-    def timed(coefs, nq, steps, use_p2p=True, tol=0.001):
+    def timed(coefs, nq, steps, use_p2p=True, tol=0.001, cf=None):
         # warm-up: a steady caller's chain is captured into a CUDA graph once its key has been seen twice on each of the
         # four staging slots (4 plain calls, 4 captures), replays from then on
         for _ in range(12):
-            step(coefs, nq, use_p2p, tol)
+            step(coefs, nq, use_p2p, tol, cf)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -412,7 +413,7 @@ def match_bench(ctx, args, rank, world, device, dist):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(coefs, nq, use_p2p, tol)
+            step(coefs, nq, use_p2p, tol, cf)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -451,6 +452,20 @@ def match_bench(ctx, args, rank, world, device, dist):
         bt, ut = _global_winners(*bf.winners_coefs1(qv, T), world, dist)
         sweep[str(tol)] = {"value": Q / (ms_t * 1e-3), "unit": "queries/s", "ms_per_batch": ms_t, "kernel_ms_rank0": k_t,
                            "verified_queries": _compare(result(), bt, ut, F_q)}
+    # a batch of recordings of very different loudness: every query keeps its frames, shifted by a whole number of dB so that
+    # the batch's frames take 64 distinct integer values of max1 -- 64 distinct windows, the most the shared-window path
+    # holds (64-bit patterns); one window more and the batch takes the per-query kernel
+    shift = (torch.arange(Q, device=device, dtype=torch.float64) % 16) * 4.0 - 35.0      # 16 shifts x 4 integers = 64 values
+    shift[: Q // 5] = 0.0                                                                # the copies keep their level
+    qv_w = qv + shift[:, None]
+    coef_w = torch.stack([torch.pow(10.0, qv_w / 10.0).float(), coef[:, :, 1]], dim=2).contiguous()
+    qv_w = 10.0 * torch.log10(coef_w[:, :, 0].double())
+    n_win_w = int(torch.unique(torch.trunc(qv_w).to(torch.int64)).numel())
+    ms_w, k_w, _ = timed(1, Q, max(args.steps, 20), cf=coef_w)
+    bw, uw = _global_winners(*bf.winners_coefs1(qv_w, 1000), world, dist)
+    many_windows = {"value": Q / (ms_w * 1e-3), "unit": "queries/s", "ms_per_batch": ms_w, "kernel_ms_rank0": k_w,
+                    "distinct_windows": n_win_w, "verified_queries": _compare(result(), bw, uw, F_q),
+                    "note": "shared-window path on 64-bit patterns (33..64 distinct windows); round 1: the per-query kernel from 33 windows on"}
     # honest roofline of the shared-window path: the bytes the algorithm must move per BATCH on this rank
     # (every distinct window's rows once: 2 B uid each, one 16 B range header per window and index block,
     # the coefficients in and the hits out) over the chain time
@@ -481,7 +496,7 @@ def match_bench(ctx, args, rank, world, device, dist):
            "verified_queries": verified, "verification": "torch brute force over every stored row of every rank, all queries (bench.py BruteForce)",
            "per_query_path_coefs2": {"value": nq2 / (ms2 * 1e-3), "unit": "queries/s", "ms_per_batch": ms2, "queries_per_batch": nq2,
                                      "kernel_ms_rank0": k_ms2, "coefs": 2, "tolerance": 0.001, "verified_queries": verified2},
-           "tolerance_sweep": sweep, "self_matches_top": int((hits["match_count"][: Q // 10] > 0).sum()),
+           "tolerance_sweep": sweep, "many_distinct_windows": many_windows, "self_matches_top": int((hits["match_count"][: Q // 10] > 0).sum()),
            "search_e2e": search_e2e, "cpu_baseline": cpu_match, "roofline": roofline}
     del bf, uu, v1, v2
     torch.cuda.empty_cache()
@@ -972,6 +987,7 @@ def main():
                 "coefs2_qps": match["per_query_path_coefs2"]["value"], "coefs2_verified": v(match["per_query_path_coefs2"]["verified_queries"]),
                 "tol_0.01_qps": match["tolerance_sweep"]["0.01"]["value"], "tol_0.01_verified": v(match["tolerance_sweep"]["0.01"]["verified_queries"]),
                 "tol_0.05_qps": match["tolerance_sweep"]["0.05"]["value"], "tol_0.05_verified": v(match["tolerance_sweep"]["0.05"]["verified_queries"]),
+                "win64_qps": match["many_distinct_windows"]["value"], "win64_verified": v(match["many_distinct_windows"]["verified_queries"]),
                 "search_e2e_qps": match["search_e2e"]["value"], "search_e2e_verified": v(match["search_e2e"]["verified_queries"]),
                 "db938_qps": (match.get("db_938_frames") or {}).get("value"), "db938_verified": v((match.get("db_938_frames") or {}).get("verified_queries")),
             }
