@@ -147,7 +147,7 @@ void tir_close(tir_ctx *ctx) {
   if (ctx->db) tir_db_destroy(ctx->db);
   cudaFree(ctx->d_win4), cudaFree(ctx->d_twp4), cudaFree(ctx->d_twu4);
   free_dev(ctx->d_clipmeta), free_dev(ctx->d_tilemeta), free_dev(ctx->d_pcm), free_dev(ctx->d_coef);
-  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_qmeta2), free_dev(ctx->d_hits), free_dev(ctx->d_hits2), free_dev(ctx->d_y), free_dev(ctx->d_counter), free_dev(ctx->d_ulaw), free_dev(ctx->d_mix);
+  free_dev(ctx->d_vq), free_dev(ctx->d_qmeta), free_dev(ctx->d_qmeta2), free_dev(ctx->d_hits), free_dev(ctx->d_hits2), free_dev(ctx->d_y), free_dev(ctx->d_counter), free_dev(ctx->d_ulaw), free_dev(ctx->d_mix), free_dev(ctx->d_items);
   for (int k = 0; k < tir_ctx::kStageSlots; k++) {
     if (ctx->h_stage[k].p) cudaFreeHost(ctx->h_stage[k].p);
     if (ctx->h_stage_ev[k]) cudaEventDestroy(ctx->h_stage_ev[k]);

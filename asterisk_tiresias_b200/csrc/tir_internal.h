@@ -40,7 +40,7 @@ struct tir_ctx {
   // device copies of the kernel-layout tables
   float4 *d_win4 = nullptr, *d_twp4 = nullptr, *d_twu4 = nullptr;
   // reusable device scratch
-  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_qmeta2, d_hits, d_hits2, d_y, d_counter, d_ulaw, d_mix;
+  DevBuf d_clipmeta, d_tilemeta, d_pcm, d_coef, d_vq, d_qmeta, d_qmeta2, d_hits, d_hits2, d_y, d_counter, d_ulaw, d_mix, d_items;
   // pinned staging for small metadata: a ring, so that a call does not have to wait for the previous
   // call's copy (each slot is guarded by an event recorded after the copy that reads it)
   static constexpr int kStageSlots = 4;

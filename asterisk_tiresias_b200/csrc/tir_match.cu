@@ -541,7 +541,7 @@ struct TirBatch {
   uint32_t n_distinct, use_general; // published by the last qprep CTA (use_general also by an inserter that finds the set full)
   uint32_t n_patterns; // hashed mode: occupied slots of the batch's table (listed in pat_list)
   uint32_t overflow;   // a pattern table filled up, or two windows shared a 64-bit key -> per-query path
-  uint32_t done, done_general, pad_[2];    // qprep CTAs / per-query CTAs that have finished
+  uint32_t done, done_general, n_ovf, pad_; // qprep CTAs / per-query CTAs that have finished; items tir_match2_kernel left over
   unsigned long long wkey[TIR_WSET_SLOTS]; // 0 = free, else the 64-bit key of the window that claimed the slot
   TirWindow wfull[TIR_WSET_SLOTS];         // ... and the window itself (written by the claimer)
   uint32_t wbit[TIR_WSET_SLOTS];           // slot -> bit of the window in the patterns
@@ -564,6 +564,8 @@ __device__ __forceinline__ unsigned long long tir_window_key(const TirWindow &w)
   return k ? k : 1ull;
 }
 __device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w, bool &claimed) {
+  // (a set that overflowed stays overflowed: coefs == 2 batches would otherwise probe all its slots for every frame)
+  if (*reinterpret_cast<volatile uint32_t *>(&batch->use_general)) return 0;
   const unsigned long long key = tir_window_key(w);
   uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> 57); // 7 bits
   for (int probe = 0; probe < TIR_WSET_SLOTS; probe++, h = (h + 1) & (TIR_WSET_SLOTS - 1)) {
@@ -608,6 +610,18 @@ __device__ __forceinline__ uint32_t tir_pat_hash(tir_pat64 p) {
 #define TIR_QPREP_THREADS 128
 #define TIR_QPREP_BINS 1024 // trunc(max1) in [-512, 512): every value 10*log10|float| can take, and then some
 
+#define TIR_QPREP_SORT_MAX TIR_QPREP_THREADS // coefs == 2 queries of up to this many windows leave qprep sorted
+__device__ __forceinline__ bool tir_window_open2(int32_t lo2, int32_t hi2) { return lo2 == INT32_MIN && hi2 == INT32_MAX; }
+__device__ __forceinline__ int tir_window_cmp(const TirWindow &a, const TirWindow &b) {
+  if (a.lo1 != b.lo1) return a.lo1 < b.lo1 ? -1 : 1;
+  if (a.hi1 != b.hi1) return a.hi1 < b.hi1 ? -1 : 1;
+  const int oa = tir_window_open2(a.lo2, a.hi2), ob = tir_window_open2(b.lo2, b.hi2);
+  if (oa != ob) return oa < ob ? -1 : 1;
+  if (a.lo2 != b.lo2) return a.lo2 < b.lo2 ? -1 : 1;
+  if (a.hi2 != b.hi2) return a.hi2 < b.hi2 ? -1 : 1;
+  return 0;
+}
+
 template <bool FROM_COEF>
 __global__ void __launch_bounds__(TIR_QPREP_THREADS)
     tir_qprep_kernel(const double *__restrict__ y, const float *__restrict__ coef, const uint64_t *__restrict__ frame_off,
@@ -621,6 +635,7 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
   __shared__ uint32_t s_hist[TIR_QPREP_BINS];
   __shared__ uint16_t s_lead[TIR_QPREP_BINS];
   __shared__ uint32_t s_warp[TIR_QPREP_THREADS / 32], s_base, s_nlead, s_last;
+  __shared__ TirWindow s_sort[TIR_QPREP_SORT_MAX];
   for (int i = threadIdx.x; i < TIR_QPREP_BINS; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x == 0) s_base = 0, s_nlead = 0;
   __syncthreads();
@@ -698,6 +713,24 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
         s_base = t;
       }
       __syncthreads();
+    }
+    // Short queries (what a dialplan recording is): the windows sorted by (max1 window, "no predicate on max2", lo2, hi2),
+    // so that the per-query kernel finds the frames of one max1 window side by side and, inside such a group, both
+    // bounds ascending (lo2 = q(v2 - tol) and hi2 = q(v2 + tol) are monotone in v2): the frames a row matches are then a
+    // contiguous range.  A rank sort in shared memory; the votes do not depend on the order.
+    const uint32_t n = s_base;
+    if (n > 1 && n <= TIR_QPREP_SORT_MAX) {
+      if (threadIdx.x < n) s_sort[threadIdx.x] = wq[threadIdx.x];
+      __syncthreads();
+      if (threadIdx.x < n) {
+        const TirWindow mine = s_sort[threadIdx.x];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) {
+          const int c = tir_window_cmp(s_sort[j], mine);
+          rank += (c < 0 || (c == 0 && j < threadIdx.x)) ? 1u : 0u;
+        }
+        wq[rank] = mine;
+      }
     }
   }
   __syncthreads();
@@ -1127,6 +1160,8 @@ __global__ void __launch_bounds__(TIR_RESOLVE_THREADS)
 // in flight per lane (uid, 2 B/row; key2 too for coefs == 2); a warp clears its bitmap only after a
 // window that voted.
 #define TIR_GEN_CHUNK 128
+#define TIR_M2_MAX_FRAMES 96 // coefs == 2 fast path: windows of a query (frame positions fit three mask words / 7 bits)
+#define TIR_M2_CAND 1024     // ... and the matching rows of one (index block, query) item it keeps
 // WIDE: u32 counters (64 KB) for batches that hold a query of more than 65 535 frames -- a u16 counter
 // could wrap (35 min of audio at 8 kHz / hop 256, but only 6 min at 44.1 kHz)
 #define TIR_GEN_SMEM_OF(wide) (TIR_BLOCK_UUIDS * ((wide) ? 4 : 2) + (TIR_MATCH_THREADS / 32) * (TIR_BLOCK_UUIDS / 8))
@@ -1147,7 +1182,8 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
                      TirBatch *__restrict__ batch, const uint32_t *__restrict__ order, const uint8_t *__restrict__ uuids,
-                     tir_hit *__restrict__ hits, const TirP2PArgs x, const uint8_t *__restrict__ dead) {
+                     tir_hit *__restrict__ hits, const TirP2PArgs x, const uint8_t *__restrict__ dead,
+                     const uint64_t *__restrict__ item_list) {
   TIR_PDL_PROLOGUE();
   if (!(batch->use_general || batch->overflow)) return;
   extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word (WIDE: u32); then the warps' bitmaps
@@ -1158,8 +1194,10 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   __shared__ unsigned long long s_best[TIR_MATCH_THREADS / 32];
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t n_items = (uint64_t)n_blocks * n_queries;
-  for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+  // item_list: tir_match2_kernel ran before this kernel and left only the items it could not finish (batch->n_ovf of them)
+  const uint64_t n_items = item_list ? (uint64_t)batch->n_ovf : (uint64_t)n_blocks * n_queries;
+  for (uint64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const uint64_t item = item_list ? item_list[it] : it;
     const uint32_t blk = (uint32_t)(item % n_blocks), q = (uint32_t)(item / n_blocks);
     const uint64_t bs = block_start[blk], be = block_start[blk + 1];
     const uint32_t nw = n_windows[q];
@@ -1250,6 +1288,268 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
   }
 }
 
+// ---- per-query path, coefs == 2, short queries: ROW-major -------------------------------------------------------
+// The frame-major kernel above reads the rows of a max1 window once per FRAME that has it (94 frames over 4 integer
+// values of max1: every row 24 times, 250 MB per query against 10 M fingerprints).  A query of at most 96 windows leaves
+// tir_qprep_kernel SORTED by (max1 window, "no predicate on max2", lo2, hi2), so the frames of one max1 window are a
+// GROUP with both max2 bounds ascending.  Per (index block, query) item: one pair of bound searches per group, every row
+// read once, the frames it matches found by two binary searches over the group's lo2 / hi2 (a contiguous range of
+// frames), and only the rows that match anything (a handful at narrow tolerances) are kept, as (uuid, first frame,
+// last frame).  Sorted by uuid, the union of a uuid's frame ranges is its vote count -- one vote per frame and uuid, as
+// GROUP BY audio_uuid asks.  Small CTAs and 13 KB of shared memory: sixteen items in flight per SM hide the item's chain
+// of dependent loads.  An item with more candidates than the list holds (wide tolerances) or a longer query goes to
+// item_list: the frame-major kernel, next in the chain, works that list off.
+#define TIR_M2_THREADS 128 // four warps, each on its own unit
+#define TIR_M2_GROUPS 32   // max1 windows of a query this kernel handles
+#define TIR_M2_FGROUPS 8   // groups that get a max2 occupancy bitmap (1 024 bins each); further groups are not filtered
+struct TirM2Warp { // one warp's shared memory (6.6 KB)
+  uint32_t cand[TIR_M2_CAND];                                  // uid << 16 | first << 8 | last
+  int32_t qv[256];                                             // rows of one sweep step that passed the filter: max2 ...
+  uint32_t qk[256];                                            // ... and uid
+  int32_t lo2[TIR_M2_MAX_FRAMES], hi2[TIR_M2_MAX_FRAMES];      // the query's max2 bounds, sorted inside every group
+  int32_t gl1[TIR_M2_GROUPS], gh1[TIR_M2_GROUPS];              // max1 window of a group
+  uint32_t gstart[TIR_M2_GROUPS + 1], pref[TIR_M2_GROUPS + 1]; // first window of a group / rows of the block before it
+  uint64_t range[TIR_M2_GROUPS][2];
+  // which max2 values can match a frame of the group at all: a bitmap over [fbase, fbase + fspan] in bins of 2^fshift
+  // micro-units; at narrow tolerances it rejects ~95 % of the rows before the binary searches
+  uint32_t fbm[TIR_M2_FGROUPS][32];
+  int32_t fbase[TIR_M2_FGROUPS];
+  uint32_t fspan[TIR_M2_FGROUPS], fshift[TIR_M2_FGROUPS], fon[TIR_M2_FGROUPS];
+  uint32_t gopen; // bit g: the group's frames have no predicate on max2
+  uint32_t ncand;
+};
+__global__ void __launch_bounds__(TIR_M2_THREADS, 8)
+    tir_match2_kernel(const int32_t *__restrict__ key1, const uint16_t *__restrict__ uid, const int32_t *__restrict__ key2,
+                      const uint64_t *__restrict__ block_start, const TirWindow *__restrict__ windows,
+                      const uint32_t *__restrict__ n_windows, const uint64_t *__restrict__ frame_off,
+                      unsigned long long *__restrict__ best, uint32_t n_blocks, uint32_t n_queries,
+                      TirBatch *__restrict__ batch, const uint8_t *__restrict__ dead, uint64_t *__restrict__ item_list) {
+  TIR_PDL_PROLOGUE();
+  if (!(batch->use_general || batch->overflow)) return;
+  __shared__ TirM2Warp s_all[TIR_M2_THREADS / 32];
+  const int lane = threadIdx.x & 31;
+  TirM2Warp &S = s_all[threadIdx.x >> 5];
+  // unit of work of a WARP: one query x a range of index blocks (the query's set-up -- windows, groups, filters -- is paid
+  // once per unit; no CTA barrier anywhere: an SM keeps 32 independent chains of dependent loads in flight)
+  const uint64_t n_warps = (uint64_t)gridDim.x * (TIR_M2_THREADS / 32), me = (uint64_t)blockIdx.x * (TIR_M2_THREADS / 32) + (threadIdx.x >> 5);
+  const uint32_t parts = (uint32_t)max((uint64_t)1, min((uint64_t)n_blocks, n_warps / n_queries));
+  const uint32_t bpp = (n_blocks + parts - 1) / parts;
+  const uint64_t n_units = (uint64_t)n_queries * parts;
+  for (uint64_t unit = me; unit < n_units; unit += n_warps) {
+    const uint32_t q = (uint32_t)(unit / parts), b0 = (uint32_t)(unit % parts) * bpp, b1 = min(n_blocks, b0 + bpp);
+    const uint32_t nw = n_windows[q];
+    if (nw == 0 || b0 >= b1) continue;
+    const TirWindow *wq = windows + frame_off[q];
+    __syncwarp();
+    // the query's windows (sorted by tir_qprep_kernel) -> groups of equal (max1 window, open)
+    uint32_t ng = 0, my_g[3] = {0, 0, 0};
+    int32_t c_l1 = 0, c_h1 = 0; // last window of the previous chunk of 32
+    bool c_open = false;
+    if (nw <= TIR_M2_MAX_FRAMES) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const uint32_t i = 32u * c + lane;
+        const bool valid = i < nw;
+        TirWindow w;
+        w.lo1 = w.hi1 = w.lo2 = w.hi2 = 0;
+        if (valid) w = wq[i], S.lo2[i] = w.lo2, S.hi2[i] = w.hi2;
+        const bool open = tir_window_open2(w.lo2, w.hi2);
+        int32_t p_l1 = __shfl_up_sync(0xffffffffu, w.lo1, 1), p_h1 = __shfl_up_sync(0xffffffffu, w.hi1, 1);
+        bool p_open = __shfl_up_sync(0xffffffffu, (int)open, 1) != 0;
+        if (lane == 0) p_l1 = c_l1, p_h1 = c_h1, p_open = c_open;
+        const bool flag = valid && (i == 0 || w.lo1 != p_l1 || w.hi1 != p_h1 || open != p_open);
+        const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+        const uint32_t g = ng + __popc(bal & ((2u << lane) - 1u)) - 1u;
+        my_g[c] = g;
+        if (flag && g < TIR_M2_GROUPS) S.gstart[g] = i, S.gl1[g] = w.lo1, S.gh1[g] = w.hi1;
+        ng += __popc(bal);
+        c_l1 = __shfl_sync(0xffffffffu, w.lo1, 31), c_h1 = __shfl_sync(0xffffffffu, w.hi1, 31);
+        c_open = __shfl_sync(0xffffffffu, (int)open, 31) != 0;
+      }
+    }
+    if (nw > TIR_M2_MAX_FRAMES || ng > TIR_M2_GROUPS) { // (warp-uniform) a longer query (not sorted) or too many max1 windows
+      for (uint32_t blk = b0 + lane; blk < b1; blk += 32)
+        if (block_start[blk] != block_start[blk + 1]) item_list[atomicAdd(&batch->n_ovf, 1u)] = (uint64_t)q * n_blocks + blk;
+      continue;
+    }
+    if (lane == 0) S.gstart[ng] = nw;
+    for (int i = lane; i < TIR_M2_FGROUPS * 32; i += 32) (&S.fbm[0][0])[i] = 0;
+    __syncwarp();
+    {
+      bool open = false;
+      if ((uint32_t)lane < ng) open = tir_window_open2(S.lo2[S.gstart[lane]], S.hi2[S.gstart[lane]]);
+      const uint32_t ob = __ballot_sync(0xffffffffu, open);
+      if (lane == 0) S.gopen = ob;
+      if ((uint32_t)lane < ng && lane < TIR_M2_FGROUPS) { // the group's max2 span (bounds ascend inside a group)
+        const uint32_t gs = S.gstart[lane], ge = S.gstart[lane + 1];
+        const uint32_t span = (uint32_t)S.hi2[ge - 1] - (uint32_t)S.lo2[gs]; // hi >= lo: fits 32 bits
+        uint32_t sh = 0;
+        while ((span >> sh) >= 1024u) sh++;
+        S.fbase[lane] = S.lo2[gs], S.fspan[lane] = span, S.fshift[lane] = sh, S.fon[lane] = open ? 0u : 1u;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t i = 32u * c + lane, g = my_g[c];
+      if (i < nw && g < TIR_M2_FGROUPS && S.fon[g]) {
+        const uint32_t f0 = ((uint32_t)S.lo2[i] - (uint32_t)S.fbase[g]) >> S.fshift[g];
+        const uint32_t f1 = ((uint32_t)S.hi2[i] - (uint32_t)S.fbase[g]) >> S.fshift[g];
+        if (f1 - f0 >= 64u) S.fon[g] = 0u; // a wide tolerance: the filter would reject little (benign race: only ever cleared)
+        else
+          for (uint32_t f = f0; f <= f1; f++) atomicOr(&S.fbm[g][f >> 5], 1u << (f & 31));
+      }
+    }
+    __syncwarp();
+    const uint32_t gopen = S.gopen;
+    unsigned long long qbest = 0;
+    for (uint32_t blk = b0; blk < b1; blk++) {
+      const uint64_t bs = block_start[blk], be = block_start[blk + 1];
+      if (bs == be) continue;
+      { // the groups' bounds: G lanes per search, the searches of a round concurrently
+        const int G = 2 * ng <= 8 ? 4 : 2;
+        for (uint32_t j0 = 0; j0 < 2 * ng; j0 += 32u / G) {
+          const uint32_t j = j0 + (uint32_t)lane / (uint32_t)G;
+          const bool active = j < 2 * ng;
+          const uint32_t g = active ? (j >> 1) : 0;
+          const uint64_t r = tir_group_bound(key1, bs, be, (j & 1) ? S.gh1[g] : S.gl1[g], (j & 1) != 0, G, lane, active);
+          if (active && (lane & (G - 1)) == 0) S.range[g][j & 1] = r;
+        }
+      }
+      if (lane == 0) S.ncand = 0;
+      __syncwarp();
+      uint32_t total;
+      { // rows before every group
+        uint32_t n = (uint32_t)lane < ng ? (uint32_t)(S.range[lane][1] - S.range[lane][0]) : 0u, incl = n;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if ((uint32_t)lane < ng) S.pref[lane] = incl - n;
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) S.pref[ng] = total;
+      }
+      __syncwarp();
+      if (total == 0) continue; // no row of this block in any of the query's max1 windows
+      // Group by group (32 warps per SM hide a group's load latency; the kernel is bound by instructions per row, so the
+      // group's constants stay in registers): eight row pairs (uuid, max2) in flight per lane, the filter, then the rows
+      // that pass it (a few per cent at narrow tolerances) are compacted so that the binary searches run with every
+      // lane on a survivor instead of once per unrolled slot for the one or two lanes that have one.
+      constexpr int UF = 8;
+      for (uint32_t g = 0; g < ng && S.ncand <= TIR_M2_CAND; g++) {
+        const uint64_t r0 = S.range[g][0], r1 = S.range[g][1];
+        if (r0 == r1) continue;
+        const uint32_t gs = S.gstart[g], cnt = S.gstart[g + 1] - gs;
+        const bool open = ((gopen >> g) & 1u) != 0;
+        const bool filt = g < TIR_M2_FGROUPS && S.fon[g] != 0;
+        const int32_t fbase = filt ? S.fbase[g] : 0;
+        const uint32_t fspan = filt ? S.fspan[g] : 0, fshift = filt ? S.fshift[g] : 0;
+        const uint32_t *fbm = S.fbm[filt ? g : 0];
+        for (uint64_t rr = r0; rr < r1; rr += UF * 32) { // (warp-uniform trip count: the body votes)
+          uint32_t u[UF];
+          int32_t v[UF];
+          bool ok[UF];
+#pragma unroll
+          for (int e = 0; e < UF; e++) {
+            const uint64_t re = rr + (uint32_t)(32 * e + lane);
+            ok[e] = re < r1;
+            u[e] = 0, v[e] = 0;
+            if (ok[e]) u[e] = (uint32_t)__ldg(uid + re), v[e] = __ldg(key2 + re);
+          }
+          uint32_t nq = 0;
+#pragma unroll
+          for (int e = 0; e < UF; e++) {
+            bool pass = ok[e];
+            if (filt && pass) { // can this max2 match any frame of the group?
+              const uint32_t d = (uint32_t)v[e] - (uint32_t)fbase;
+              pass = v[e] >= fbase && d <= fspan;
+              if (pass) {
+                const uint32_t f = d >> fshift;
+                pass = ((fbm[f >> 5] >> (f & 31)) & 1u) != 0;
+              }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+              const uint32_t at = nq + __popc(bal & ((1u << lane) - 1u));
+              S.qv[at] = v[e], S.qk[at] = u[e];
+            }
+            nq += __popc(bal);
+          }
+          __syncwarp();
+          for (uint32_t j = lane; j < nq; j += 32) {
+            const int32_t vv = S.qv[j];
+            uint32_t a = 0, b = cnt; // frames [a, b) of the group hold the row's max2
+            if (!open) {
+              uint32_t lo = 0, hi = cnt; // first frame with hi2 >= v
+              while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.hi2[gs + mid] < vv) lo = mid + 1; else hi = mid;
+              }
+              a = lo, hi = cnt; // first frame with lo2 > v (not before a: lo2 <= hi2)
+              while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.lo2[gs + mid] <= vv) lo = mid + 1; else hi = mid;
+              }
+              b = lo;
+            }
+            if (a < b) {
+              const uint32_t at = atomicAdd(&S.ncand, 1u);
+              if (at < TIR_M2_CAND) S.cand[at] = (S.qk[j] << 16) | ((gs + a) << 8) | (gs + b - 1);
+            }
+          }
+          __syncwarp();
+          if (S.ncand > TIR_M2_CAND) break; // (warp-uniform) the item goes to the frame-major kernel anyway
+        }
+      }
+      __syncwarp();
+      const uint32_t ncand = S.ncand;
+      if (ncand == 0) continue;
+      if (ncand > TIR_M2_CAND) { // too many matching rows (a wide tolerance): the frame-major kernel takes the item
+        if (lane == 0) item_list[atomicAdd(&batch->n_ovf, 1u)] = (uint64_t)q * n_blocks + blk;
+        continue;
+      }
+      uint32_t n2 = 32;
+      while (n2 < ncand) n2 <<= 1;
+      for (uint32_t i = ncand + lane; i < n2; i += 32) S.cand[i] = 0xffffffffu;
+      __syncwarp();
+      for (uint32_t size = 2; size <= n2; size <<= 1) // bitonic sort, ascending: by uuid first
+        for (uint32_t stride = size >> 1; stride; stride >>= 1) {
+          for (uint32_t t = lane; t < n2 / 2; t += 32) {
+            const uint32_t lo_i = 2 * t - (t & (stride - 1)), hi_i = lo_i + stride;
+            const uint32_t x0 = S.cand[lo_i], x1 = S.cand[hi_i];
+            const bool up = (lo_i & size) == 0;
+            if ((x0 > x1) == up) S.cand[lo_i] = x1, S.cand[hi_i] = x0;
+          }
+          __syncwarp();
+        }
+      unsigned long long bestv = 0;
+      for (uint32_t i = lane; i < ncand; i += 32) {
+        const uint32_t id = S.cand[i] >> 16;
+        if (i && (S.cand[i - 1] >> 16) == id) continue; // not the first row of its uuid
+        uint32_t m0 = 0, m1 = 0, m2 = 0;
+        for (uint32_t j = i; j < ncand && (S.cand[j] >> 16) == id; j++) {
+          const int fa = (int)((S.cand[j] >> 8) & 0xffu), fb = (int)(S.cand[j] & 0xffu); // positions in the sorted query
+#pragma unroll
+          for (int wd = 0; wd < 3; wd++) {
+            const int lo_b = max(fa - 32 * wd, 0), hi_b = min(fb - 32 * wd, 31);
+            if (lo_b <= hi_b) {
+              const uint32_t m = (hi_b == 31 ? 0xffffffffu : ((2u << hi_b) - 1u)) & ~((1u << lo_b) - 1u);
+              if (wd == 0) m0 |= m; else if (wd == 1) m1 |= m; else m2 |= m;
+            }
+          }
+        }
+        const uint64_t rk = (uint64_t)blk * TIR_BLOCK_UUIDS + id;
+        const uint32_t votes = __popc(m0) + __popc(m1) + __popc(m2);
+        if (votes && !(dead && dead[rk])) bestv = max(bestv, ((unsigned long long)votes << 32) | rk);
+      }
+      for (int o = 16; o; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
+      qbest = max(qbest, bestv);
+      __syncwarp();
+    } // blocks of the unit
+    if (lane == 0 && qbest) atomicMax(best + q, qbest);
+  }
+}
+
 // empty table: every query gets {no uuid, 0, frame_count}
 __global__ void tir_no_hits_kernel(const uint64_t *__restrict__ frame_off, uint32_t n_queries, tir_hit *__restrict__ hits) {
   TIR_PDL_PROLOGUE();
@@ -1314,6 +1614,10 @@ int tir_search_reserve(tir_ctx *ctx, uint32_t n_queries, uint64_t F, uint64_t n_
   if ((rc = tir_reserve(ctx, ctx->d_clipmeta, nc1 * 20 + 64))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_tilemeta, (size_t)(F / 32 + n_queries + 1) * 32))) return rc;
   if ((rc = tir_reserve(ctx, ctx->d_counter, 256))) return rc;
+  if (ctx->db) { // the coefs == 2 item list of the larger index
+    const uint64_t items = (uint64_t)std::max(ctx->db->main.n_blocks, ctx->db->tail.n_blocks) * n_queries;
+    if (items * 8 <= (1ull << 30) && (rc = tir_reserve(ctx, ctx->d_items, (size_t)items * 8 + 8))) return rc;
+  }
   for (int k = 0; k < tir_ctx::kStageSlots; k++)
     if ((rc = tir_reserve_host(ctx, ctx->h_stage[k], nc1 * 20 + 64))) return rc;
   return TIR_OK;
@@ -1331,7 +1635,7 @@ int tir_db_ensure_index_public(tir_ctx *ctx) {
 
 // the match chain of one index: qprep -> pattern_block -> resolve -> per-query kernel (PDL-chained), hits to d_hits
 static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, const double *d_y, const float *d_coef,
-                     const uint64_t *frame_off, uint32_t n_queries, uint64_t F, const TirMatchParams &mp, bool wide,
+                     const uint64_t *frame_off, uint32_t n_queries, uint64_t F, const TirMatchParams &mp, bool wide, bool short2,
                      tir_hit *d_hits, const TirP2PArgs &x) {
   cudaStream_t st = ctx->stream;
   int rc;
@@ -1347,6 +1651,11 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   if ((rc = tir_stage_acquire(ctx, ((size_t)n_queries + 1) * 8, &hp, &slot))) return rc;
   std::memcpy(hp, frame_off, ((size_t)n_queries + 1) * 8);
   const bool indexed = idx.n_blocks && idx.n_indexed;
+  // coefs == 2 and only short queries: tir_match2_kernel runs ahead of the frame-major kernel and leaves it a list of the
+  // items it could not finish (8 B per (index block, query))
+  const uint64_t items_all = (uint64_t)idx.n_blocks * n_queries;
+  const bool fast2 = indexed && short2 && mp.coefs >= 2 && items_all * 8 <= (1ull << 30);
+  if (fast2 && (rc = tir_reserve(ctx, ctx->d_items, (size_t)items_all * 8))) return rc;
   if (indexed && !ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
     TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
     TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));
@@ -1393,11 +1702,21 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     // ... per-query path (returns at once otherwise): persistent over (block, query) items
     const uint64_t items = (uint64_t)idx.n_blocks * n_queries;
     const uint32_t ggrid = (uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * 3);
+    uint64_t *d_items = fast2 ? (uint64_t *)ctx->d_items.p : nullptr;
+    static const int m2_ctas_per_sm = [] { // every warp of the grid resident at once: the units are cut for that
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tir_match2_kernel, TIR_M2_THREADS, 0) != cudaSuccess || n < 1) n = 4;
+      return n;
+    }();
+    if (fast2)
+      TIR_CUDA(ctx, tir_launch_pdl(tir_match2_kernel, dim3((uint32_t)std::min<uint64_t>(items, (uint64_t)ctx->num_sms * m2_ctas_per_sm)), dim3(TIR_M2_THREADS), st,
+                                   k1, uid, k2, bst, (const TirWindow *)d_win, (const uint32_t *)d_nw, d_foff, d_best, idx.n_blocks, n_queries,
+                                   d_batch, dead, d_items));
     auto gen = coefs >= 2 ? (wide ? tir_match_kernel<2, true> : tir_match_kernel<2, false>)
                           : (wide ? tir_match_kernel<1, true> : tir_match_kernel<1, false>);
     TIR_CUDA(ctx, tir_launch_pdl_smem(gen, dim3(ggrid), dim3(TIR_MATCH_THREADS), (size_t)TIR_GEN_SMEM_OF(wide), st, k1, uid, k2, bst,
                                       (const TirWindow *)d_win, (const uint32_t *)d_nw, d_foff, d_best, idx.n_blocks, n_queries, d_batch,
-                                      order, uuids, d_hits, x, dead));
+                                      order, uuids, d_hits, x, dead, (const uint64_t *)d_items));
     if (ctx->profiling && !in_graph) {
       TIR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
       ctx->ev_valid[1] = true;
@@ -1413,7 +1732,8 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     struct Key {
       const void *scratch, *hp, *d_y, *d_coef, *d_hits, *k1, *uid, *k2, *bst, *order, *uuids, *dead;
       uint64_t F;
-      uint32_t n_queries, n_blocks, num_sms, wide;
+      uint32_t n_queries, n_blocks, num_sms, wide, fast2;
+      const void *items;
       TirMatchParams mp; // (key comparison only: same bytes as the argument)
     } key;
     static_assert(sizeof(Key) <= sizeof(TirDb::ChainGraph::key), "graph key storage");
@@ -1421,7 +1741,7 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     key.scratch = scratch.p, key.hp = hp, key.d_y = d_y, key.d_coef = d_coef, key.d_hits = d_hits;
     key.k1 = idx.key1.p, key.uid = idx.uid.p, key.k2 = idx.key2.p, key.bst = idx.block_start.p, key.order = idx.order.p;
     key.uuids = (const uint8_t *)db->uuids.p + (size_t)idx.a0 * 16, key.dead = idx.n_dead ? idx.dead.p : nullptr;
-    key.F = F, key.n_queries = n_queries, key.n_blocks = idx.n_blocks, key.num_sms = (uint32_t)ctx->num_sms, key.wide = wide;
+    key.F = F, key.n_queries = n_queries, key.n_blocks = idx.n_blocks, key.num_sms = (uint32_t)ctx->num_sms, key.wide = wide, key.fast2 = fast2, key.items = fast2 ? ctx->d_items.p : nullptr;
     std::memcpy(&key.mp, &mp, sizeof mp);
     TirDb::ChainGraph &g = db->cg[slot];
     const bool cached = g.exec && std::memcmp(g.key, &key, sizeof key) == 0;
@@ -1456,13 +1776,13 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
         ctx->ev_valid[1] = true;
       }
       if ((rc = tir_stage_release(ctx, slot))) return rc;
-      ctx->launches += 4, db->n_graph_launches++;
+      ctx->launches += fast2 ? 5 : 4, db->n_graph_launches++;
       return TIR_OK;
     }
   }
   if ((rc = enqueue())) return rc;
   if ((rc = tir_stage_release(ctx, slot))) return rc;
-  ctx->launches += indexed ? 4 : 2;
+  ctx->launches += indexed ? (fast2 ? 5 : 4) : 2;
   if (!indexed) {
     if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x))) return rc; // an empty shard still answers
     if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x, n_queries))) return rc;
@@ -1485,11 +1805,14 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   const uint64_t F = frame_off[n_queries] - frame_off[0];
   if (frame_off[0] != 0) return tir_fail(ctx, TIR_ERR_ARG, "frame_off[0] must be 0");
   bool wide = false; // a query of more than 65 535 frames: the per-query kernel counts in u32
+  uint64_t max_nf = 0;
   for (uint32_t q = 0; q < n_queries; q++) {
     if (frame_off[q + 1] < frame_off[q] || frame_off[q + 1] - frame_off[q] > 0x7fffffffull)
       return tir_fail(ctx, TIR_ERR_ARG, "frame_off must be non-decreasing (and a query shorter than 2^31 frames)");
     wide |= frame_off[q + 1] - frame_off[q] > 65535;
+    max_nf = std::max<uint64_t>(max_nf, frame_off[q + 1] - frame_off[q]);
   }
+  const bool short2 = max_nf <= 96; // coefs == 2: every query fits the row-major kernel (TIR_M2_MAX_FRAMES)
   TirMatchParams mp;
   std::memset(&mp, 0, sizeof mp); // (its bytes are part of the key of the cached chain graph: no stray padding)
   mp.coefs = coefs;
@@ -1498,14 +1821,14 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   mp.thr_lo = mp.use_lo ? 10 * log10((double)ign_lo) : 0.0; // :294, :300
   mp.thr_hi = mp.use_hi ? 10 * log10((double)ign_hi) : 0.0;
   const bool have_tail = db->tail.n_blocks && db->tail.n_indexed, have_main = db->main.n_blocks && db->main.n_indexed;
-  if (!have_tail) return run_chain(ctx, db, db->main, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, d_hits, x);
-  if (!have_main) return run_chain(ctx, db, db->tail, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, d_hits, x);
+  if (!have_tail) return run_chain(ctx, db, db->main, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, short2, d_hits, x);
+  if (!have_main) return run_chain(ctx, db, db->tail, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, short2, d_hits, x);
   // audios added since the last full build live in the small tail index: both chains run, the two winners of
   // every query are folded like the winners of two shards (greatest count, ties -> greatest uuid)
   if ((rc = tir_reserve(ctx, ctx->d_hits2, (size_t)2 * n_queries * sizeof(tir_hit)))) return rc;
   tir_hit *h2 = (tir_hit *)ctx->d_hits2.p;
-  if ((rc = run_chain(ctx, db, db->main, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, h2, none))) return rc;
-  if ((rc = run_chain(ctx, db, db->tail, ctx->d_qmeta2, d_y, d_coef, frame_off, n_queries, F, mp, wide, h2 + n_queries, none))) return rc;
+  if ((rc = run_chain(ctx, db, db->main, ctx->d_qmeta, d_y, d_coef, frame_off, n_queries, F, mp, wide, short2, h2, none))) return rc;
+  if ((rc = run_chain(ctx, db, db->tail, ctx->d_qmeta2, d_y, d_coef, frame_off, n_queries, F, mp, wide, short2, h2 + n_queries, none))) return rc;
   tir_merge_hits_kernel<<<(n_queries + 127) / 128, 128, 0, ctx->stream>>>(h2, 2, n_queries, d_hits);
   TIR_CUDA(ctx, cudaGetLastError());
   ctx->launches++;

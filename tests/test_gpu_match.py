@@ -540,3 +540,39 @@ def test_churn_compacts_the_table_and_still_follows_sqlite(gpu_ctx, oracle):
     with pytest.raises(capi.TirError):
         gpu_ctx.db_remove(capi.uuid_to_bytes(db[0][0]))                 # compacted away long ago: unknown
     assert gpu_ctx.db_stats() == (150 + 40 - 4, sq.count_rows())
+
+
+def test_coefs2_short_queries_take_the_row_major_kernel(gpu_ctx, oracle):
+    """coefs = 2 (src/fp_handler.c:318-351: a window on max2 as well, per frame).  A batch whose queries all have at most
+    96 windows runs tir_match2_kernel (row-major over the frames of one max1 window, candidates united per uuid); the same
+    queries batched with one long recording run the frame-major kernel; both must give SQLite's answer.  Covered: several
+    rows of one audio inside one frame's window (one vote per frame and uuid), frames whose max2 falls to freq_ignore (no
+    predicate on max2), NULL max2 rows, a tolerance wide enough to overflow the candidate list (the item is handed to
+    the frame-major kernel), more than 32 distinct max1 windows in one query (likewise)."""
+    rng = np.random.default_rng(2024)
+    db = synth_db.make_db(3000, 5, 40, seed=77, near_int_frac=0.6, null_frac=0.02)
+    twin = np.array([[17.0003, 5.0], [17.0004, 5.0002], [16.9998, 5.0001], [17.0001, 4.9999], [18.0002, 7.5], [18.0003, 7.5004]])
+    db.append((synth.uuid_for(88_000_001), twin))
+    db.append((synth.uuid_for(88_000_002), np.stack([np.arange(-10, 30) + 0.0002, np.full(40, 6.0)], axis=1)))   # a row next to 40 integers
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    gpu_ctx.db_load(*synth_db.db_arrays(db))
+    ys = [db[int(i)][1][:96].copy() for i in rng.integers(0, 3000, 6)]
+    ys += [synth_db.random_y(rng, int(n), near_int_frac=0.7, null_frac=0.05 if n % 2 else 0.0) for n in (1, 2, 31, 32, 33, 64, 95, 96)]
+    ys.append(np.array([[17.4, 5.0001], [17.9, 5.0], [17.2, 4.99995], [18.1, 7.5002], [18.7, 7.5001], [16.0, 5.0]]))      # the twin audio: rows share frames
+    ys.append(np.stack([np.arange(-10, 30) + 0.5, np.full(40, 6.0)], axis=1))                                          # 40 max1 windows: not for the row-major kernel
+    ys.append(np.zeros((0, 2)))
+    long_q = synth_db.random_y(rng, 200, near_int_frac=0.7)
+    foff = np.zeros(len(ys) + 1, np.uint64); foff[1:] = np.cumsum([y.shape[0] for y in ys])
+    foff_l = np.concatenate([foff, [foff[-1] + long_q.shape[0]]]).astype(np.uint64)
+    for tol, lo, hi in ((0.001, -1, -1), (0.01, -1, -1), (0.5, -1, -1), (2.0, 30, 60), (0.002, 50, -1), (0.0, -1, -1)):
+        short = gpu_ctx.match(np.concatenate(ys), foff, 2, tol, lo, hi)
+        mixed = gpu_ctx.match(np.concatenate(ys + [long_q]), foff_l, 2, tol, lo, hi)
+        for qi, y in enumerate(ys):
+            assert gpu_result(short[qi]) == gpu_result(mixed[qi]), (tol, lo, hi, qi)
+            if y.shape[0] and (qi % 2 == 0 or qi >= 14):
+                assert gpu_result(short[qi]) == sql_result(sq.search(y, 2, tol, lo, hi, has_y=np.isfinite(y))), (tol, lo, hi, qi)
+        assert gpu_result(mixed[len(ys)]) == sql_result(sq.search(long_q, 2, tol, lo, hi, has_y=np.isfinite(long_q))), (tol, lo, hi)
+    h = gpu_ctx.match(ys[14], None, 2, 0.001)[0]
+    assert gpu_result(h) == (synth.uuid_for(88_000_001), 5, 6)           # five frames see the twin audio, once each

@@ -7,6 +7,8 @@ import numpy as np, torch
 from asterisk_tiresias_b200 import capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 Q = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+COEFS = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+TOL = float(sys.argv[4]) if len(sys.argv) > 4 else 0.001
 F = 94
 dev = "cuda"
 st = torch.cuda.Stream()
@@ -29,17 +31,17 @@ coef = torch.stack([torch.pow(10.0, qv / 10.0).float(), torch.pow(10.0, q2 / 10.
 foff = np.arange(Q + 1, dtype=np.uint64) * F
 d_hits = torch.zeros(Q * 24, dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
-steps = 3 if os.environ.get("TIR_NCU") else 200
+steps = 3 if os.environ.get("TIR_NCU") else (200 if COEFS == 1 else 10)
 with torch.cuda.stream(st):
     for _ in range(3):
-        ctx.match_dev(coef.data_ptr(), foff, d_hits.data_ptr(), 1, 0.001)
+        ctx.match_dev(coef.data_ptr(), foff, d_hits.data_ptr(), COEFS, TOL)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for _ in range(steps):
-        ctx.match_dev(coef.data_ptr(), foff, d_hits.data_ptr(), 1, 0.001)
+        ctx.match_dev(coef.data_ptr(), foff, d_hits.data_ptr(), COEFS, TOL)
     e1.record(st)
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 hits = d_hits.cpu().numpy().view(capi.HIT_DTYPE)
-print(f"n={n} Q={Q}: {ms * 1e3:.1f} us per batch, {Q / ms * 1e3 / 1e6:.2f} M queries/s, found {(hits['match_count'] > 0).sum()}, "
+print(f"n={n} Q={Q} coefs={COEFS} tol={TOL}: {ms * 1e3:.1f} us per batch, {Q / ms * 1e3 / 1e6:.2f} M queries/s, found {(hits['match_count'] > 0).sum()}, "
       f"exact copies found with 94 votes: {(hits['match_count'][: Q // 10] == 94).sum()}/{Q // 10}")
