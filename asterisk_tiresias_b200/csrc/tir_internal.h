@@ -107,6 +107,10 @@ struct TirP2PArgs {
   uint32_t *done; // CTA counter (left at 0)
   unsigned char *local = nullptr; // this rank's own region
   tir_hit *final_out = nullptr;   // [n_queries] global winners
+  // When set, the kernels read the batch number from this device word instead of `epoch`: the match chain copies it in
+  // together with the query offsets, so the kernels' arguments do not change from batch to batch and a steady caller's
+  // exchange chain replays as a CUDA graph too.
+  const uint32_t *epoch_dev = nullptr;
 };
 #define TIR_P2P_MAX_RANKS 16
 #define TIR_P2P_HDR 256 // bytes of flags before the two gather buffers of a region:

@@ -850,7 +850,7 @@ __device__ __forceinline__ void tir_write_hit(unsigned long long b, const uint32
   }
   hits[q] = v.h;
   if (x.peer) {
-    const size_t off = (size_t)TIR_P2P_HDR + ((size_t)(x.epoch & 1u) * x.world + x.rank) * x.max_queries * sizeof(tir_hit) + (size_t)q * sizeof(tir_hit);
+    const size_t off = (size_t)TIR_P2P_HDR + ((size_t)(tir_p2p_epoch(x) & 1u) * x.world + x.rank) * x.max_queries * sizeof(tir_hit) + (size_t)q * sizeof(tir_hit);
     for (int p = 0; p < x.world; p++) {
       unsigned long long *dst = reinterpret_cast<unsigned long long *>(x.peer[p] + off);
       dst[0] = v.w[0], dst[1] = v.w[1], dst[2] = v.w[2]; // NVLink peer stores
@@ -861,7 +861,7 @@ __device__ __forceinline__ void tir_write_hit(unsigned long long b, const uint32
 __device__ __forceinline__ void tir_exchange_release(const TirP2PArgs &x) {
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < (unsigned)x.world) tir_st_release_sys(reinterpret_cast<uint32_t *>(x.peer[threadIdx.x]) + x.rank, x.epoch);
+  if (threadIdx.x < (unsigned)x.world) tir_st_release_sys(reinterpret_cast<uint32_t *>(x.peer[threadIdx.x]) + x.rank, tir_p2p_epoch(x));
 }
 
 // One CTA per index block, everything in shared memory: (1) the 2K bound searches of the K distinct
@@ -1147,7 +1147,8 @@ __global__ void __launch_bounds__(TIR_RESOLVE_THREADS)
   if (threadIdx.x == 0) *x.done = 0;
   if (*reinterpret_cast<volatile uint32_t *>(&batch->overflow)) return;
   tir_exchange_release(x);
-  tir_p2p_fused_merge(x, n_queries); // this CTA also folds the ranks' candidates once their flags arrive
+  // (the ranks' candidates are folded by the whole grid of the kernel that follows in the chain -- tir_match_kernel, idle
+  // on this path: one CTA folding 1 000 queries x 8 ranks alone was the tail of the exchange)
 }
 
 // ---- per-query path -------------------------------------------------------------------------------
@@ -1185,7 +1186,12 @@ __global__ void __launch_bounds__(TIR_MATCH_THREADS)
                      tir_hit *__restrict__ hits, const TirP2PArgs x, const uint8_t *__restrict__ dead,
                      const uint64_t *__restrict__ item_list) {
   TIR_PDL_PROLOGUE();
-  if (!(batch->use_general || batch->overflow)) return;
+  if (!(batch->use_general || batch->overflow)) {
+    // the shared-window path produced (and released) this rank's winners: every CTA of this otherwise idle grid waits
+    // for the ranks' flags and folds its share of the queries
+    if (x.peer) tir_p2p_fused_merge(x, n_queries, blockIdx.x * TIR_MATCH_THREADS + threadIdx.x, gridDim.x * TIR_MATCH_THREADS);
+    return;
+  }
   extern __shared__ __align__(16) uint32_t s_cnt[]; // u16 vote counters, two per word (WIDE: u32); then the warps' bitmaps
   constexpr int CNT_WORDS = WIDE ? TIR_BLOCK_UUIDS : TIR_BLOCK_UUIDS / 2;
   constexpr int TIR_GEN_SMEM = TIR_GEN_SMEM_OF(WIDE);
@@ -1587,7 +1593,7 @@ struct TirMatchScratch {
 };
 static TirMatchScratch match_scratch_layout(uint32_t n_queries, uint64_t F) {
   TirMatchScratch L;
-  L.o_foff = 0, L.o_nw = L.o_foff + ((size_t)n_queries + 1) * 8, L.o_best = (L.o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
+  L.o_foff = 0, L.o_nw = L.o_foff + ((size_t)n_queries + 2) * 8 /* offsets, then the exchange's batch number */, L.o_best = (L.o_nw + (size_t)n_queries * 4 + 15) & ~(size_t)15;
   L.o_batch = (L.o_best + (size_t)n_queries * 8 + 15) & ~(size_t)15;
   L.o_maxr = (L.o_batch + sizeof(TirBatch) + 15) & ~(size_t)15;
   L.o_gkeys = L.o_maxr + ((size_t)4 << TIR_SHARED_DIRECT), L.o_gvals = L.o_gkeys + (size_t)8 * TIR_PAT_HASH_GLOBAL;
@@ -1636,7 +1642,7 @@ int tir_db_ensure_index_public(tir_ctx *ctx) {
 // the match chain of one index: qprep -> pattern_block -> resolve -> per-query kernel (PDL-chained), hits to d_hits
 static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, const double *d_y, const float *d_coef,
                      const uint64_t *frame_off, uint32_t n_queries, uint64_t F, const TirMatchParams &mp, bool wide, bool short2,
-                     tir_hit *d_hits, const TirP2PArgs &x) {
+                     tir_hit *d_hits, const TirP2PArgs &x_in) {
   cudaStream_t st = ctx->stream;
   int rc;
   const int coefs = mp.coefs;
@@ -1648,8 +1654,14 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   unsigned char *d = (unsigned char *)scratch.p;
   void *hp;
   int slot;
-  if ((rc = tir_stage_acquire(ctx, ((size_t)n_queries + 1) * 8, &hp, &slot))) return rc;
+  if ((rc = tir_stage_acquire(ctx, ((size_t)n_queries + 2) * 8, &hp, &slot))) return rc;
   std::memcpy(hp, frame_off, ((size_t)n_queries + 1) * 8);
+  // the exchange's batch number travels with the offsets (one copy): the kernels read it from the device, their
+  // arguments are the same for every batch
+  const uint64_t epoch_word = x_in.epoch;
+  std::memcpy((unsigned char *)hp + ((size_t)n_queries + 1) * 8, &epoch_word, 8);
+  TirP2PArgs x = x_in;
+  if (x.peer) x.epoch = 0, x.epoch_dev = (const uint32_t *)(d + o_foff + ((size_t)n_queries + 1) * 8);
   const bool indexed = idx.n_blocks && idx.n_indexed;
   // coefs == 2 and only short queries: tir_match2_kernel runs ahead of the frame-major kernel and leaves it a list of the
   // items it could not finish (8 B per (index block, query))
@@ -1666,7 +1678,7 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   bool in_graph = false; // (the profiling events cannot be recorded inside a capture)
   // everything the chain enqueues, as one function: run directly, or captured once into a graph and replayed
   auto enqueue = [&]() -> int {
-  TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, hp, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+  TIR_CUDA(ctx, cudaMemcpyAsync(d + o_foff, hp, ((size_t)n_queries + 2) * 8, cudaMemcpyHostToDevice, st));
   TIR_CUDA(ctx, cudaMemsetAsync(d + o_best, 0, o_plist - o_best, st)); // best, batch, max_rank1, pattern hash table
   const uint64_t *d_foff = (const uint64_t *)(d + o_foff);
   uint32_t *d_nw = (uint32_t *)(d + o_nw);
@@ -1727,13 +1739,14 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   return TIR_OK;
   }; // enqueue
 
-  // ---- a steady caller: replay the cached graph of this staging slot (no exchange: its epoch changes every batch)
-  if (indexed && !x.peer && !db->graph_off) {
+  // ---- a steady caller: replay the cached graph of this staging slot (with or without an exchange)
+  if (indexed && !db->graph_off) {
     struct Key {
       const void *scratch, *hp, *d_y, *d_coef, *d_hits, *k1, *uid, *k2, *bst, *order, *uuids, *dead;
       uint64_t F;
       uint32_t n_queries, n_blocks, num_sms, wide, fast2;
-      const void *items;
+      const void *items, *x_peer, *x_local, *x_final, *x_done;
+      uint32_t x_rank, x_world, x_maxq, pad;
       TirMatchParams mp; // (key comparison only: same bytes as the argument)
     } key;
     static_assert(sizeof(Key) <= sizeof(TirDb::ChainGraph::key), "graph key storage");
@@ -1742,6 +1755,8 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
     key.k1 = idx.key1.p, key.uid = idx.uid.p, key.k2 = idx.key2.p, key.bst = idx.block_start.p, key.order = idx.order.p;
     key.uuids = (const uint8_t *)db->uuids.p + (size_t)idx.a0 * 16, key.dead = idx.n_dead ? idx.dead.p : nullptr;
     key.F = F, key.n_queries = n_queries, key.n_blocks = idx.n_blocks, key.num_sms = (uint32_t)ctx->num_sms, key.wide = wide, key.fast2 = fast2, key.items = fast2 ? ctx->d_items.p : nullptr;
+    key.x_peer = x.peer, key.x_local = x.local, key.x_final = x.final_out, key.x_done = x.done;
+    key.x_rank = (uint32_t)x.rank, key.x_world = (uint32_t)x.world, key.x_maxq = x.max_queries;
     std::memcpy(&key.mp, &mp, sizeof mp);
     TirDb::ChainGraph &g = db->cg[slot];
     const bool cached = g.exec && std::memcmp(g.key, &key, sizeof key) == 0;
@@ -1784,8 +1799,8 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   if ((rc = tir_stage_release(ctx, slot))) return rc;
   ctx->launches += indexed ? (fast2 ? 5 : 4) : 2;
   if (!indexed) {
-    if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x))) return rc; // an empty shard still answers
-    if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x, n_queries))) return rc;
+    if (x.peer && (rc = tir_p2p_publish_launch(ctx, d_hits, n_queries, x_in))) return rc; // an empty shard still answers
+    if (x.peer && x.final_out && (rc = tir_p2p_merge_launch(ctx, x_in, n_queries))) return rc;
   }
   TIR_CUDA(ctx, cudaGetLastError());
   return TIR_OK;

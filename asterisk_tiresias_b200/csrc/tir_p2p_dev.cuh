@@ -75,10 +75,17 @@ __device__ __forceinline__ void tir_p2p_poison(tir_hit *__restrict__ out, uint32
 
 // the fused tail of the kernels that produce the winners: (all threads of the LAST CTA, after
 // tir_exchange_release) wait for every rank's flag, fold into x.final_out
-__device__ __forceinline__ void tir_p2p_fused_merge(const TirP2PArgs &x, uint32_t n_queries) {
+__device__ __forceinline__ uint32_t tir_p2p_epoch(const TirP2PArgs &x) { return x.epoch_dev ? *x.epoch_dev : x.epoch; }
+// (`first` / `stride` in queries: one CTA folds everything, or every CTA of a grid its share -- each CTA waits for
+// the flags itself)
+__device__ __forceinline__ void tir_p2p_fused_merge(const TirP2PArgs &x, uint32_t n_queries, uint32_t first, uint32_t stride) {
   if (!x.final_out) return;
-  if (tir_p2p_wait_flags(reinterpret_cast<uint32_t *>(x.local), 0, x.world, x.epoch))
-    tir_p2p_fold(x.local, x.world, x.max_queries, n_queries, x.epoch, x.final_out, threadIdx.x, blockDim.x);
+  const uint32_t epoch = tir_p2p_epoch(x);
+  if (tir_p2p_wait_flags(reinterpret_cast<uint32_t *>(x.local), 0, x.world, epoch))
+    tir_p2p_fold(x.local, x.world, x.max_queries, n_queries, epoch, x.final_out, first, stride);
   else
-    tir_p2p_poison(x.final_out, n_queries, threadIdx.x, blockDim.x);
+    tir_p2p_poison(x.final_out, n_queries, first, stride);
+}
+__device__ __forceinline__ void tir_p2p_fused_merge(const TirP2PArgs &x, uint32_t n_queries) {
+  tir_p2p_fused_merge(x, n_queries, threadIdx.x, blockDim.x);
 }
