@@ -111,6 +111,7 @@ struct TirP2PArgs {
   // together with the query offsets, so the kernels' arguments do not change from batch to batch and a steady caller's
   // exchange chain replays as a CUDA graph too.
   const uint32_t *epoch_dev = nullptr;
+  bool may_alloc = false; // the caller drives this rank alone (one process per GPU): scratch may grow inside the call
 };
 #define TIR_P2P_MAX_RANKS 16
 #define TIR_P2P_HDR 256 // bytes of flags before the two gather buffers of a region:

@@ -1666,7 +1666,10 @@ static int run_chain(tir_ctx *ctx, TirDb *db, TirIndex &idx, DevBuf &scratch, co
   // coefs == 2 and only short queries: tir_match2_kernel runs ahead of the frame-major kernel and leaves it a list of the
   // items it could not finish (8 B per (index block, query))
   const uint64_t items_all = (uint64_t)idx.n_blocks * n_queries;
-  const bool fast2 = indexed && short2 && mp.coefs >= 2 && items_all * 8 <= (1ull << 30);
+  // (inside an exchange nothing may be allocated or freed between the ranks' enqueues -- tir_search_reserve: the list
+  // is used there only if it was sized beforehand)
+  const bool fast2 = indexed && short2 && mp.coefs >= 2 && items_all * 8 <= (1ull << 30) &&
+                     (!x_in.peer || x_in.may_alloc || ctx->d_items.cap >= (size_t)items_all * 8);
   if (fast2 && (rc = tir_reserve(ctx, ctx->d_items, (size_t)items_all * 8))) return rc;
   if (indexed && !ctx->match_smem_attr_set) { // per context: the attribute belongs to the device the context is on
     TIR_CUDA(ctx, cudaFuncSetAttribute(tir_match_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TIR_GEN_SMEM_OF(false)));

@@ -219,6 +219,7 @@ int tir_p2p_match_dev(tir_p2p *p, const float *d_coef, const uint64_t *frame_off
   if (n_queries == 0) return TIR_OK;
   TirP2PArgs a{p->d_peer, p->rank, p->world, p->max_queries, epoch, p->d_done};
   a.local = p->local, a.final_out = d_final; // the kernel that produces the winners also folds the ranks' candidates
+  a.may_alloc = true; // (SPMD entry point: this rank's host thread enqueues nothing for other ranks)
   const int rc = tir_match_dev_exchange(ctx, d_coef, frame_off, n_queries, coefs, tolerance, freq_ignore_low, freq_ignore_high,
                                         p->d_local_hits, &a);
   if (rc != TIR_OK) p2p_publish_nothing(p, n_queries, a);
@@ -231,8 +232,8 @@ int tir_p2p_reserve(tir_p2p *p, uint64_t max_local_samples) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   TIR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
   int rc;
-  if ((rc = tir_search_reserve(ctx, p->max_queries, p->max_frames, max_local_samples))) return rc;
-  return tir_db_ensure_index(ctx);
+  if ((rc = tir_db_ensure_index(ctx))) return rc; // (first: the reserve sizes the coefs == 2 item list from the index's blocks)
+  return tir_search_reserve(ctx, p->max_queries, p->max_frames, max_local_samples);
 }
 
 // SPMD sharded search (header: tir_p2p_search).  Rank r brings the clips [first_query, first_query + n_local)
