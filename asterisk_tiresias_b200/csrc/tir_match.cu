@@ -1451,28 +1451,33 @@ __global__ void __launch_bounds__(TIR_M2_THREADS, 8)
         const int32_t fbase = filt ? S.fbase[g] : 0;
         const uint32_t fspan = filt ? S.fspan[g] : 0, fshift = filt ? S.fshift[g] : 0;
         const uint32_t *fbm = S.fbm[filt ? g : 0];
-        for (uint64_t rr = r0; rr < r1; rr += UF * 32) { // (warp-uniform trip count: the body votes)
+        const uint32_t nrows = (uint32_t)(r1 - r0); // (a block holds fewer than 2^32 rows)
+        const uint16_t *pu = uid + r0 + lane;
+        const int32_t *pk = key2 + r0 + lane;
+        for (uint32_t rr = 0; rr < nrows; rr += UF * 32) { // (warp-uniform trip count: the body votes)
           uint32_t u[UF];
           int32_t v[UF];
-          bool ok[UF];
+          uint32_t okm = 0xffu; // slots of this lane that hold a row
+          if (rr + UF * 32 <= nrows) { // a full step: no bounds checks
 #pragma unroll
-          for (int e = 0; e < UF; e++) {
-            const uint64_t re = rr + (uint32_t)(32 * e + lane);
-            ok[e] = re < r1;
-            u[e] = 0, v[e] = 0;
-            if (ok[e]) u[e] = (uint32_t)__ldg(uid + re), v[e] = __ldg(key2 + re);
+            for (int e = 0; e < UF; e++) u[e] = (uint32_t)__ldg(pu + rr + 32 * e), v[e] = __ldg(pk + rr + 32 * e);
+          } else {
+            okm = 0;
+#pragma unroll
+            for (int e = 0; e < UF; e++) {
+              const bool ok = rr + 32 * e + lane < nrows;
+              u[e] = 0, v[e] = 0;
+              if (ok) u[e] = (uint32_t)__ldg(pu + rr + 32 * e), v[e] = __ldg(pk + rr + 32 * e), okm |= 1u << e;
+            }
           }
           uint32_t nq = 0;
 #pragma unroll
           for (int e = 0; e < UF; e++) {
-            bool pass = ok[e];
-            if (filt && pass) { // can this max2 match any frame of the group?
-              const uint32_t d = (uint32_t)v[e] - (uint32_t)fbase;
-              pass = v[e] >= fbase && d <= fspan;
-              if (pass) {
-                const uint32_t f = d >> fshift;
-                pass = ((fbm[f >> 5] >> (f & 31)) & 1u) != 0;
-              }
+            bool pass = (okm >> e) & 1u;
+            if (filt) { // can this max2 match any frame of the group?  (only a filter: a value below fbase may wrap into
+              const uint32_t d = (uint32_t)v[e] - (uint32_t)fbase; // the span and pass; the searches below decide)
+              const uint32_t f = min(d, fspan) >> fshift;
+              pass = pass && d <= fspan && ((fbm[f >> 5] >> (f & 31)) & 1u) != 0;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             if (pass) {
