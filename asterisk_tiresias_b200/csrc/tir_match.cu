@@ -486,6 +486,7 @@ static int db_refresh(tir_ctx *ctx, TirDb *db) {
 
 struct TirMatchParams {
   int coefs;
+  int force_general; // coefs == 2 and more frames than the window set could hold anyway: skip the set, per-query path
   double tol;
   int use_lo, use_hi;
   double thr_lo, thr_hi; // 10*log10(freq_ignore_*), computed on the host exactly like the reference
@@ -563,7 +564,8 @@ __device__ __forceinline__ unsigned long long tir_window_key(const TirWindow &w)
   k ^= (m >> 29);
   return k ? k : 1ull;
 }
-__device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w, bool &claimed) {
+__device__ __forceinline__ uint32_t tir_wset_insert(TirBatch *batch, const TirWindow &w, bool &claimed, bool skip = false) {
+  if (skip) return 0;
   // (a set that overflowed stays overflowed: coefs == 2 batches would otherwise probe all its slots for every frame)
   if (*reinterpret_cast<volatile uint32_t *>(&batch->use_general)) return 0;
   const unsigned long long key = tir_window_key(w);
@@ -638,6 +640,9 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
   __shared__ TirWindow s_sort[TIR_QPREP_SORT_MAX];
   for (int i = threadIdx.x; i < TIR_QPREP_BINS; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x == 0) s_base = 0, s_nlead = 0;
+  // coefs == 2 with hundreds of frames: practically every frame is a window of its own, the set would overflow after
+  // every CTA had fought for its 128 slots (0.1 ms per 100 queries) -- the host says so up front
+  if (mp.force_general && threadIdx.x == 0) batch->use_general = 1u;
   __syncthreads();
   bool claimed = false;
   if (mp.coefs == 1) {
@@ -703,7 +708,7 @@ __global__ void __launch_bounds__(TIR_QPREP_THREADS)
       uint32_t pos = s_base + __popc(bal & ((1u << lane) - 1u));
       for (int k = 0; k < wid; k++) pos += s_warp[k];
       if (leader) {
-        w.pad = tir_wset_insert(batch, w, claimed); // slot in the batch's window set
+        w.pad = tir_wset_insert(batch, w, claimed, mp.force_general != 0); // slot in the batch's window set
         wq[pos] = w;
       }
       __syncthreads();
@@ -1839,6 +1844,7 @@ static int match_on_device(tir_ctx *ctx, const double *d_y, const float *d_coef,
   TirMatchParams mp;
   std::memset(&mp, 0, sizeof mp); // (its bytes are part of the key of the cached chain graph: no stray padding)
   mp.coefs = coefs;
+  mp.force_general = coefs >= 2 && F > 4 * TIR_WSET_SLOTS; // (only a choice of path: both give the same votes)
   mp.tol = tolerance < 0 ? 0.001 : tolerance; // DEF_SEARCH_TOLERANCE, src/fp_handler.c:252-256
   mp.use_lo = ign_lo > 0, mp.use_hi = ign_hi > 0;
   mp.thr_lo = mp.use_lo ? 10 * log10((double)ign_lo) : 0.0; // :294, :300
