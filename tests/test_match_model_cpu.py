@@ -59,3 +59,49 @@ def test_shared_window_evaluation_order_equals_sql(oracle):
             h = sq.search(y, 1, tol, has_y=np.isfinite(y))
             want = None if h is None else (h["uuid"], h["match_count"], h["frame_count"])
             assert g == want
+
+
+def row_major_model_coefs2(db, y, tol):
+    """The order of evaluation of tir_match2_kernel (coefs = 2, short queries), restated in numpy: the
+    query's windows sorted by (max1 window, lo2, hi2); inside one max1 group both max2 bounds ascend, so the frames a
+    stored row matches are a contiguous range found by two binary searches; a matching row is kept as (uuid, first frame,
+    last frame); the union of a uuid's ranges is its vote count (one vote per frame and uuid: GROUP BY audio_uuid)."""
+    q = lambda v: int(synth_db.quantize_y(np.array([v]))[0])
+    wins = []
+    for v1, v2 in np.where(np.isfinite(y), y, 0.0):
+        f = float(np.trunc(v1))
+        wins.append((q(f - tol), q(f + tol), max(q(v2 - tol), -(2**31) + 1), q(v2 + tol)))
+    wins.sort()
+    groups = {}                                                        # (lo1, hi1) -> positions in the sorted query
+    for pos, w in enumerate(wins):
+        groups.setdefault(w[:2], []).append(pos)
+    best = None
+    for u, ydb in db:
+        v = synth_db.quantize_y(ydb)
+        frames = set()
+        for (lo1, hi1), poss in groups.items():
+            lo2 = np.array([wins[p][2] for p in poss]); hi2 = np.array([wins[p][3] for p in poss])
+            assert (np.diff(lo2) >= 0).all() and (np.diff(hi2) >= 0).all()      # what the binary searches rely on
+            for r in np.nonzero((v[:, 0] != -(2**31)) & (v[:, 0] >= lo1) & (v[:, 0] <= hi1))[0]:
+                a = int(np.searchsorted(hi2, v[r, 1], side="left"))             # first frame with hi2 >= max2
+                b = int(np.searchsorted(lo2, v[r, 1], side="right"))            # first frame with lo2 > max2
+                frames.update(poss[a:b])
+        if frames and (best is None or (len(frames), u) > best):
+            best = (len(frames), u)
+    return None if best is None else (best[1], best[0], y.shape[0])
+
+
+def test_row_major_coefs2_evaluation_order_equals_sql(oracle):
+    rng = np.random.default_rng(8)
+    db = synth_db.make_db(250, 3, 25, seed=21, near_int_frac=0.7, null_frac=0.04)
+    db.append((synth_db.uuid_for(9_100_001), np.array([[17.0003, 5.0], [17.0004, 5.0002], [16.9998, 5.0001], [18.0002, 7.5]])))  # rows sharing frames
+    sq = oracle.SqliteDB()
+    for u, y in db:
+        sq.add_audio(u, y)
+    queries = [synth_db.random_y(rng, int(rng.integers(1, 60)), near_int_frac=0.7) for _ in range(10)]
+    queries += [db[3][1].copy(), np.array([[17.4, 5.0001], [17.9, 5.0], [17.2, 4.99995], [18.1, 7.5002], [16.0, 5.0]])]
+    for tol in (0.001, 0.02, 0.6):
+        for y in queries:
+            h = sq.search(y, 2, tol, has_y=np.isfinite(y))
+            want = None if h is None else (h["uuid"], h["match_count"], h["frame_count"])
+            assert row_major_model_coefs2(db, y, tol) == want, tol
