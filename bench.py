@@ -788,8 +788,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = F * BYTES_PER_FRAME / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 529.6 * F,   # ncu dram__bytes_read+write per launch, scaled from the capture below (529.6 B/frame; round 1: 530.2)
-                "traffic_source": "profiles/r2_extract_ncu_full.txt (ncu --set full capture of the same kernel, round 2; not measured in this run)",
+                "traffic": 529.2 * F,   # ncu dram__bytes_read+write per launch, scaled from the capture below (529.2 B/frame; round 1: 530.2)
+                "traffic_source": "profiles/r2_extract_ncu_full_final.txt (ncu --set full capture of the same kernel, final tree of round 2; not measured in this run)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "tir_extract_kernel<512>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": F * BYTES_PER_FRAME,
                 "note": "issue/latency-bound SIMT kernel on packed f32x2 instructions (float32 FFT reproduced operation for operation; FP32-pipe floor of the DAG = 24.7% of the HBM peak); see DESIGN.md 2.3 and profiles/"}
