@@ -156,9 +156,25 @@ TIR_DEV float tir_s16hi(uint32_t w) { return (float)(int16_t)(w >> 16); }
 // z[n], n = 16*n1 + n2, is the complex point (x[2n], x[2n+1]) of the windowed, fvec_shift'ed frame:
 // sample index (2n + WIN/2) mod WIN, i.e. hop chunk f + 1 - (n1 >> 3), 32-bit word 16*(n1 & 7) + n2.
 // the four samples of unit (chunk, 8*(n1&7)+w) as (re lo, re hi, im lo, im hi) = (s0, s2, s1, s3)
+#if defined(__CUDACC__) && !defined(TIR_I2F_CONVERT)
+// s16 -> f32 without the conversion unit (I2F runs at a quarter of the ALU rate and its latency sat in front of every
+// window product): bias both halves of a word to unsigned (one XOR), splice each half under the exponent of 2^23 (one
+// PRMT), and take 2^23 + 2^15 off again with ONE packed subtraction for two samples -- all exact.
+#define TIR_S16_MAGIC 8421376.0f // 2^23 + 2^15
+TIR_DEV void tir_s16x2(uint32_t wa, uint32_t wb, TirP2 &lo, TirP2 &hi) { // (lo half of wa, lo half of wb), (hi, hi)
+  const uint32_t a = wa ^ 0x80008000u, b = wb ^ 0x80008000u;
+  const TirP2 k = tir_pbc(TIR_S16_MAGIC);
+  lo = tir_psub(tir_pmk(__uint_as_float(__byte_perm(a, 0x4B00u, 0x5410)), __uint_as_float(__byte_perm(b, 0x4B00u, 0x5410))), k);
+  hi = tir_psub(tir_pmk(__uint_as_float(__byte_perm(a, 0x4B00u, 0x5432)), __uint_as_float(__byte_perm(b, 0x4B00u, 0x5432))), k);
+}
+#else
+TIR_DEV void tir_s16x2(uint32_t wa, uint32_t wb, TirP2 &lo, TirP2 &hi) {
+  lo = tir_pmk(tir_s16lo(wa), tir_s16lo(wb)), hi = tir_pmk(tir_s16hi(wa), tir_s16hi(wb));
+}
+#endif
 TIR_DEV void tir_unit4(const uint2 *pcm, int idx, TirP2 &re, TirP2 &im) {
   const uint2 u = pcm[idx];
-  re = tir_pmk(tir_s16lo(u.x), tir_s16lo(u.y)), im = tir_pmk(tir_s16hi(u.x), tir_s16hi(u.y));
+  tir_s16x2(u.x, u.y, re, im);
 }
 TIR_DEV void tir_unit4(const float4 *pcm, int idx, TirP2 &re, TirP2 &im) {
   const float4 u = pcm[idx];
@@ -209,7 +225,7 @@ TIR_DEV void tir_pass1_512(SM &sm, const U *pcm, int w, int f, TirP2 nz) {
 TIR_DEV void tir_pair2(const uint2 *pcm, int idx, TirP2 &re, TirP2 &im) {
   const uint32_t *p = reinterpret_cast<const uint32_t *>(pcm) + idx;
   const uint32_t ue = p[0], uo = p[16];
-  re = tir_pmk(tir_s16lo(ue), tir_s16lo(uo)), im = tir_pmk(tir_s16hi(ue), tir_s16hi(uo));
+  tir_s16x2(ue, uo, re, im);
 }
 TIR_DEV void tir_pair2(const float4 *pcm, int idx, TirP2 &re, TirP2 &im) {
   const float2 *p = reinterpret_cast<const float2 *>(pcm) + idx;
