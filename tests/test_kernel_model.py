@@ -90,3 +90,14 @@ def test_quantiser_equals_printf(emul, oracle):
         assert emul.emul_quantize(float(v)) == oracle.quantize(float(v)), v
     assert emul.emul_quantize(float("nan")) == oracle.NULL_V
     assert emul.emul_quantize(float("-inf")) == oracle.NULL_V
+
+
+def test_s16_to_f32_without_the_conversion_unit_is_exact():
+    """tir_s16x2 (csrc/tir_extract_core.cuh): XOR 0x8000, splice the 16 bits under the exponent of 2^23 (PRMT), subtract
+    2^23 + 2^15 in float32 -- the same float as (float)(int16_t) for every one of the 65 536 samples."""
+    s = np.arange(-32768, 32768, dtype=np.int32)
+    biased = (s.astype(np.uint32) & 0xFFFF) ^ 0x8000                      # s + 32768 as an unsigned half word
+    spliced = (np.uint32(0x4B000000) | biased).view(np.float32)           # 2^23 + (s + 32768), exactly
+    assert np.array_equal(spliced.astype(np.float64), 8388608.0 + s + 32768.0)
+    got = (spliced - np.float32(8421376.0)).astype(np.float32)            # one float32 subtraction
+    assert np.array_equal(got, s.astype(np.float32)) and np.array_equal(got.view(np.uint32), s.astype(np.float32).view(np.uint32))
