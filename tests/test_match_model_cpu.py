@@ -105,3 +105,26 @@ def test_row_major_coefs2_evaluation_order_equals_sql(oracle):
             h = sq.search(y, 2, tol, has_y=np.isfinite(y))
             want = None if h is None else (h["uuid"], h["match_count"], h["frame_count"])
             assert row_major_model_coefs2(db, y, tol) == want, tol
+
+
+def _pat_hash(p):
+    """tir_pat_hash (csrc/tir_match.cu), restated"""
+    M = (1 << 64) - 1
+    p ^= p >> 33
+    p = (p * 0xff51afd7ed558ccd) & M
+    p ^= p >> 33
+    return ((p & 0xFFFFFFFF) ^ ((p >> 17) & 0xFFFFFFFF)) & 0xFFFFFFFF
+
+
+def test_pattern_hash_spreads_sparse_bit_sets():
+    """The patterns are one-, two- and three-bit sets over up to 64 windows.  The first hash (a 32-bit multiply, then the
+    LOW product bits) sent every pattern made of windows >= 17 to slot 0 of the 1 024-slot CTA table -- K = 32 took 219 us
+    per batch instead of 84.  The mixer must spread them: at most a handful of patterns per slot, and the old one shown
+    failing the same bound."""
+    pats = [1 << a for a in range(64)] + [(1 << a) | (1 << b) for a in range(64) for b in range(a)]       # 2 080 patterns
+    load = np.bincount([_pat_hash(p) & 1023 for p in pats], minlength=1024)
+    assert load.max() <= 10 and (load > 0).sum() >= 850, (load.max(), (load > 0).sum())
+    old = np.bincount([(((p & 0xFFFFFFFF) * 0x9e3779b1) & 0xFFFFFFFF) >> 7 & 1023 for p in pats if p < (1 << 32)], minlength=1024)
+    assert old.max() > 100                                               # the cluster the round-1 hash built at slot 0
+    g = np.bincount([_pat_hash(p) & 16383 for p in pats], minlength=16384)
+    assert g.max() <= 4
