@@ -128,3 +128,33 @@ def test_pattern_hash_spreads_sparse_bit_sets():
     assert old.max() > 100                                               # the cluster the round-1 hash built at slot 0
     g = np.bincount([_pat_hash(p) & 16383 for p in pats], minlength=16384)
     assert g.max() <= 4
+
+
+def _group_bound(key, lo, hi, target, upper, G):
+    """tir_group_bound (csrc/tir_match.cu), one group of G lanes, restated: (G+1)-ary search, then one step of G probes"""
+    levels = 0
+    while hi - lo > G:
+        step = (hi - lo + G) // (G + 1)
+        nb = 0
+        for sub in range(G):                                             # probes are monotone: the first nb are below
+            p = lo + (sub + 1) * step - 1
+            if p < hi and (key[p] <= target if upper else key[p] < target):
+                nb += 1
+        lo, hi = lo + nb * step, (min(hi, lo + (nb + 1) * step) if nb < G else hi)
+        levels += 1
+    nb = sum(1 for sub in range(G) if lo + sub < hi and (key[lo + sub] <= target if upper else key[lo + sub] < target))
+    return lo + nb, levels
+
+
+def test_lane_group_bound_search_equals_searchsorted():
+    rng = np.random.default_rng(12)
+    for n in (0, 1, 2, 31, 32, 33, 1000, 40_000):
+        key = np.sort(rng.integers(-50, 50, n) * 1000 + rng.integers(0, 3, n))       # many duplicates
+        for G in (2, 4, 8, 16, 32):
+            for t in list(rng.integers(-60_000, 60_000, 12)) + ([int(key[0]), int(key[-1]), int(key[n // 2])] if n else []):
+                lo, hi = (5, n - 3) if n > 20 else (0, n)                             # a block is a sub-range of the array
+                got_l, lv = _group_bound(key, lo, hi, t, False, G)
+                got_u, _ = _group_bound(key, lo, hi, t, True, G)
+                assert got_l == lo + int(np.searchsorted(key[lo:hi], t, side="left")), (n, G, t)
+                assert got_u == lo + int(np.searchsorted(key[lo:hi], t, side="right")), (n, G, t)
+                assert lv <= int(np.ceil(np.log(max(hi - lo, 2)) / np.log(G + 1))) + 1
